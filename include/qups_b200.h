@@ -1,0 +1,183 @@
+/* qups_b200.h — C ABI of libqups_b200.so: the B200-native (sm_100a) drop-in for
+ * the one data-parallel hot path of thorstone25/qups — delay-and-sum
+ * beamforming and the Green's-function point-scatterer simulator.
+ *
+ * Every entry point replaces one `parallel.gpu.CUDAKernel.feval` call site of
+ * the reference (MATLAB -> PTX-by-name).  Argument order and meaning follow the
+ * reference kernels' argument lists so that the MATLAB-side glue
+ * (mex/qups_b200_mex.cu, matlab/*.m) is a direct forward:
+ *
+ *   qups_das          <-  kern/das_spec.m:371-373   k.feval(yg,Pi,Pr,Pv,Nv,apod,cinv,[cstride,astride],x,[fs,fmod])
+ *                         src/bf.cu:144-172         DAS / DASf / DASh
+ *   qups_delays       <-  kern/das_spec.m:376-377   fun='delays'  (src/bf.cu:209-298 delays / delaysf)
+ *   qups_wsinterpd2   <-  kern/wsinterpd2.m:226-235 k.feval(y,w,x,t1,t2,sizes,iflags,strides,flag,extrapval,omega)
+ *                         src/interpd.cu:451-476    wsinterpd2 / wsinterpd2f / wsinterpd2h
+ *   qups_wsinterpd    <-  kern/wsinterpd.m:205-213  (src/interpd.cu:422-447)
+ *   qups_greens       <-  src/UltrasoundSystem.m:718 k.feval(x,ps,as,pn,pv,kn,sb,iblock,[t0k,t0x,fs,fsr,cinv,R0],[E,E],flag)
+ *                         src/greens.cu:88-122      greens / greensf / greensh
+ *   qups_modulate     <-  kern/das_spec.m:413-417   x .* exp(2i*pi*fmod.*t)  (CPU-branch convention, fused pre-pass)
+ *   qups_*_host       <-  the same calls for callers holding HOST arrays (plain MEX, no gpuArray)
+ *
+ * Conventions
+ *   - column-major (MATLAB) layouts, complex = interleaved (re,im)
+ *   - all array pointers are DEVICE pointers unless the function name ends in
+ *     _host; small descriptor arrays (strides, sizes) are HOST pointers
+ *   - buffers are caller-owned; the library never frees or retains them
+ *   - return value: 0 on success, negative qups_status on error;
+ *     qups_last_error() returns a thread-local message
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream); calls are
+ *     asynchronous w.r.t. the host unless stated
+ *   - re-entrant; no global mutable state besides the thread-local error text
+ *   - results follow the reference's CPU semantics (kern/das_spec.m CPU branch +
+ *     MATLAB interp1(…, extrapval=0)), not the edge quirks of src/interpd.cu
+ */
+#ifndef QUPS_B200_H
+#define QUPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QUPS_B200_VERSION 100
+
+#if defined(__GNUC__)
+#define QUPS_API __attribute__((visibility("default")))
+#else
+#define QUPS_API
+#endif
+
+typedef void *qups_stream_t; /* cudaStream_t */
+
+typedef enum {
+    QUPS_OK = 0,
+    QUPS_ERR_INVALID = -1,     /* bad argument / inconsistent sizes          */
+    QUPS_ERR_CUDA = -2,        /* CUDA runtime error (see qups_last_error)   */
+    QUPS_ERR_UNSUPPORTED = -3, /* valid request this build does not handle   */
+    QUPS_ERR_ALLOC = -4        /* device / host allocation failed            */
+} qups_status;
+
+typedef enum { QUPS_F32 = 0, QUPS_F16 = 1, QUPS_F64 = 2 } qups_dtype;
+/* interpolation ids == bits 0-2 of QUPS_BF_FLAG (kern/das_spec.m:198-203) */
+typedef enum { QUPS_NEAREST = 0, QUPS_LINEAR = 1, QUPS_CUBIC = 2, QUPS_LANCZOS3 = 3 } qups_interp;
+
+/* QUPS_BF_FLAG bits (kern/das_spec.m:199-213, src/bf.cu:127-137) */
+#define QUPS_FLAG_INTERP_MASK 7
+#define QUPS_FLAG_KEEP_RX 8
+#define QUPS_FLAG_KEEP_TX 16
+#define QUPS_FLAG_TRANSPOSE 32
+
+typedef enum { QUPS_PATH_AUTO = 0, QUPS_PATH_GENERIC = 1, QUPS_PATH_TILED = 2 } qups_path;
+
+/* ---- DAS -------------------------------------------------------------- */
+/* Image of the reference's __constant__ symbols QUPS_{I1,I2,I3,N,M,T,S,VS,DV,
+ * BF_FLAG} (src/sizes.cu:6-53, src/bf.cu:45-47) set at kern/das_spec.m:294-298. */
+typedef struct {
+    uint32_t struct_size; /* = sizeof(qups_das_params) */
+    int32_t dtype;        /* qups_dtype of x / apod / y ('f'/'h'/'' kernel suffix, kern/das_spec.m:218-222) */
+    uint64_t I1, I2, I3;  /* pixel grid; I = I1*I2*I3 */
+    uint64_t N, M, T;     /* receives, transmits, time samples */
+    uint64_t F;           /* frames looped by the library (kern/das_spec.m:371); 0 -> 1 */
+    uint64_t S;           /* number of apodization arrays (0 -> none, i.e. apod = 1) */
+    int32_t flag;         /* QUPS_BF_FLAG */
+    int32_t vs, dv;       /* QUPS_VS (0 = plane waves), QUPS_DV (1 = diverging waves) */
+    int32_t apod_real;    /* extension: apod arrays are real (the reference forces complex, :237-243) */
+    int32_t y_f32;        /* extension: with dtype F16 write float2 output instead of half2 */
+    int32_t path;         /* qups_path; AUTO picks the tiled kernel when eligible */
+    double fs;            /* sampling frequency */
+    double fmod;          /* modulation frequency (data re-modulated at absolute time, kern/das_spec.m:413-417) */
+    uint64_t x_frame_stride; /* complex elements between frames of x; 0 -> T*N*M */
+    uint64_t y_frame_stride; /* complex elements between frames of y; 0 -> I*[N]*[M] */
+    void *workspace;         /* optional device scratch for the modulated cube (fmod != 0); NULL -> stream-ordered alloc */
+    uint64_t workspace_bytes;
+} qups_das_params;
+
+/* y      : out, complex, I x [N if keep_rx] x [M if keep_tx] (x F)
+ * Pi     : 3 x I real (float for F32/F16, double for F64)
+ * Pr     : 3 x N ;  Pv4 : 4 x M (row 4 = t0 per transmit, kern/das_spec.m:361) ; Nv : 3 x M
+ * apod   : the S arrays flattened and concatenated (kern/das_spec.m:344-345), complex (or real if apod_real); NULL if S == 0
+ * cinv   : real, 1/c broadcastable to I1 x I2 x I3 x N x M
+ * acstride (HOST): uint64[6 + 6*S] = [cstride(6), astride(6 x S)] exactly as built at kern/das_spec.m:256-260
+ *          (per-dim element strides, 0 for singleton dims; entry 6 of each column = base offset into apod)
+ * x      : complex T x N x M (x F)   (T x M x N if QUPS_FLAG_TRANSPOSE)                                              */
+QUPS_API int qups_das(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
+             const void *apod, const void *cinv, const uint64_t *acstride, const void *x, qups_stream_t stream);
+
+/* tau(i,n,m) = cinv .* (dv + dr)   (no -t0)   kern/das_spec.m:448-449; tau : real I x N x M */
+QUPS_API int qups_delays(const qups_das_params *p, void *tau, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
+                const void *cinv, const uint64_t *cstride, qups_stream_t stream);
+
+/* Same as qups_das but every array pointer is a HOST pointer; performs H2D, compute, D2H and synchronises.
+ * Pinned host memory is used at full PCIe rate; pageable memory works but is slower. */
+QUPS_API int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
+                  const void *apod, uint64_t apod_elems, const void *cinv, uint64_t cinv_elems,
+                  const uint64_t *acstride, const void *x, int device);
+
+/* x(t,n,m) *= exp(2i*pi*fmod*(t0(m) + t/fs))  out-of-place; t0 : M reals (device). kern/das_spec.m:413-417 */
+QUPS_API int qups_modulate(int32_t dtype, void *xout, const void *x, const void *t0, uint64_t T, uint64_t N, uint64_t M,
+                  int32_t transpose, double fs, double fmod, qups_stream_t stream);
+
+/* ---- wsinterpd / wsinterpd2 ------------------------------------------ */
+/* y(l) = sum over dims with ystride==0 of  exp(1i*omega*t) * w(k) * interp1(x(:,v), 1+t, interp, 0),  t = t1(r)+t2(u)
+ * Image of the reference argument list (src/interpd.cu:344-349): D broadcast dims of size sizes[d]; dstride is
+ * uint64[5*D], column d = element strides of {w, y, t1, t2, x-trace} along dim d (kern/wsinterpd2.m:193-219).
+ * The reference reduces with global atomics; this library reduces deterministically inside one thread. */
+typedef struct {
+    uint32_t struct_size;
+    int32_t dtype;
+    uint64_t T;        /* samples per trace */
+    uint32_t D;        /* number of broadcast dims (<= 8) */
+    int32_t interp;
+    int32_t w_real;    /* extension: weights are real */
+    int32_t y_f32;
+    double omega;      /* imaginary part of omega = 2*pi*fmod/fs  (src/ChannelData.m:1439) */
+    uint64_t sizes[8];
+    uint64_t dstride[40];
+} qups_ws2_params;
+
+QUPS_API int qups_wsinterpd2(const qups_ws2_params *p, void *y, const void *w, const void *x, const void *t1, const void *t2,
+                    qups_stream_t stream);
+/* single-table variant (kern/wsinterpd.m): dstride columns are {w, y, t, (ignored), x} */
+QUPS_API int qups_wsinterpd(const qups_ws2_params *p, void *y, const void *w, const void *x, const void *t, qups_stream_t stream);
+
+/* ---- greens ------------------------------------------------------------ */
+/* Image of the scalar pack [t0k,t0x,fs,fsr,cinv,R0], [E,E], flag  (src/UltrasoundSystem.m:718, src/greens.cu:8-27).
+ * Output sample s (0-based) is absolute sample index n0 + s, n0 = round(t0k*fs).
+ * Semantics follow the CPU path (:797-851): R0 == 0 means "no propagation loss" (the reference GPU kernel
+ * divides by R0^2 there, src/greens.cu:84), no 1/R0^2 scaling, sum order = scatterer order as given. */
+typedef struct {
+    uint32_t struct_size;
+    int32_t dtype;
+    uint64_t I;       /* scatterers   (QUPS_I) */
+    uint64_t S;       /* output time samples (QUPS_S) */
+    uint64_t T;       /* kernel (waveform) samples (QUPS_T) */
+    uint64_t N, M;    /* receives, transmits */
+    uint64_t E;       /* sub-elements per element (both apertures) */
+    int64_t n0;       /* first output sample index */
+    int32_t interp;
+    int32_t y_f32;
+    double t0x;       /* waveform start time wv.t0 */
+    double fs, fsr;   /* output sampling frequency, kernel/output sampling ratio */
+    double c0;        /* sound speed (the CPU path divides by c0, :797-798; the reference GPU pack carries 1/c0) */
+    double R0;        /* minimum distance */
+} qups_greens_params;
+
+/* y : out complex S x N x M ; Pi : 3 x I scatterer positions ; a : I real amplitudes ;
+ * Pr : 3 x N x E ; Pv : 3 x M x E ; kern : complex T */
+QUPS_API int qups_greens(const qups_greens_params *p, void *y, const void *Pi, const void *a, const void *Pr, const void *Pv,
+                const void *kern, qups_stream_t stream);
+
+/* ---- misc --------------------------------------------------------------- */
+QUPS_API const char *qups_last_error(void);
+QUPS_API int qups_version(void);
+/* number of kernels this library launched on this thread since the last reset (bench.py's gpu_launches) */
+QUPS_API uint64_t qups_launch_count(int reset);
+/* name of the DAS kernel variant the last qups_das call on this thread dispatched to */
+QUPS_API const char *qups_last_das_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUPS_B200_H */

@@ -1,0 +1,114 @@
+"""_lib.py — ctypes binding of libqups_b200.so (include/qups_b200.h).
+
+The product path: there is NO CPU fallback.  If the CUDA library is missing or
+cannot be loaded, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqups_b200.so")
+
+F32, F16, F64 = 0, 1, 2
+NEAREST, LINEAR, CUBIC, LANCZOS3 = 0, 1, 2, 3
+FLAG_KEEP_RX, FLAG_KEEP_TX, FLAG_TRANSPOSE = 8, 16, 32
+PATH_AUTO, PATH_GENERIC, PATH_TILED = 0, 1, 2
+INTERP = {"nearest": NEAREST, "linear": LINEAR, "cubic": CUBIC, "lanczos3": LANCZOS3}
+
+EXPORTS = (
+    "qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
+    "qups_greens", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
+)
+
+
+class QupsError(RuntimeError):
+    """Raised for a negative qups_status; mirrors MATLAB error() at the reference's call sites."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[qups_b200 {code}] {msg}")
+        self.code = code
+
+
+class DasParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("dtype", C.c_int32),
+        ("I1", C.c_uint64), ("I2", C.c_uint64), ("I3", C.c_uint64),
+        ("N", C.c_uint64), ("M", C.c_uint64), ("T", C.c_uint64),
+        ("F", C.c_uint64), ("S", C.c_uint64),
+        ("flag", C.c_int32), ("vs", C.c_int32), ("dv", C.c_int32),
+        ("apod_real", C.c_int32), ("y_f32", C.c_int32), ("path", C.c_int32),
+        ("fs", C.c_double), ("fmod", C.c_double),
+        ("x_frame_stride", C.c_uint64), ("y_frame_stride", C.c_uint64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+    ]
+
+
+class Ws2Params(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("dtype", C.c_int32),
+        ("T", C.c_uint64),
+        ("D", C.c_uint32), ("interp", C.c_int32), ("w_real", C.c_int32), ("y_f32", C.c_int32),
+        ("omega", C.c_double),
+        ("sizes", C.c_uint64 * 8),
+        ("dstride", C.c_uint64 * 40),
+    ]
+
+
+class GreensParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("dtype", C.c_int32),
+        ("I", C.c_uint64), ("S", C.c_uint64), ("T", C.c_uint64), ("N", C.c_uint64), ("M", C.c_uint64),
+        ("E", C.c_uint64),
+        ("n0", C.c_int64),
+        ("interp", C.c_int32), ("y_f32", C.c_int32),
+        ("t0x", C.c_double), ("fs", C.c_double), ("fsr", C.c_double), ("c0", C.c_double), ("R0", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; fail loudly when it is absent (no CPU fallback on this path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m qups_b200.build` (nvcc, sm_100a). "
+            "qups_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+    L.qups_das.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, vp, u64p, vp, vp]
+    L.qups_delays.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, u64p, vp]
+    L.qups_das_host.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, u64p, vp,
+                                C.c_int]
+    L.qups_modulate.argtypes = [C.c_int32, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_double,
+                                C.c_double, vp]
+    L.qups_wsinterpd2.argtypes = [C.POINTER(Ws2Params), vp, vp, vp, vp, vp, vp]
+    L.qups_wsinterpd.argtypes = [C.POINTER(Ws2Params), vp, vp, vp, vp, vp]
+    L.qups_greens.argtypes = [C.POINTER(GreensParams), vp, vp, vp, vp, vp, vp, vp]
+    for f in ("qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
+              "qups_greens", "qups_version"):
+        getattr(L, f).restype = C.c_int
+    L.qups_last_error.restype = C.c_char_p
+    L.qups_last_das_kernel.restype = C.c_char_p
+    L.qups_launch_count.restype = C.c_uint64
+    L.qups_launch_count.argtypes = [C.c_int]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise QupsError(rc, lib().qups_last_error().decode("utf-8", "replace"))
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().qups_launch_count(1 if reset else 0))
+
+
+def last_das_kernel() -> str:
+    return lib().qups_last_das_kernel().decode()

@@ -1,0 +1,48 @@
+// das_args.cuh — kernel argument block shared by the DAS kernels and launchers.
+#pragma once
+#include <stdint.h>
+#include "common.cuh"
+
+namespace qups {
+
+constexpr int MAX_APOD = 8;
+
+// One launch = one frame. Mirrors the reference feval argument list
+// (kern/das_spec.m:372) plus its __constant__ sizes (src/sizes.cu).
+template <typename R> struct DasArgs {
+    uint64_t I1, I2, I3, I, N, M, T;
+    int S, interp;
+    int keep_rx, keep_tx, tpose, VS, DV, apod_real;
+    R fs;
+    const R *Pi;   // 3 x I
+    const R *Pr;   // 3 x N
+    const R *Pv4;  // 4 x M (row 4 = t0)
+    const R *Nv;   // 3 x M
+    const R *cinv; // broadcast, strides cstride[0..4]
+    const void *apod;
+    const void *x;
+    void *y;
+    uint64_t cstride[6];
+    uint64_t astride[MAX_APOD][6];
+};
+
+// launch entry points implemented in das_generic.cu / das_tiled.cu
+// (return cudaError_t as int)
+template <typename DIN, typename DA, typename DOUT, typename R>
+int launch_das_generic(const DasArgs<R> &a, cudaStream_t st);
+template <typename R> int launch_delays(const DasArgs<R> &a, R *tau, cudaStream_t st);
+template <typename DIN, typename DOUT, typename R>
+int launch_modulate(DOUT *xo, const DIN *x, const R *t0, int t0_stride, uint64_t T, uint64_t N, uint64_t M, int tpose,
+                    R fs, double fmod, cudaStream_t st);
+
+// tiled fast path (fp32 data, sum over both apertures, scalar cinv, no apodization arrays)
+struct TiledPlan {
+    int eligible;      // 1 if the tiled kernel can take this call
+    const char *why;   // reason when not eligible
+};
+TiledPlan das_tiled_plan(const DasArgs<float> &a, int dtype_in, int dtype_out);
+int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st);
+
+void count_launch(uint64_t n = 1);
+
+} // namespace qups

@@ -1,0 +1,429 @@
+// das_tiled.cu — the hot DAS kernel for sm_100a (B200): fp32 complex data, both
+// apertures summed (fun = 'DAS'), scalar sound speed, no apodization arrays.
+//
+// What it replaces: the serial M x N loop of src/bf.cu:96-139 (one thread per
+// pixel, two sqrt + 64-bit stride math + 1/2/4 dependent global gathers per
+// (pixel,rx,tx) pair).  Design:
+//
+//   * CTA = 32 x 16 pixel tile (lanes along the slow image axis, where delays
+//     vary slowly => few shared-memory wavefronts per gather), 8 consumer warps
+//     (2 pixel rows per thread) + 1 producer warp.
+//   * loop nest: receive tile (16 traces) outer, transmit m inner.  dr(i,n) for
+//     the 16 receives lives in registers for all M transmits; dv(i,m) is
+//     recomputed once per (pixel, m, receive tile)  (1 sqrt per 16 pairs).
+//   * the producer warp derives, per (n,m) trace, the exact range of sample
+//     indices the tile can touch from per-tile min/max of dv and dr — every
+//     operation of the delay sequence is monotone and individually rounded, so
+//     [k(dvmin,drmin), k(dvmax,drmax)] is a rigorous bound in floating point —
+//     and stages just that window of the trace into shared memory with one
+//     cp.async.bulk (UBLKCP) per trace, completion on an mbarrier
+//     (4-stage full/empty ring).
+//   * consumers gather taps with 64-bit LDS at 32-bit shared addresses; no
+//     bounds checks in the inner loop (the window is proven to cover them).
+//   * traces whose window leaves [first+1, last-1] of the trace, does not fit
+//     the slot, or has a NaN bound take a slow path with the full interp1 edge
+//     semantics straight from global memory; traces entirely outside the data
+//     are skipped (they contribute exactly 0).
+//
+// Numerics: the sample position xq uses the canonical individually-rounded
+// sequence (common.cuh), so tap indices are bit-identical to the oracle; the
+// interpolation weights / accumulation use FMAs (tolerance-level difference).
+#include <limits.h>
+#include "das_args.cuh"
+
+namespace qups {
+
+constexpr int kNT = 16;     // traces (receives) per stage
+constexpr int kR = 2;       // pixel rows per thread
+constexpr int kCW = 8;      // consumer warps
+constexpr int kStages = 4;  // smem ring depth
+constexpr int kThreads = (kCW + 1) * 32;
+constexpr int kTA = 32;        // tile extent along the lane axis
+constexpr int kTB = kCW * kR;  // tile extent along the row axis
+
+enum { TR_FAST = 0, TR_SKIP = 1, TR_SLOW = 2 };
+
+struct TiledArgs {
+    const float *Pi, *Pr, *Pv4, *Nv, *cinv;
+    const float2 *x;
+    float2 *y;
+    uint32_t N, M, T;
+    uint32_t IA, IB, IC;    // extents: lane axis, row axis, slice axis
+    uint64_t sA, sB, sC;    // pixel-index strides of those axes
+    uint32_t tilesA, tilesB;
+    uint32_t wmax;          // samples per smem slot (even)
+    uint32_t numNT;
+    float fs;
+    int VS, DV, tpose;
+    uint64_t total_elems;   // T*N*M
+};
+
+// ---- small PTX wrappers -----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk async copy (TMA engine, SASS UBLKCP), completes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+// order-preserving float <-> int map (involution)
+__device__ __forceinline__ int f2o(float f) {
+    const int b = __float_as_int(f);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float o2f(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7fffffff)); }
+
+// ---- inner bodies: one (pixel, trace) pair from the staged window -------------
+// xq = 1-based sample position (bit-identical to the oracle); soff = shared
+// address such that the first tap of index k = floor(xq) is at soff + 8*k.
+template <int INTERP> __device__ __forceinline__ void fast_pair(float xq, uint32_t soff, float &ar, float &ai) {
+    if (INTERP == 2) {
+        const float kf = floorf(xq);
+        const float u = xq - kf; // exact
+        const uint32_t addr = soff + ((uint32_t)__float2int_rz(kf) << 3);
+        const float2 v0 = lds64(addr), v1 = lds64(addr + 8), v2 = lds64(addr + 16), v3 = lds64(addr + 24);
+        // Keys cubic convolution a = -1/2 (interior identical to interp1 'cubic', R2020b+)
+        const float u2 = u * u;
+        float t0 = fmaf(-0.5f, u, 1.0f);
+        t0 = fmaf(t0, u, -0.5f);
+        const float w0 = t0 * u;
+        const float w1 = fmaf(fmaf(1.5f, u, -2.5f), u2, 1.0f);
+        float t2 = fmaf(-1.5f, u, 2.0f);
+        t2 = fmaf(t2, u, 0.5f);
+        const float w2 = t2 * u;
+        const float w3 = fmaf(0.5f, u, -0.5f) * u2;
+        ar = fmaf(w0, v0.x, ar); ai = fmaf(w0, v0.y, ai);
+        ar = fmaf(w1, v1.x, ar); ai = fmaf(w1, v1.y, ai);
+        ar = fmaf(w2, v2.x, ar); ai = fmaf(w2, v2.y, ai);
+        ar = fmaf(w3, v3.x, ar); ai = fmaf(w3, v3.y, ai);
+    } else if (INTERP == 1) {
+        const float kf = floorf(xq);
+        const float u = xq - kf;
+        const uint32_t addr = soff + ((uint32_t)__float2int_rz(kf) << 3);
+        const float2 v0 = lds64(addr), v1 = lds64(addr + 8);
+        ar += fmaf(u, v1.x - v0.x, v0.x);
+        ai += fmaf(u, v1.y - v0.y, v0.y);
+    } else {
+        // round half away from zero == floor(xq + 0.5) exactly for xq >= 1
+        const float kf = floorf(__fadd_rn(xq, 0.5f));
+        const uint32_t addr = soff + ((uint32_t)__float2int_rz(kf) << 3);
+        const float2 v0 = lds64(addr);
+        ar += v0.x;
+        ai += v0.y;
+    }
+}
+
+// full-semantics slow path (edges, oversize windows, NaN): straight from global memory
+__device__ __noinline__ void slow_pair(const float2 *trace, uint32_t T, float xq, int interp, float &ar, float &ai) {
+    const cplx<float> v = interp1<float2>(trace, (long)T, xq, interp);
+    ar += v.re;
+    ai += v.im;
+}
+
+template <int INTERP>
+__global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [0,64) full/empty mbarriers | desc[kStages][kNT] int2 | allfast[kStages] |
+    //         dvmin[M] dvmax[M] drmin[N] drmax[N] (ordered ints) | 128B-aligned stage ring
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    int2 *desc = reinterpret_cast<int2 *>(smem_raw + 64);
+    int *allfast = reinterpret_cast<int *>(smem_raw + 64 + sizeof(int2) * kStages * kNT);
+    int *s_dvmin = allfast + kStages;
+    int *s_dvmax = s_dvmin + a.M;
+    int *s_drmin = s_dvmax + a.M;
+    int *s_drmax = s_drmin + a.N;
+    const uint32_t ring_off = (uint32_t)((64 + sizeof(int2) * kStages * kNT + sizeof(int) * (kStages + 2 * a.M + 2 * a.N) + 127) & ~127u);
+    const uint32_t ring = smem_u32(smem_raw) + ring_off;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- tile coordinates -------------------------------------------------------
+    const uint32_t tile = blockIdx.x;
+    const uint32_t ta = tile % a.tilesA, tb = (tile / a.tilesA) % a.tilesB, tc = tile / (a.tilesA * a.tilesB);
+    const uint32_t ia = ta * kTA + lane;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, kCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    for (uint32_t i = tid; i < a.M; i += kThreads) { s_dvmin[i] = INT_MAX; s_dvmax[i] = INT_MIN; }
+    for (uint32_t i = tid; i < a.N; i += kThreads) { s_drmin[i] = INT_MAX; s_drmax[i] = INT_MIN; }
+    __syncthreads();
+
+    const float cinv = __ldg(a.cinv);
+    const float fs = a.fs;
+    const bool VS = a.VS, DV = a.DV;
+
+    if (warp < kCW) {
+        // =========================== consumers =====================================
+        float px[kR], py[kR], pz[kR];
+        uint64_t pix[kR];
+        bool valid[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+            const uint32_t ib = tb * kTB + warp * kR + r;
+            valid[r] = (ia < a.IA) && (ib < a.IB);
+            // out-of-image lanes shadow a valid pixel so they never widen the windows
+            const uint32_t ca = ia < a.IA ? ia : a.IA - 1, cb = ib < a.IB ? ib : a.IB - 1;
+            pix[r] = (uint64_t)ca * a.sA + (uint64_t)cb * a.sB + (uint64_t)tc * a.sC;
+            px[r] = __ldg(a.Pi + 3 * pix[r]);
+            py[r] = __ldg(a.Pi + 3 * pix[r] + 1);
+            pz[r] = __ldg(a.Pi + 3 * pix[r] + 2);
+        }
+        // ---- phase 0: per-tile min/max of dv(.,m) and dr(.,n) -------------------------
+        for (uint32_t m = 0; m < a.M; ++m) {
+            const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
+            const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
+            int lo = INT_MAX, hi = INT_MIN;
+#pragma unroll
+            for (int r = 0; r < kR; ++r) {
+                const int o = f2o(tx_dist(px[r], py[r], pz[r], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV));
+                lo = min(lo, o);
+                hi = max(hi, o);
+            }
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if (lane == 0) { atomicMin(&s_dvmin[m], lo); atomicMax(&s_dvmax[m], hi); }
+        }
+        for (uint32_t n = 0; n < a.N; ++n) {
+            const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
+            int lo = INT_MAX, hi = INT_MIN;
+#pragma unroll
+            for (int r = 0; r < kR; ++r) {
+                const int o = f2o(rx_dist(px[r], py[r], pz[r], rx, ry, rz));
+                lo = min(lo, o);
+                hi = max(hi, o);
+            }
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if (lane == 0) { atomicMin(&s_drmin[n], lo); atomicMax(&s_drmax[n], hi); }
+        }
+        __syncthreads();
+
+        // ---- phase 1: main loop -----------------------------------------------------------
+        float ar[kR], ai[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) { ar[r] = 0.f; ai[r] = 0.f; }
+        uint32_t it = 0;
+        for (uint32_t nt = 0; nt < a.numNT; ++nt) {
+            float dr[kR][kNT];
+#pragma unroll
+            for (int j = 0; j < kNT; ++j) {
+                const uint32_t n = min(nt * kNT + j, a.N - 1);
+                const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
+#pragma unroll
+                for (int r = 0; r < kR; ++r) dr[r][j] = rx_dist(px[r], py[r], pz[r], rx, ry, rz);
+            }
+            for (uint32_t m = 0; m < a.M; ++m, ++it) {
+                const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
+                const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
+                float dv[kR];
+#pragma unroll
+                for (int r = 0; r < kR; ++r) dv[r] = tx_dist(px[r], py[r], pz[r], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+                const float t0m = pv.w;
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                mbar_wait(bar_full + 8 * s, ph);
+                const int2 *dsc = desc + s * kNT;
+                if (allfast[s]) {
+#pragma unroll
+                    for (int j = 0; j < kNT; ++j) {
+                        const uint32_t soff = (uint32_t)dsc[j].x;
+#pragma unroll
+                        for (int r = 0; r < kR; ++r)
+                            fast_pair<INTERP>(sample_pos(dv[r], dr[r][j], cinv, t0m, fs), soff, ar[r], ai[r]);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < kNT; ++j) {
+                        const int2 d = dsc[j];
+                        if (d.y == TR_SKIP) continue;
+                        const uint32_t n = nt * kNT + j;
+                        const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
+                        const uint64_t nm = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
+#pragma unroll
+                        for (int r = 0; r < kR; ++r) {
+                            const float xq = sample_pos(dv[r], rx_dist(px[r], py[r], pz[r], rx, ry, rz), cinv, t0m, fs);
+                            if (d.y == TR_FAST) fast_pair<INTERP>(xq, (uint32_t)d.x, ar[r], ai[r]);
+                            else slow_pair(a.x + nm * a.T, a.T, xq, INTERP, ar[r], ai[r]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kR; ++r)
+            if (valid[r]) a.y[pix[r]] = make_float2(ar[r], ai[r]);
+    } else {
+        // =========================== producer warp =================================
+        __syncthreads(); // matches the consumers' post-phase-0 barrier
+        const bool cinv_ok = (cinv > 0.f) && (fs > 0.f);
+        const float Tf = (float)a.T;
+        uint32_t it = 0;
+        for (uint32_t nt = 0; nt < a.numNT; ++nt) {
+            const uint32_t n = nt * kNT + lane;
+            const bool has = (lane < kNT) && (n < a.N);
+            float rlo = 0.f, rhi = 0.f;
+            if (has) { rlo = o2f(s_drmin[n]); rhi = o2f(s_drmax[n]); }
+            for (uint32_t m = 0; m < a.M; ++m, ++it) {
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                int flag = TR_SKIP;
+                uint32_t bytes = 0, soff = 0, dst = 0;
+                const float2 *src = nullptr;
+                if (has) {
+                    const float t0m = __ldg(a.Pv4 + 4 * m + 3);
+                    const float xlo = sample_pos(o2f(s_dvmin[m]), rlo, cinv, t0m, fs);
+                    const float xhi = sample_pos(o2f(s_dvmax[m]), rhi, cinv, t0m, fs);
+                    flag = TR_SLOW;
+                    if (cinv_ok && xlo <= xhi) {
+                        if (xhi < 1.0f || xlo > Tf) {
+                            flag = TR_SKIP; // every pixel of the tile is outside the trace: contributes 0
+                        } else {
+                            // in-range test for the unchecked inner loop, and tap span per method
+                            bool inr;
+                            int klo, khi, tap0, tap1;
+                            if (INTERP == 2) {        // taps k-1..k+2 (1-based) must all be real samples
+                                inr = (xlo >= 2.0f) && (xhi < Tf - 1.0f);
+                                klo = (int)floorf(xlo); khi = (int)floorf(xhi); tap0 = 2; tap1 = 1;
+                            } else if (INTERP == 1) { // taps k, k+1
+                                inr = (xlo >= 1.0f) && (xhi < Tf);
+                                klo = (int)floorf(xlo); khi = (int)floorf(xhi); tap0 = 1; tap1 = 0;
+                            } else {                  // tap round(xq)
+                                inr = (xlo >= 1.0f) && (xhi <= Tf);
+                                klo = (int)floorf(__fadd_rn(xlo, 0.5f)); khi = (int)floorf(__fadd_rn(xhi, 0.5f));
+                                tap0 = 1; tap1 = -1;
+                            }
+                            if (inr) {
+                                const uint64_t tr = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
+                                const int64_t abs_lo = (int64_t)(tr * a.T) + (klo - tap0); // 0-based first tap, absolute
+                                const int64_t abs_al = abs_lo & ~(int64_t)1;                // 16-byte aligned element
+                                const int w0 = (klo - tap0) - (int)(abs_lo - abs_al);
+                                int wlen = (khi + tap1) - w0 + 1;
+                                wlen = (wlen + 1) & ~1;
+                                if (wlen <= (int)a.wmax && abs_al >= 0 && (uint64_t)(abs_al + wlen) <= a.total_elems) {
+                                    flag = TR_FAST;
+                                    bytes = (uint32_t)wlen * 8u;
+                                    dst = ring + (s * kNT + lane) * a.wmax * 8u;
+                                    soff = dst - (uint32_t)(w0 + tap0) * 8u;
+                                    src = a.x + abs_al;
+                                }
+                            }
+                        }
+                    }
+                }
+                mbar_wait(bar_empty + 8 * s, ph ^ 1); // slot free (first lap passes immediately)
+                if (lane < kNT) desc[s * kNT + lane] = make_int2((int)soff, flag);
+                const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+                const bool all = __all_sync(0xffffffffu, flag == TR_FAST || lane >= kNT);
+                __syncwarp();
+                if (lane == 0) {
+                    allfast[s] = all ? 1 : 0;
+                    mbar_arrive_expect_tx(bar_full + 8 * s, total);
+                }
+                __syncwarp();
+                if (flag == TR_FAST) bulk_g2s(dst, src, bytes, bar_full + 8 * s);
+            }
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------
+static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax) {
+    size_t head = 64 + sizeof(int2) * kStages * kNT + sizeof(int) * (kStages + 2 * (size_t)M + 2 * (size_t)N);
+    head = (head + 127) & ~(size_t)127;
+    return head + (size_t)kStages * kNT * wmax * 8;
+}
+
+TiledPlan das_tiled_plan(const DasArgs<float> &a, int dtype_in, int dtype_out) {
+    TiledPlan p{0, ""};
+    if (dtype_in != 0 || dtype_out != 0) { p.why = "tiled path is fp32 only"; return p; }
+    if (a.keep_rx || a.keep_tx) { p.why = "tiled path sums both apertures"; return p; }
+    if (a.S != 0) { p.why = "tiled path takes no apodization arrays"; return p; }
+    for (int d = 0; d < 5; ++d)
+        if (a.cstride[d] != 0) { p.why = "tiled path needs a scalar sound speed"; return p; }
+    if (a.interp < 0 || a.interp > 2) { p.why = "tiled path: nearest|linear|cubic"; return p; }
+    if (!(a.fs > 0.f)) { p.why = "fs <= 0"; return p; }
+    if (a.T < 4 || a.T >= (1u << 22)) { p.why = "T out of range for the tiled path"; return p; }
+    if (a.N == 0 || a.M == 0 || a.I == 0) { p.why = "empty"; return p; }
+    if (a.N >= (1u << 24) || a.M >= (1u << 24) || a.I >= (1ull << 40)) { p.why = "too large"; return p; }
+    if ((reinterpret_cast<uintptr_t>(a.x) & 15) != 0) { p.why = "x not 16-byte aligned"; return p; }
+    if ((reinterpret_cast<uintptr_t>(a.Pv4) & 15) != 0) { p.why = "Pv not 16-byte aligned"; return p; }
+    if (tiled_smem_bytes((uint32_t)a.N, (uint32_t)a.M, 64) > 200 * 1024) { p.why = "N+M too large for smem"; return p; }
+    p.eligible = 1;
+    return p;
+}
+
+int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
+    TiledArgs t{};
+    t.Pi = a.Pi; t.Pr = a.Pr; t.Pv4 = a.Pv4; t.Nv = a.Nv; t.cinv = a.cinv;
+    t.x = reinterpret_cast<const float2 *>(a.x);
+    t.y = reinterpret_cast<float2 *>(a.y);
+    t.N = (uint32_t)a.N; t.M = (uint32_t)a.M; t.T = (uint32_t)a.T;
+    t.fs = a.fs; t.VS = a.VS; t.DV = a.DV; t.tpose = a.tpose;
+    t.total_elems = a.T * a.N * a.M;
+    t.numNT = (t.N + kNT - 1) / kNT;
+    // axis assignment: lanes along I2 (the slow axis of a ZXY ScanCartesian, src/ScanCartesian.m:11) when
+    // it is wide enough, rows along I1; overridable for experiments (QUPS_B200_LANE_AXIS=1|2)
+    int lane_axis = (a.I2 >= 8) ? 2 : 1;
+    if (const char *e = getenv("QUPS_B200_LANE_AXIS")) { int v = atoi(e); if (v == 1 || v == 2) lane_axis = v; }
+    if (lane_axis == 2) { t.IA = (uint32_t)a.I2; t.sA = a.I1; t.IB = (uint32_t)a.I1; t.sB = 1; }
+    else                { t.IA = (uint32_t)a.I1; t.sA = 1;    t.IB = (uint32_t)a.I2; t.sB = a.I1; }
+    t.IC = (uint32_t)a.I3; t.sC = a.I1 * a.I2;
+    t.tilesA = (t.IA + kTA - 1) / kTA;
+    t.tilesB = (t.IB + kTB - 1) / kTB;
+    uint32_t wmax = 128;
+    if (const char *e = getenv("QUPS_B200_WMAX")) { int v = atoi(e); if (v >= 8 && v <= 1024) wmax = (uint32_t)(v & ~1); }
+    while (wmax > 16 && tiled_smem_bytes(t.N, t.M, wmax) > 100 * 1024) wmax -= 16;
+    t.wmax = wmax;
+    const size_t smem = tiled_smem_bytes(t.N, t.M, wmax);
+    const uint64_t tiles = (uint64_t)t.tilesA * t.tilesB * t.IC;
+    if (tiles == 0 || tiles > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+
+    void (*kern)(const TiledArgs) = nullptr;
+    switch (a.interp) {
+        case 0: kern = das_tiled_kernel<0>; break;
+        case 1: kern = das_tiled_kernel<1>; break;
+        default: kern = das_tiled_kernel<2>; break;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<(unsigned)tiles, kThreads, smem, st>>>(t);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+} // namespace qups

@@ -1,0 +1,314 @@
+// qups_b200.cu — the extern "C" boundary of libqups_b200.so (see include/qups_b200.h).
+// Argument validation, dtype dispatch, frame loop (kern/das_spec.m:371-373),
+// modulation pre-pass (kern/das_spec.m:413-417) and the host-buffer variants.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/qups_b200.h"
+#include "das_args.cuh"
+#include "other_kernels.cuh"
+
+namespace qups {
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+static thread_local const char *g_last_das = "none";
+void count_launch(uint64_t n) { g_launches += n; }
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(int e, const char *what) {
+    return fail(QUPS_ERR_CUDA, "%s: %s", what, cudaGetErrorString((cudaError_t)e));
+}
+
+template <typename R>
+static int fill_args(DasArgs<R> &a, const qups_das_params *p, const void *Pi, const void *Pr, const void *Pv4,
+                     const void *Nv, const void *apod, const void *cinv, const uint64_t *acstride, int need_astride) {
+    a.I1 = p->I1; a.I2 = p->I2; a.I3 = p->I3;
+    a.I = p->I1 * p->I2 * p->I3;
+    a.N = p->N; a.M = p->M; a.T = p->T;
+    a.S = (int)p->S;
+    a.interp = p->flag & QUPS_FLAG_INTERP_MASK;
+    a.keep_rx = (p->flag & QUPS_FLAG_KEEP_RX) != 0;
+    a.keep_tx = (p->flag & QUPS_FLAG_KEEP_TX) != 0;
+    a.tpose = (p->flag & QUPS_FLAG_TRANSPOSE) != 0;
+    a.VS = p->vs != 0; a.DV = p->dv != 0;
+    a.apod_real = p->apod_real != 0;
+    a.fs = (R)p->fs;
+    a.Pi = (const R *)Pi; a.Pr = (const R *)Pr; a.Pv4 = (const R *)Pv4; a.Nv = (const R *)Nv;
+    a.cinv = (const R *)cinv;
+    a.apod = apod;
+    for (int d = 0; d < 6; ++d) a.cstride[d] = acstride ? acstride[d] : 0;
+    a.cstride[5] = 0; // entry 6 of cstride is unused padding in the reference (kern/das_spec.m:259)
+    for (int s = 0; s < MAX_APOD; ++s)
+        for (int d = 0; d < 6; ++d) a.astride[s][d] = (need_astride && s < a.S) ? acstride[6 + 6 * s + d] : 0;
+    return 0;
+}
+
+static int validate(const qups_das_params *p, bool is_delays) {
+    if (!p) return fail(QUPS_ERR_INVALID, "params is NULL");
+    if (p->struct_size != sizeof(qups_das_params))
+        return fail(QUPS_ERR_INVALID, "params.struct_size %u != %zu (header/library mismatch)", p->struct_size,
+                    sizeof(qups_das_params));
+    if (p->dtype < QUPS_F32 || p->dtype > QUPS_F64) return fail(QUPS_ERR_INVALID, "unknown dtype %d", p->dtype);
+    if (p->S > (uint64_t)MAX_APOD) return fail(QUPS_ERR_UNSUPPORTED, "at most %d apodization arrays", MAX_APOD);
+    const int interp = p->flag & QUPS_FLAG_INTERP_MASK;
+    if (!is_delays && interp > QUPS_LANCZOS3)
+        return fail(QUPS_ERR_INVALID, "Unrecognized interpolation id %d: must be one of nearest(0), linear(1), cubic(2), lanczos3(3)", interp);
+    if (!is_delays) {
+        if (interp == QUPS_LINEAR && p->T < 2) return fail(QUPS_ERR_INVALID, "linear interpolation needs T >= 2");
+        if (interp == QUPS_CUBIC && p->T < 3) return fail(QUPS_ERR_INVALID, "cubic interpolation needs T >= 3");
+        if (!(p->fs > 0.0) && p->fs == p->fs && p->fs != 0.0) { /* negative fs allowed on the generic path */ }
+    }
+    return 0;
+}
+
+template <typename DIN, typename DA, typename DOUT, typename R>
+static int run_das_typed(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4,
+                         const void *Nv, const void *apod, const void *cinv, const uint64_t *acstride, const void *x,
+                         cudaStream_t st, int dtype_in, int dtype_out) {
+    DasArgs<R> a;
+    fill_args<R>(a, p, Pi, Pr, Pv4, Nv, apod, cinv, acstride, 1);
+    const uint64_t F = p->F ? p->F : 1;
+    const uint64_t On = a.keep_rx ? a.N : 1, Om = a.keep_tx ? a.M : 1;
+    const uint64_t xfs = p->x_frame_stride ? p->x_frame_stride : a.T * a.N * a.M;
+    const uint64_t yfs = p->y_frame_stride ? p->y_frame_stride : a.I * On * Om;
+    if (a.I == 0 || On * Om == 0) return 0;
+    if (a.N == 0 || a.M == 0) { // empty apertures: the sums are empty => zeros
+        for (uint64_t f = 0; f < F; ++f) {
+            cudaError_t e = cudaMemsetAsync((DOUT *)y + f * yfs, 0, sizeof(DOUT) * a.I * On * Om, st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+        }
+        return 0;
+    }
+    for (uint64_t f = 0; f < F; ++f) {
+        a.x = (const DIN *)x + f * xfs;
+        a.y = (DOUT *)y + f * yfs;
+        int rc;
+        bool tiled = false;
+        if constexpr (sizeof(R) == 4) {
+            if (p->path != QUPS_PATH_GENERIC) {
+                TiledPlan plan = das_tiled_plan(a, dtype_in, dtype_out);
+                if (plan.eligible) tiled = true;
+                else if (p->path == QUPS_PATH_TILED)
+                    return fail(QUPS_ERR_UNSUPPORTED, "tiled DAS path not applicable: %s", plan.why);
+            }
+            if (tiled) {
+                rc = launch_das_tiled(a, st);
+                g_last_das = "das_tiled";
+            } else {
+                rc = launch_das_generic<DIN, DA, DOUT, R>(a, st);
+                g_last_das = "das_generic";
+            }
+        } else {
+            if (p->path == QUPS_PATH_TILED) return fail(QUPS_ERR_UNSUPPORTED, "tiled DAS path is fp32 only");
+            rc = launch_das_generic<DIN, DA, DOUT, R>(a, st);
+            g_last_das = "das_generic";
+        }
+        if (rc != 0) return cuda_fail(rc, "DAS kernel launch");
+    }
+    return 0;
+}
+
+static int das_impl(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
+                    const void *apod, const void *cinv, const uint64_t *acstride, const void *x, cudaStream_t st) {
+    if (int rc = validate(p, false)) return rc;
+    if (!y || !Pi || !Pr || !Pv4 || !Nv || !cinv || !x) {
+        const uint64_t I = p->I1 * p->I2 * p->I3;
+        if (I != 0 && p->N != 0 && p->M != 0) return fail(QUPS_ERR_INVALID, "NULL array argument");
+    }
+    if (p->S > 0 && (!apod || !acstride)) return fail(QUPS_ERR_INVALID, "S > 0 but apod/acstride is NULL");
+
+    // (de)modulation pre-pass — the CPU-branch convention (kern/das_spec.m:413-417): the DATA are
+    // re-modulated at absolute time before interpolation.  One frame of scratch.
+    if (p->fmod != 0.0 && p->T * p->N * p->M != 0) {
+        const uint64_t F = p->F ? p->F : 1;
+        const uint64_t nel = p->T * p->N * p->M;
+        const int tpose = (p->flag & QUPS_FLAG_TRANSPOSE) != 0;
+        const size_t esz = (p->dtype == QUPS_F64) ? sizeof(double2) : sizeof(float2); // fp16 data -> fp32 scratch
+        void *scratch = nullptr;
+        bool own = false;
+        if (p->workspace && p->workspace_bytes >= esz * nel) scratch = p->workspace;
+        else {
+            cudaError_t e = cudaMallocAsync(&scratch, esz * nel, st);
+            if (e != cudaSuccess) return fail(QUPS_ERR_ALLOC, "cudaMallocAsync(%zu): %s", esz * nel, cudaGetErrorString(e));
+            own = true;
+        }
+        qups_das_params q = *p;
+        q.fmod = 0.0; q.F = 1; q.workspace = nullptr; q.workspace_bytes = 0;
+        const uint64_t On = (p->flag & QUPS_FLAG_KEEP_RX) ? p->N : 1, Om = (p->flag & QUPS_FLAG_KEEP_TX) ? p->M : 1;
+        const uint64_t xfs = p->x_frame_stride ? p->x_frame_stride : nel;
+        const uint64_t yfs = p->y_frame_stride ? p->y_frame_stride : p->I1 * p->I2 * p->I3 * On * Om;
+        int rc = 0;
+        for (uint64_t f = 0; f < F && rc == 0; ++f) {
+            int e;
+            if (p->dtype == QUPS_F32) {
+                e = launch_modulate<float2, float2, float>((float2 *)scratch, (const float2 *)x + f * xfs,
+                                                           (const float *)Pv4 + 3, 4, p->T, p->N, p->M, tpose, (float)p->fs, p->fmod, st);
+                if (e) { rc = cuda_fail(e, "modulate"); break; }
+                rc = run_das_typed<float2, float2, float2, float>(&q, (float2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 0, 0);
+            } else if (p->dtype == QUPS_F16) {
+                e = launch_modulate<__half2, float2, float>((float2 *)scratch, (const __half2 *)x + f * xfs,
+                                                            (const float *)Pv4 + 3, 4, p->T, p->N, p->M, tpose, (float)p->fs, p->fmod, st);
+                if (e) { rc = cuda_fail(e, "modulate"); break; }
+                q.path = QUPS_PATH_GENERIC; // apod stays half: generic mixed-type kernel
+                if (p->y_f32) rc = run_das_typed<float2, __half2, float2, float>(&q, (float2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 0, 0);
+                else rc = run_das_typed<float2, __half2, __half2, float>(&q, (__half2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 0, 1);
+            } else {
+                e = launch_modulate<double2, double2, double>((double2 *)scratch, (const double2 *)x + f * xfs,
+                                                              (const double *)Pv4 + 3, 4, p->T, p->N, p->M, tpose, p->fs, p->fmod, st);
+                if (e) { rc = cuda_fail(e, "modulate"); break; }
+                rc = run_das_typed<double2, double2, double2, double>(&q, (double2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 2, 2);
+            }
+        }
+        if (own) cudaFreeAsync(scratch, st);
+        return rc;
+    }
+
+    switch (p->dtype) {
+        case QUPS_F32:
+            return run_das_typed<float2, float2, float2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 0, 0);
+        case QUPS_F16:
+            if (p->y_f32) return run_das_typed<__half2, __half2, float2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 1, 0);
+            return run_das_typed<__half2, __half2, __half2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 1, 1);
+        default:
+            return run_das_typed<double2, double2, double2, double>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 2, 2);
+    }
+}
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    cudaError_t alloc(size_t bytes) { return bytes ? cudaMalloc((void **)&p, bytes) : cudaSuccess; }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+} // namespace qups
+
+using namespace qups;
+
+extern "C" {
+
+int qups_version(void) { return QUPS_B200_VERSION; }
+const char *qups_last_error(void) { return g_err; }
+const char *qups_last_das_kernel(void) { return g_last_das; }
+uint64_t qups_launch_count(int reset) {
+    const uint64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int qups_das(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
+             const void *apod, const void *cinv, const uint64_t *acstride, const void *x, qups_stream_t stream) {
+    g_err[0] = 0;
+    return das_impl(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, (cudaStream_t)stream);
+}
+
+int qups_delays(const qups_das_params *p, void *tau, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
+                const void *cinv, const uint64_t *cstride, qups_stream_t stream) {
+    g_err[0] = 0;
+    if (int rc = validate(p, true)) return rc;
+    if (p->dtype == QUPS_F64) {
+        DasArgs<double> a;
+        fill_args<double>(a, p, Pi, Pr, Pv4, Nv, nullptr, cinv, cstride, 0);
+        if (int e = launch_delays<double>(a, (double *)tau, (cudaStream_t)stream)) return cuda_fail(e, "delays kernel");
+    } else {
+        DasArgs<float> a;
+        fill_args<float>(a, p, Pi, Pr, Pv4, Nv, nullptr, cinv, cstride, 0);
+        if (int e = launch_delays<float>(a, (float *)tau, (cudaStream_t)stream)) return cuda_fail(e, "delays kernel");
+    }
+    return 0;
+}
+
+int qups_modulate(int32_t dtype, void *xout, const void *x, const void *t0, uint64_t T, uint64_t N, uint64_t M,
+                  int32_t transpose, double fs, double fmod, qups_stream_t stream) {
+    g_err[0] = 0;
+    int e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == QUPS_F32) e = launch_modulate<float2, float2, float>((float2 *)xout, (const float2 *)x, (const float *)t0, 1, T, N, M, transpose, (float)fs, fmod, st);
+    else if (dtype == QUPS_F16) e = launch_modulate<__half2, __half2, float>((__half2 *)xout, (const __half2 *)x, (const float *)t0, 1, T, N, M, transpose, (float)fs, fmod, st);
+    else if (dtype == QUPS_F64) e = launch_modulate<double2, double2, double>((double2 *)xout, (const double2 *)x, (const double *)t0, 1, T, N, M, transpose, fs, fmod, st);
+    else return fail(QUPS_ERR_INVALID, "unknown dtype %d", dtype);
+    if (e) return cuda_fail(e, "modulate kernel");
+    return 0;
+}
+
+int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
+                  const void *apod, uint64_t apod_elems, const void *cinv, uint64_t cinv_elems,
+                  const uint64_t *acstride, const void *x, int device) {
+    g_err[0] = 0;
+    if (int rc = validate(p, false)) return rc;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t rsz = (p->dtype == QUPS_F64) ? 8 : 4;                       // geometry element
+    const size_t csz = (p->dtype == QUPS_F64) ? 16 : (p->dtype == QUPS_F16 ? 4 : 8); // complex data element
+    const size_t ysz = (p->dtype == QUPS_F16 && p->y_f32) ? 8 : csz;
+    const size_t asz = p->apod_real ? csz / 2 : csz;
+    const uint64_t I = p->I1 * p->I2 * p->I3, F = p->F ? p->F : 1;
+    const uint64_t On = (p->flag & QUPS_FLAG_KEEP_RX) ? p->N : 1, Om = (p->flag & QUPS_FLAG_KEEP_TX) ? p->M : 1;
+    const uint64_t xfs = p->x_frame_stride ? p->x_frame_stride : p->T * p->N * p->M;
+    const uint64_t yfs = p->y_frame_stride ? p->y_frame_stride : I * On * Om;
+    const size_t xb = csz * ((F - 1) * xfs + p->T * p->N * p->M), yb = ysz * ((F - 1) * yfs + I * On * Om);
+    cudaStream_t st;
+    if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    DevBuf<char> dPi, dPr, dPv, dNv, dA, dC, dX, dY;
+    int rc = 0;
+#define QUPS_UP(buf, src, bytes)                                                                        \
+    if (rc == 0 && (bytes)) {                                                                           \
+        if ((e = buf.alloc(bytes)) != cudaSuccess) rc = fail(QUPS_ERR_ALLOC, "cudaMalloc(%zu): %s", (size_t)(bytes), cudaGetErrorString(e)); \
+        else if ((e = cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = cuda_fail(e, "H2D copy"); \
+    }
+    QUPS_UP(dX, x, xb)
+    QUPS_UP(dPi, Pi, rsz * 3 * I)
+    QUPS_UP(dPr, Pr, rsz * 3 * p->N)
+    QUPS_UP(dPv, Pv4, rsz * 4 * p->M)
+    QUPS_UP(dNv, Nv, rsz * 3 * p->M)
+    QUPS_UP(dA, apod, asz * apod_elems)
+    QUPS_UP(dC, cinv, rsz * cinv_elems)
+#undef QUPS_UP
+    if (rc == 0 && yb && (e = dY.alloc(yb)) != cudaSuccess) rc = fail(QUPS_ERR_ALLOC, "cudaMalloc(%zu): %s", yb, cudaGetErrorString(e));
+    if (rc == 0) rc = das_impl(p, dY.p, dPi.p, dPr.p, dPv.p, dNv.p, dA.p, dC.p, acstride, dX.p, st);
+    if (rc == 0 && yb && (e = cudaMemcpyAsync(y, dY.p, yb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = cuda_fail(e, "D2H copy");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess && rc == 0) rc = cuda_fail(e, "cudaStreamSynchronize");
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+int qups_wsinterpd2(const qups_ws2_params *p, void *y, const void *w, const void *x, const void *t1, const void *t2,
+                    qups_stream_t stream) {
+    g_err[0] = 0;
+    if (!p || p->struct_size != sizeof(qups_ws2_params)) return fail(QUPS_ERR_INVALID, "bad qups_ws2_params");
+    if (p->D == 0 || p->D > 8) return fail(QUPS_ERR_INVALID, "D must be in 1..8");
+    if (p->interp < 0 || p->interp > 3) return fail(QUPS_ERR_INVALID, "Interp option not recognized: %d", p->interp);
+    if (int e = launch_wsinterpd2(*p, y, w, x, t1, t2, (cudaStream_t)stream)) {
+        if (e == -3) return fail(QUPS_ERR_UNSUPPORTED, "unsupported dtype/layout for wsinterpd2");
+        return cuda_fail(e, "wsinterpd2 kernel");
+    }
+    return 0;
+}
+
+int qups_wsinterpd(const qups_ws2_params *p, void *y, const void *w, const void *x, const void *t, qups_stream_t stream) {
+    return qups_wsinterpd2(p, y, w, x, t, nullptr, stream);
+}
+
+int qups_greens(const qups_greens_params *p, void *y, const void *Pi, const void *a, const void *Pr, const void *Pv,
+                const void *kern, qups_stream_t stream) {
+    g_err[0] = 0;
+    if (!p || p->struct_size != sizeof(qups_greens_params)) return fail(QUPS_ERR_INVALID, "bad qups_greens_params");
+    if (p->interp < 0 || p->interp > 3) return fail(QUPS_ERR_INVALID, "Interp option not recognized: %d", p->interp);
+    if (!(p->fs > 0) || !(p->fsr > 0) || !(p->c0 > 0)) return fail(QUPS_ERR_INVALID, "fs, fsr and c0 must be positive");
+    if (int e = launch_greens(*p, y, Pi, a, Pr, Pv, kern, (cudaStream_t)stream)) {
+        if (e == -3) return fail(QUPS_ERR_UNSUPPORTED, "unsupported dtype for greens");
+        if (e == -4) return fail(QUPS_ERR_ALLOC, "greens scratch allocation failed");
+        return cuda_fail(e, "greens kernel");
+    }
+    return 0;
+}
+
+} // extern "C"

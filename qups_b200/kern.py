@@ -1,0 +1,347 @@
+"""kern.py — host-side mirror of the reference's L2 "kern" functions for the hot path.
+
+Same names, option strings, argument meaning and error behaviour as
+
+    kern/das_spec.m     das_spec(fun, Pi, Pr, Pv, Nv, x, t0, fs, c, varargin)
+    kern/wsinterpd2.m   wsinterpd2(x, t1, t2, dim, w, sdim, interp, extrapval, omega)
+    kern/wsinterpd.m    wsinterpd(x, t, dim, w, sdim, interp, extrapval, omega)
+
+so the parity tests read like the reference's own.  The reference host language
+is MATLAB (absent from this image); this module is the Python stand-in for the
+MATLAB glue in matlab/ + mex/ and calls the SAME C ABI (include/qups_b200.h).
+All computation happens in libqups_b200.so on the GPU; there is no CPU path
+here ('device', 0 raises).  PyTorch is used only for device memory and streams.
+
+Arrays use MATLAB's logical shapes (x is T x N x M x F..., Pi is 3 x I1 x I2 x I3)
+and may be NumPy arrays (copied to the GPU, result returned as NumPy) or CUDA
+torch tensors (result is a CUDA tensor).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DasParams, Ws2Params, QupsError
+
+_RT = {"single": torch.float32, "double": torch.float64, "halfT": torch.float32}
+_CT = {"single": torch.complex64, "double": torch.complex128}
+_DT = {"single": _lib.F32, "double": _lib.F64, "halfT": _lib.F16}
+
+
+def _as_tensor(a):
+    if isinstance(a, torch.Tensor):
+        return a
+    return torch.from_numpy(np.ascontiguousarray(a) if np.ndim(a) == 0 else np.asarray(a))
+
+
+def _colmajor(t: torch.Tensor, dtype, device) -> torch.Tensor:
+    """Contiguous device tensor whose memory is the column-major image of `t` (shape reversed)."""
+    if t.ndim > 1:
+        t = t.permute(*reversed(range(t.ndim)))
+    return t.to(device=device, dtype=dtype).contiguous()
+
+
+def _from_colmajor(buf: torch.Tensor, shape: Sequence[int]) -> torch.Tensor:
+    shape = tuple(int(s) for s in shape)
+    v = buf.reshape(tuple(reversed(shape)))
+    return v.permute(*reversed(range(len(shape)))) if len(shape) > 1 else v
+
+
+def _cplx_buf(t: torch.Tensor, prec: str, device) -> torch.Tensor:
+    """Column-major interleaved complex buffer in the precision's storage type."""
+    if prec == "halfT":
+        c = _colmajor(t if t.is_complex() else t.to(torch.complex64), torch.complex64, device)
+        return torch.view_as_real(c).to(torch.float16).contiguous()
+    c = _colmajor(t if t.is_complex() else t.to(_CT[prec]), _CT[prec], device)
+    return c
+
+
+def _ptr(t) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(0)
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _mod_size(P: torch.Tensor) -> torch.Tensor:
+    """parse_inputs/modSize: coordinates in the 1st dimension (kern/das_spec.m:587-597)."""
+    if P.ndim == 1:
+        P = P.reshape(-1, 1)
+    if P.shape[0] <= 4:
+        return P
+    if P.ndim == 2 and P.shape[1] <= 4:
+        return P.T
+    return P
+
+
+def _mod_dim(P: torch.Tensor) -> torch.Tensor:
+    """expand_inputs/modDim: lift 1-D / 2-D / 4-D coordinates to 3-D (kern/das_spec.m:656-669)."""
+    d = P.shape[0]
+    z = torch.zeros_like(P[:1])
+    if d == 1:
+        return torch.cat([P, z, z], 0)
+    if d == 2:
+        return torch.cat([P[:1], z, P[1:2]], 0)
+    if d == 3:
+        return P
+    if d == 4:
+        return P[:3] / P[3:4]
+    raise ValueError("Improper coordinate dimension.")
+
+
+def _stride5(sz):
+    """[1; cumprod(sz(1:end-1))] .* (sz ~= 1)   (kern/das_spec.m:259-260)."""
+    st, acc = [], 1
+    for s in sz:
+        st.append(acc if s != 1 else 0)
+        acc *= s
+    return st
+
+
+def das_spec(fun, Pi, Pr, Pv, Nv, x, t0, fs=None, c=1540.0, *varargin, _path=_lib.PATH_AUTO, _y_f32=False):
+    """Specialised delay-and-sum beamformer — mirror of ``kern/das_spec.m:1``.
+
+    fun in {'DAS','SYN','MUL','BF','delays'}; options (strings, as the reference :113-148):
+    'plane-waves' | 'virtual-source' | 'diverging-waves' | 'focused-waves' |
+    'input-precision', {'single','double','halfT'} | 'device', d | 'interp', method |
+    'apod', A (repeatable) | 'modulation', fmod | 'transpose', tf.
+    Returns I1 x I2 x I3 x [1|N] x [1|M] x F x ...
+    """
+    if fun not in ("DAS", "SYN", "BF", "MUL", "delays"):
+        raise ValueError("Invalid beamformer.")
+    VS, DV, interp_type, apod, fmod, tpose, device = True, False, "linear", [], 0.0, False, -1
+    xt = _as_tensor(x) if x is not None else torch.zeros((0,))
+    if xt.dtype in (torch.float64, torch.complex128):
+        prec = "double"
+    elif xt.dtype in (torch.float16,):
+        prec = "halfT"
+    else:
+        prec = "single" if xt.dtype in (torch.float32, torch.complex64) else "double"
+    n, args = 0, list(varargin)
+    while n < len(args):
+        o = args[n]
+        if o == "plane-waves": VS = False
+        elif o == "virtual-source": VS = True
+        elif o == "diverging-waves": DV = True
+        elif o == "focused-waves": DV = False
+        elif o == "input-precision": n += 1; prec = str(args[n])
+        elif o == "device": n += 1; device = int(args[n])
+        elif o == "interp": n += 1; interp_type = str(args[n])
+        elif o == "apod": n += 1; apod.append(args[n])
+        elif o == "modulation": n += 1; fmod = float(args[n])
+        elif o == "transpose": n += 1; tpose = bool(args[n])
+        else:
+            raise ValueError("Unrecognized option")
+        n += 1
+    if prec not in _DT:
+        raise ValueError(f"unknown input-precision {prec!r}")
+    if device == 0:
+        raise QupsError(-3, "qups_b200 implements only the GPU branch of das_spec; 'device', 0 (native interp1) "
+                            "is the reference's own CPU path")
+    if interp_type not in _lib.INTERP:  # QUPS:das_spec:UnrecognizedInput  (kern/das_spec.m:203-207)
+        raise ValueError(f"Unrecognized interpolation of type {interp_type}: must be one of "
+                         "{'nearest', 'linear', 'cubic', 'lanczos3'}.")
+    if fs is None:
+        if fun == "delays":
+            fs = 1.0
+        else:
+            t0a = np.asarray(t0, dtype=np.float64).reshape(-1)
+            if t0a.size < 2:
+                raise ValueError("Undefined sampling rate.")
+            fs, t0 = float(np.mean(np.diff(t0a))), float(t0a.min())
+    numpy_out = not any(isinstance(v, torch.Tensor) and v.is_cuda for v in (Pi, Pr, Pv, Nv, x))
+    dev = torch.device("cuda", torch.cuda.current_device() if device < 0 else device - 1)
+    L = _lib.lib()
+    rt = _RT[prec]
+
+    Pi_t, Pr_t, Pv_t, Nv_t = (_mod_size(_as_tensor(P)) for P in (Pi, Pr, Pv, Nv))
+    Pi_t = Pi_t.reshape(tuple(Pi_t.shape) + (1,) * (4 - Pi_t.ndim))
+    Isz = tuple(int(s) for s in Pi_t.shape[1:4])
+    I = Isz[0] * Isz[1] * Isz[2]
+    if fun == "delays":
+        T = 0
+        N = Pr_t.shape[1]
+        M = max(Pv_t.shape[1], Nv_t.shape[1])
+        fsz = ()
+    else:
+        xs = tuple(xt.shape) + (1,) * (3 - xt.ndim)
+        T, d2, d3 = xs[:3]
+        N, M = (d3, d2) if tpose else (d2, d3)
+        fsz = tuple(xs[3:])
+    F = int(np.prod(fsz)) if fsz else 1
+    # expand_inputs (kern/das_spec.m:602-670)
+    if Pv_t.shape[1] == 1: Pv_t = Pv_t.expand(Pv_t.shape[0], M)
+    if Nv_t.shape[1] == 1: Nv_t = Nv_t.expand(Nv_t.shape[0], M)
+    if Pr_t.shape[1] == 1: Pr_t = Pr_t.expand(Pr_t.shape[0], N)
+    if not (Pv_t.shape[1] == M and Nv_t.shape[1] == M):
+        raise AssertionError("Inconsistent transmitter data size.")
+    if Pr_t.shape[1] != N:
+        raise AssertionError("Inconsistent receiver data size.")
+    cinv_t = 1.0 / _as_tensor(np.asarray(c) if not isinstance(c, torch.Tensor) else c).to(rt)  # cinv = 1./c  (:170)
+    csz = tuple(cinv_t.shape) + (1,) * (5 - cinv_t.ndim)
+    full = Isz + (N, M)
+    if not all(csz[d] in (1, full[d]) for d in range(3)):
+        raise AssertionError("Sound speed data size inconsistent with pixel data size")
+    if csz[3] not in (1, N): raise AssertionError("Sound speed data size inconsistent with receiver data size")
+    if csz[4] not in (1, M): raise AssertionError("Sound speed data size inconsistent with transmit data size")
+    apod_t = [_as_tensor(a) for a in apod]
+    apod_real = all(not a.is_complex() for a in apod_t)
+    asz = []
+    for a in apod_t:
+        s = tuple(a.shape) + (1,) * (5 - a.ndim)
+        if len(s) > 5 or not all(s[d] in (1, full[d]) for d in range(3)):
+            raise AssertionError("Apodization data size inconsistent with pixel data size")
+        if s[3] not in (1, N): raise AssertionError("Apodization data size inconsistent with receiver data size")
+        if s[4] not in (1, M): raise AssertionError("Apodization data size inconsistent with transmit data size")
+        asz.append(s)
+    S = len(apod_t)
+
+    # device buffers (column-major)
+    # pixels: keep (d, I1, I2, I3) logical shape -> column-major buffer is 3 x I with I1 fastest
+    dPi = _colmajor(_mod_dim(Pi_t), rt, dev)
+    dPr = _colmajor(_mod_dim(Pr_t), rt, dev)
+    dNv = _colmajor(_mod_dim(Nv_t), rt, dev)
+    Pv3 = _mod_dim(Pv_t).to(rt)
+    t0v = _as_tensor(np.asarray(t0, dtype=np.float64) if not isinstance(t0, torch.Tensor) else t0).reshape(-1).to(rt)
+    if t0v.numel() not in (1, M):
+        raise AssertionError("t0 must be a scalar or have one entry per transmit")
+    Pv4 = torch.cat([Pv3, t0v.to(Pv3.device).expand(M).reshape(1, M)], 0)  # Pv(4,:) = t0   (:361)
+    dPv = _colmajor(Pv4, rt, dev)
+    dC = _colmajor(cinv_t.reshape(csz), rt, dev)
+    if S:
+        if prec == "halfT":
+            parts = [(_cplx_buf(a.reshape(s), prec, dev).reshape(-1) if not apod_real else
+                      _colmajor(a.reshape(s), torch.float16, dev).reshape(-1)) for a, s in zip(apod_t, asz)]
+        else:
+            parts = [(_colmajor(a.reshape(s), rt, dev) if apod_real else _cplx_buf(a.reshape(s), prec, dev)).reshape(-1)
+                     for a, s in zip(apod_t, asz)]
+        dA = torch.cat(parts)
+    else:
+        dA = None
+    # [cstride, astride]   (kern/das_spec.m:256-260)
+    acs = _stride5(csz) + [0]
+    base = 0
+    for s in asz:
+        acs += _stride5(s) + [base]
+        base += int(np.prod(s))
+    acs_c = (C.c_uint64 * len(acs))(*acs)
+
+    p = DasParams()
+    p.struct_size = C.sizeof(DasParams)
+    p.dtype = _DT[prec]
+    p.I1, p.I2, p.I3 = Isz
+    p.N, p.M, p.T, p.F, p.S = N, M, T, F, S
+    keep_rx, keep_tx = fun in ("SYN", "BF"), fun in ("MUL", "BF")
+    p.flag = _lib.INTERP[interp_type] + 8 * keep_rx + 16 * keep_tx + 32 * tpose  # :209-213
+    p.vs, p.dv = int(VS), int(DV)
+    p.apod_real, p.y_f32, p.path = int(apod_real), int(_y_f32), int(_path)
+    p.fs, p.fmod = float(fs), float(fmod)
+    st = _stream(dev)
+
+    with torch.cuda.device(dev):
+        if fun == "delays":
+            tau = torch.empty(I * N * M, dtype=rt, device=dev)
+            _lib.check(L.qups_delays(C.byref(p), _ptr(tau), _ptr(dPi), _ptr(dPr), _ptr(dPv), _ptr(dNv), _ptr(dC),
+                                     acs_c, st))
+            y = _from_colmajor(tau, Isz + (N, M))
+        else:
+            dX = _cplx_buf(xt.reshape(xs[:3] + (F,)), prec, dev)
+            On, Om = (N if keep_rx else 1), (M if keep_tx else 1)
+            if prec == "halfT" and not _y_f32:
+                yb = torch.empty((F * Om * On * I, 2), dtype=torch.float16, device=dev)
+            else:
+                yb = torch.empty(F * Om * On * I, dtype=torch.complex64 if prec != "double" else torch.complex128, device=dev)
+            _lib.check(L.qups_das(C.byref(p), _ptr(yb), _ptr(dPi), _ptr(dPr), _ptr(dPv), _ptr(dNv), _ptr(dA), _ptr(dC),
+                                  acs_c, _ptr(dX), st))
+            if yb.dtype == torch.float16:
+                yb = torch.view_as_complex(yb.float())
+            y = _from_colmajor(yb, Isz + (On, Om) + (fsz if fsz else ()))
+    if numpy_out:
+        return np.asfortranarray(y.cpu().numpy())
+    return y
+
+
+def _sz(t, nd):
+    return tuple(t.shape) + (1,) * (nd - t.ndim)
+
+
+def _swapdim(t, a, b):
+    nd = max(t.ndim, a + 1, b + 1)
+    t = t.reshape(_sz(t, nd))
+    return t.transpose(a, b) if a != b else t
+
+
+def wsinterpd2(x, t1, t2, dim=1, w=1, sdim=(), interp="linear", extrapval=0, omega=0):
+    """Weighted-sum interpolation with separable delays — mirror of ``kern/wsinterpd2.m:1``.
+
+    y = sum_{sdim} w .* exp(omega .* (t1+t2)) .* interp1(x, 1 + t1 + t2, interp, 0)
+    `dim`/`sdim` are 1-based as in MATLAB.  Only extrapval = 0 (what every hot-path caller passes:
+    src/ChannelData.m:1445, src/UltrasoundSystem.m:843) is implemented.
+    """
+    if interp not in _lib.INTERP:
+        raise ValueError("Interp option not recognized: " + str(interp))
+    if not (extrapval == 0):
+        raise QupsError(-3, "qups_b200.wsinterpd2 implements extrapval = 0 only")
+    if np.real(omega) != 0:
+        raise QupsError(-3, "real(omega) ~= 0 is handled by the reference's native path only (kern/wsinterpd2.m:101)")
+    xt, t1t = _as_tensor(x), _as_tensor(t1)
+    t2t = _as_tensor(t2) if t2 is not None else None
+    wt = _as_tensor(np.asarray(w)) if not isinstance(w, torch.Tensor) else w
+    if t1t.is_complex() or (t2t is not None and t2t.is_complex()):
+        raise AssertionError("Sample indices must be real.")
+    numpy_out = not any(isinstance(v, torch.Tensor) and v.is_cuda for v in (x, t1, t2, w))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    prec = "double" if xt.dtype in (torch.float64, torch.complex128) else "single"
+    rt, ct = _RT[prec], _CT[prec]
+    d0 = dim - 1
+    sd = [s - 1 for s in (sdim if np.ndim(sdim) else [sdim])]
+    sd = [d0 if s == 0 else (0 if s == d0 else s) for s in sd]  # swap with the moved dim (:67)
+    nd = max(xt.ndim, t1t.ndim, t2t.ndim if t2t is not None else 1, wt.ndim, dim, max(sd, default=0) + 1)
+    xt, t1t, wt = (_swapdim(v, d0, 0) for v in (xt, t1t, wt))
+    nd = max(nd, xt.ndim, t1t.ndim, wt.ndim)
+    xs, s1, ws = _sz(xt, nd), _sz(t1t, nd), _sz(wt, nd)
+    if t2t is not None:
+        t2t = _swapdim(t2t, d0, 0)
+        s2 = _sz(t2t, nd)
+    else:
+        s2 = (1,) * nd
+    T = xs[0]
+    dsz = [max(s1[0], s2[0])] + [max(s1[k], s2[k], xs[k]) for k in range(1, nd)]
+    for k in range(nd):
+        for nm, s in (("t1", s1), ("t2", s2), ("w", ws)) + ((("x", xs),) if k else ()):
+            if s[k] not in (1, dsz[k]):
+                raise AssertionError(f"size of {nm} incompatible in dim {k + 1}")
+    osz = [1 if k in sd else dsz[k] for k in range(nd)]
+    if nd > 8:
+        raise QupsError(-3, "at most 8 dims")
+    strides = [_stride5(ws), _stride5(osz), _stride5(s1), _stride5(s2), _stride5((1,) + tuple(xs[1:]))]
+    p = Ws2Params()
+    p.struct_size = C.sizeof(Ws2Params)
+    p.dtype = _DT[prec]
+    p.T, p.D, p.interp = T, nd, _lib.INTERP[interp]
+    w_real = not wt.is_complex()
+    p.w_real = int(w_real)
+    p.omega = float(np.imag(omega))
+    for k in range(nd):
+        p.sizes[k] = dsz[k]
+        for r in range(5):
+            p.dstride[r + 5 * k] = strides[r][k]
+    dX = _cplx_buf(xt.reshape(xs), prec, dev)
+    d1 = _colmajor(t1t.reshape(s1), rt, dev)
+    d2 = _colmajor(t2t.reshape(s2), rt, dev) if t2t is not None else None
+    dW = _colmajor(wt.reshape(ws), rt, dev) if w_real else _cplx_buf(wt.reshape(ws), prec, dev)
+    yb = torch.zeros(int(np.prod(osz)), dtype=ct, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().qups_wsinterpd2(C.byref(p), _ptr(yb), _ptr(dW), _ptr(dX), _ptr(d1), _ptr(d2), _stream(dev)))
+    y = _swapdim(_from_colmajor(yb, osz), 0, d0)
+    return np.asfortranarray(y.cpu().numpy()) if numpy_out else y
+
+
+def wsinterpd(x, t, dim=1, w=1, sdim=(), interp="linear", extrapval=0, omega=0):
+    """Mirror of ``kern/wsinterpd.m:1`` (single delay table)."""
+    return wsinterpd2(x, t, None, dim, w, sdim, interp, extrapval, omega)
