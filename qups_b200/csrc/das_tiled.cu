@@ -41,7 +41,8 @@ constexpr int kThreads = (kCW + 1) * 32;
 constexpr int kTA = 32;        // tile extent along the lane axis
 constexpr int kTB = kCW * kR;  // tile extent along the row axis
 
-enum { TR_FAST = 0, TR_SKIP = 1, TR_SLOW = 2 };
+enum { TR_FAST = 0, TR_SKIP = 1, TR_SLOW = 2, TR_EDGE = 3 };   // per (n,m) trace
+enum { ST_MIXED = 0, ST_ALL_FAST = 1, ST_ALL_SKIP = 2 };        // per stage of kNT traces
 
 struct TiledArgs {
     const float *Pi, *Pr, *Pv4, *Nv, *cinv;
@@ -101,25 +102,25 @@ __device__ __forceinline__ int f2o(float f) {
 }
 __device__ __forceinline__ float o2f(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7fffffff)); }
 
-// ---- inner bodies: one (pixel, trace) pair from the staged window -------------
+// ---- inner bodies ---------------------------------------------------------------
 // xq = 1-based sample position (bit-identical to the oracle); soff = shared
 // address such that the first tap of index k = floor(xq) is at soff + 8*k.
+__device__ __forceinline__ void cubic_weights(float u, float &w0, float &w1, float &w2, float &w3) {
+    // Keys cubic convolution a = -1/2 (interior identical to interp1 'cubic', R2020b+), 1/2 folded in
+    const float u2 = u * u;
+    w0 = fmaf(fmaf(-0.5f, u, 1.0f), u, -0.5f) * u;
+    w1 = fmaf(fmaf(1.5f, u, -2.5f), u2, 1.0f);
+    w2 = fmaf(fmaf(-1.5f, u, 2.0f), u, 0.5f) * u;
+    w3 = fmaf(0.5f, u, -0.5f) * u2;
+}
 template <int INTERP> __device__ __forceinline__ void fast_pair(float xq, uint32_t soff, float &ar, float &ai) {
     if (INTERP == 2) {
         const float kf = floorf(xq);
         const float u = xq - kf; // exact
         const uint32_t addr = soff + ((uint32_t)__float2int_rz(kf) << 3);
         const float2 v0 = lds64(addr), v1 = lds64(addr + 8), v2 = lds64(addr + 16), v3 = lds64(addr + 24);
-        // Keys cubic convolution a = -1/2 (interior identical to interp1 'cubic', R2020b+)
-        const float u2 = u * u;
-        float t0 = fmaf(-0.5f, u, 1.0f);
-        t0 = fmaf(t0, u, -0.5f);
-        const float w0 = t0 * u;
-        const float w1 = fmaf(fmaf(1.5f, u, -2.5f), u2, 1.0f);
-        float t2 = fmaf(-1.5f, u, 2.0f);
-        t2 = fmaf(t2, u, 0.5f);
-        const float w2 = t2 * u;
-        const float w3 = fmaf(0.5f, u, -0.5f) * u2;
+        float w0, w1, w2, w3;
+        cubic_weights(u, w0, w1, w2, w3);
         ar = fmaf(w0, v0.x, ar); ai = fmaf(w0, v0.y, ai);
         ar = fmaf(w1, v1.x, ar); ai = fmaf(w1, v1.y, ai);
         ar = fmaf(w2, v2.x, ar); ai = fmaf(w2, v2.y, ai);
@@ -141,6 +142,48 @@ template <int INTERP> __device__ __forceinline__ void fast_pair(float xq, uint32
     }
 }
 
+// Two pixel rows of one thread against one staged trace.  The delay sequence stays SCALAR with
+// explicit _rn intrinsics: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (observed in SASS),
+// which would break bit-identity of xq with the oracle; scalar mul.rn/add.rn are never contracted.
+// The interpolation weights (tolerance-level arithmetic) use packed fp32x2 FFMA2/FMUL2 (sm_100).
+struct Pack2 {
+    float2 dv;
+    float cinv, t0, fs;
+};
+template <int INTERP>
+__device__ __forceinline__ void fast_pair2(const Pack2 &c, float2 dr, uint32_t soff, float2 &acc0, float2 &acc1) {
+    float2 xq;
+    xq.x = sample_pos(c.dv.x, dr.x, c.cinv, c.t0, c.fs);
+    xq.y = sample_pos(c.dv.y, dr.y, c.cinv, c.t0, c.fs);
+    if (INTERP == 2) {
+        const float2 kf = make_float2(floorf(xq.x), floorf(xq.y));
+        const float2 u = __ffma2_rn(kf, make_float2(-1.f, -1.f), xq); // exact
+        const uint32_t a0 = soff + ((uint32_t)__float2int_rz(kf.x) << 3);
+        const uint32_t a1 = soff + ((uint32_t)__float2int_rz(kf.y) << 3);
+        const float2 p0 = lds64(a0), p1 = lds64(a0 + 8), p2 = lds64(a0 + 16), p3 = lds64(a0 + 24);
+        const float2 q0 = lds64(a1), q1 = lds64(a1 + 8), q2 = lds64(a1 + 16), q3 = lds64(a1 + 24);
+        const float2 u2 = __fmul2_rn(u, u);
+        const float2 w0 = __fmul2_rn(__ffma2_rn(__ffma2_rn(make_float2(-0.5f, -0.5f), u, make_float2(1.f, 1.f)), u,
+                                                make_float2(-0.5f, -0.5f)), u);
+        const float2 w1 = __ffma2_rn(__ffma2_rn(make_float2(1.5f, 1.5f), u, make_float2(-2.5f, -2.5f)), u2,
+                                     make_float2(1.f, 1.f));
+        const float2 w2 = __fmul2_rn(__ffma2_rn(__ffma2_rn(make_float2(-1.5f, -1.5f), u, make_float2(2.f, 2.f)), u,
+                                                make_float2(0.5f, 0.5f)), u);
+        const float2 w3 = __fmul2_rn(__ffma2_rn(make_float2(0.5f, 0.5f), u, make_float2(-0.5f, -0.5f)), u2);
+        acc0.x = fmaf(w0.x, p0.x, acc0.x); acc0.y = fmaf(w0.x, p0.y, acc0.y);
+        acc1.x = fmaf(w0.y, q0.x, acc1.x); acc1.y = fmaf(w0.y, q0.y, acc1.y);
+        acc0.x = fmaf(w1.x, p1.x, acc0.x); acc0.y = fmaf(w1.x, p1.y, acc0.y);
+        acc1.x = fmaf(w1.y, q1.x, acc1.x); acc1.y = fmaf(w1.y, q1.y, acc1.y);
+        acc0.x = fmaf(w2.x, p2.x, acc0.x); acc0.y = fmaf(w2.x, p2.y, acc0.y);
+        acc1.x = fmaf(w2.y, q2.x, acc1.x); acc1.y = fmaf(w2.y, q2.y, acc1.y);
+        acc0.x = fmaf(w3.x, p3.x, acc0.x); acc0.y = fmaf(w3.x, p3.y, acc0.y);
+        acc1.x = fmaf(w3.y, q3.x, acc1.x); acc1.y = fmaf(w3.y, q3.y, acc1.y);
+    } else {
+        fast_pair<INTERP>(xq.x, soff, acc0.x, acc0.y);
+        fast_pair<INTERP>(xq.y, soff, acc1.x, acc1.y);
+    }
+}
+
 // full-semantics slow path (edges, oversize windows, NaN): straight from global memory
 __device__ __noinline__ void slow_pair(const float2 *trace, uint32_t T, float xq, int interp, float &ar, float &ai) {
     const cplx<float> v = interp1<float2>(trace, (long)T, xq, interp);
@@ -148,15 +191,23 @@ __device__ __noinline__ void slow_pair(const float2 *trace, uint32_t T, float xq
     ai += v.im;
 }
 
+// may the unchecked gather be used for this sample position?
+template <int INTERP> __device__ __forceinline__ bool interior(float xq, float Tf) {
+    if (INTERP == 2) return (xq >= 2.0f) && (xq < Tf - 1.0f); // taps k-1..k+2 are real samples
+    if (INTERP == 1) return (xq >= 1.0f) && (xq < Tf);
+    return (xq >= 1.0f) && (xq <= Tf);
+}
+
 template <int INTERP>
 __global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs a) {
+    static_assert(kR == 2, "the packed fp32x2 inner loop assumes two pixel rows per thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [0,64) full/empty mbarriers | desc[kStages][kNT] int2 | allfast[kStages] |
+    // layout: [0,64) full/empty mbarriers | desc[kStages][kNT] int2 | stage_kind[kStages] |
     //         dvmin[M] dvmax[M] drmin[N] drmax[N] (ordered ints) | 128B-aligned stage ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     int2 *desc = reinterpret_cast<int2 *>(smem_raw + 64);
-    int *allfast = reinterpret_cast<int *>(smem_raw + 64 + sizeof(int2) * kStages * kNT);
-    int *s_dvmin = allfast + kStages;
+    int *stage_kind = reinterpret_cast<int *>(smem_raw + 64 + sizeof(int2) * kStages * kNT);
+    int *s_dvmin = stage_kind + kStages;
     int *s_dvmax = s_dvmin + a.M;
     int *s_drmin = s_dvmax + a.M;
     int *s_drmax = s_drmin + a.N;
@@ -185,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs 
 
     const float cinv = __ldg(a.cinv);
     const float fs = a.fs;
+    const float Tf = (float)a.T;
     const bool VS = a.VS, DV = a.DV;
 
     if (warp < kCW) {
@@ -234,50 +286,61 @@ __global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs 
         __syncthreads();
 
         // ---- phase 1: main loop -----------------------------------------------------------
-        float ar[kR], ai[kR];
-#pragma unroll
-        for (int r = 0; r < kR; ++r) { ar[r] = 0.f; ai[r] = 0.f; }
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        Pack2 pk;
+        pk.cinv = cinv;
+        pk.fs = fs;
         uint32_t it = 0;
         for (uint32_t nt = 0; nt < a.numNT; ++nt) {
-            float dr[kR][kNT];
+            float2 dr[kNT]; // .x = pixel row 0, .y = pixel row 1
 #pragma unroll
             for (int j = 0; j < kNT; ++j) {
                 const uint32_t n = min(nt * kNT + j, a.N - 1);
                 const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
-#pragma unroll
-                for (int r = 0; r < kR; ++r) dr[r][j] = rx_dist(px[r], py[r], pz[r], rx, ry, rz);
+                dr[j].x = rx_dist(px[0], py[0], pz[0], rx, ry, rz);
+                dr[j].y = rx_dist(px[1], py[1], pz[1], rx, ry, rz);
             }
+            // transmit parameters are prefetched one iteration ahead (hides the L1/L2 latency)
+            float4 pv_n = __ldg(reinterpret_cast<const float4 *>(a.Pv4));
+            float nx_n = __ldg(a.Nv), ny_n = __ldg(a.Nv + 1), nz_n = __ldg(a.Nv + 2);
             for (uint32_t m = 0; m < a.M; ++m, ++it) {
-                const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
-                const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
-                float dv[kR];
-#pragma unroll
-                for (int r = 0; r < kR; ++r) dv[r] = tx_dist(px[r], py[r], pz[r], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
-                const float t0m = pv.w;
+                const float4 pv = pv_n;
+                const float nx = nx_n, ny = ny_n, nz = nz_n;
+                const uint32_t mn = min(m + 1, a.M - 1);
+                pv_n = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + mn);
+                nx_n = __ldg(a.Nv + 3 * mn); ny_n = __ldg(a.Nv + 3 * mn + 1); nz_n = __ldg(a.Nv + 3 * mn + 2);
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                 mbar_wait(bar_full + 8 * s, ph);
-                const int2 *dsc = desc + s * kNT;
-                if (allfast[s]) {
+                const int kind = stage_kind[s];
+                if (kind != ST_ALL_SKIP) {
+                    pk.dv.x = tx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+                    pk.dv.y = tx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+                    const float t0m = pv.w;
+                    pk.t0 = t0m;
+                    const int2 *dsc = desc + s * kNT;
+                    if (kind == ST_ALL_FAST) {
 #pragma unroll
-                    for (int j = 0; j < kNT; ++j) {
-                        const uint32_t soff = (uint32_t)dsc[j].x;
-#pragma unroll
-                        for (int r = 0; r < kR; ++r)
-                            fast_pair<INTERP>(sample_pos(dv[r], dr[r][j], cinv, t0m, fs), soff, ar[r], ai[r]);
-                    }
-                } else {
+                        for (int j = 0; j < kNT; ++j)
+                            fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, acc0, acc1);
+                    } else {
 #pragma unroll 1
-                    for (int j = 0; j < kNT; ++j) {
-                        const int2 d = dsc[j];
-                        if (d.y == TR_SKIP) continue;
-                        const uint32_t n = nt * kNT + j;
-                        const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
-                        const uint64_t nm = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
-#pragma unroll
-                        for (int r = 0; r < kR; ++r) {
-                            const float xq = sample_pos(dv[r], rx_dist(px[r], py[r], pz[r], rx, ry, rz), cinv, t0m, fs);
-                            if (d.y == TR_FAST) fast_pair<INTERP>(xq, (uint32_t)d.x, ar[r], ai[r]);
-                            else slow_pair(a.x + nm * a.T, a.T, xq, INTERP, ar[r], ai[r]);
+                        for (int j = 0; j < kNT; ++j) {
+                            const int2 d = dsc[j];
+                            if (d.y == TR_SKIP) continue;
+                            const uint32_t n = nt * kNT + j;
+                            const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
+                            const uint64_t nm = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
+                            const float xq0 = sample_pos(pk.dv.x, rx_dist(px[0], py[0], pz[0], rx, ry, rz), cinv, t0m, fs);
+                            const float xq1 = sample_pos(pk.dv.y, rx_dist(px[1], py[1], pz[1], rx, ry, rz), cinv, t0m, fs);
+                            // FAST: window proven; EDGE: window holds every interior tap, the rest goes the slow way
+                            if (d.y == TR_FAST || (d.y == TR_EDGE && interior<INTERP>(xq0, Tf)))
+                                fast_pair<INTERP>(xq0, (uint32_t)d.x, acc0.x, acc0.y);
+                            else if (d.y == TR_SLOW || (xq0 >= 1.0f && xq0 <= Tf))
+                                slow_pair(a.x + nm * a.T, a.T, xq0, INTERP, acc0.x, acc0.y);
+                            if (d.y == TR_FAST || (d.y == TR_EDGE && interior<INTERP>(xq1, Tf)))
+                                fast_pair<INTERP>(xq1, (uint32_t)d.x, acc1.x, acc1.y);
+                            else if (d.y == TR_SLOW || (xq1 >= 1.0f && xq1 <= Tf))
+                                slow_pair(a.x + nm * a.T, a.T, xq1, INTERP, acc1.x, acc1.y);
                         }
                     }
                 }
@@ -285,14 +348,12 @@ __global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs 
                 if (lane == 0) mbar_arrive(bar_empty + 8 * s);
             }
         }
-#pragma unroll
-        for (int r = 0; r < kR; ++r)
-            if (valid[r]) a.y[pix[r]] = make_float2(ar[r], ai[r]);
+        if (valid[0]) a.y[pix[0]] = acc0;
+        if (valid[1]) a.y[pix[1]] = acc1;
     } else {
         // =========================== producer warp =================================
         __syncthreads(); // matches the consumers' post-phase-0 barrier
         const bool cinv_ok = (cinv > 0.f) && (fs > 0.f);
-        const float Tf = (float)a.T;
         uint32_t it = 0;
         for (uint32_t nt = 0; nt < a.numNT; ++nt) {
             const uint32_t n = nt * kNT + lane;
@@ -313,34 +374,28 @@ __global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs 
                         if (xhi < 1.0f || xlo > Tf) {
                             flag = TR_SKIP; // every pixel of the tile is outside the trace: contributes 0
                         } else {
-                            // in-range test for the unchecked inner loop, and tap span per method
-                            bool inr;
+                            // every delay operation is monotone and individually rounded, so all tap
+                            // indices of the tile lie in [k(xlo), k(xhi)]; clip to the trace for EDGE
+                            const bool inr = interior<INTERP>(xlo, Tf) && interior<INTERP>(xhi, Tf);
+                            const float xl = fmaxf(xlo, 1.0f), xh = fminf(xhi, Tf);
                             int klo, khi, tap0, tap1;
-                            if (INTERP == 2) {        // taps k-1..k+2 (1-based) must all be real samples
-                                inr = (xlo >= 2.0f) && (xhi < Tf - 1.0f);
-                                klo = (int)floorf(xlo); khi = (int)floorf(xhi); tap0 = 2; tap1 = 1;
-                            } else if (INTERP == 1) { // taps k, k+1
-                                inr = (xlo >= 1.0f) && (xhi < Tf);
-                                klo = (int)floorf(xlo); khi = (int)floorf(xhi); tap0 = 1; tap1 = 0;
-                            } else {                  // tap round(xq)
-                                inr = (xlo >= 1.0f) && (xhi <= Tf);
-                                klo = (int)floorf(__fadd_rn(xlo, 0.5f)); khi = (int)floorf(__fadd_rn(xhi, 0.5f));
-                                tap0 = 1; tap1 = -1;
-                            }
-                            if (inr) {
-                                const uint64_t tr = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
-                                const int64_t abs_lo = (int64_t)(tr * a.T) + (klo - tap0); // 0-based first tap, absolute
-                                const int64_t abs_al = abs_lo & ~(int64_t)1;                // 16-byte aligned element
-                                const int w0 = (klo - tap0) - (int)(abs_lo - abs_al);
-                                int wlen = (khi + tap1) - w0 + 1;
-                                wlen = (wlen + 1) & ~1;
-                                if (wlen <= (int)a.wmax && abs_al >= 0 && (uint64_t)(abs_al + wlen) <= a.total_elems) {
-                                    flag = TR_FAST;
-                                    bytes = (uint32_t)wlen * 8u;
-                                    dst = ring + (s * kNT + lane) * a.wmax * 8u;
-                                    soff = dst - (uint32_t)(w0 + tap0) * 8u;
-                                    src = a.x + abs_al;
-                                }
+                            if (INTERP == 2)      { klo = (int)floorf(xl); khi = (int)floorf(xh); tap0 = 2; tap1 = 1; }
+                            else if (INTERP == 1) { klo = (int)floorf(xl); khi = (int)floorf(xh); tap0 = 1; tap1 = 0; }
+                            else { klo = (int)floorf(__fadd_rn(xl, 0.5f)); khi = (int)floorf(__fadd_rn(xh, 0.5f)); tap0 = 1; tap1 = -1; }
+                            int t_lo = klo - tap0, t_hi = khi + tap1; // 0-based first / last tap
+                            if (!inr) { t_lo = max(t_lo, 0); t_hi = min(t_hi, (int)a.T - 1); }
+                            const uint64_t tr = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
+                            const int64_t abs_lo = (int64_t)(tr * a.T) + t_lo;
+                            const int64_t abs_al = abs_lo & ~(int64_t)1; // 16-byte aligned element
+                            const int w0 = t_lo - (int)(abs_lo - abs_al);
+                            int wlen = t_hi - w0 + 1;
+                            wlen = (wlen + 1) & ~1;
+                            if (wlen > 0 && wlen <= (int)a.wmax && abs_al >= 0 && (uint64_t)(abs_al + wlen) <= a.total_elems) {
+                                flag = inr ? TR_FAST : TR_EDGE;
+                                bytes = (uint32_t)wlen * 8u;
+                                dst = ring + (s * kNT + lane) * a.wmax * 8u;
+                                soff = dst - (uint32_t)(w0 + tap0) * 8u;
+                                src = a.x + abs_al;
                             }
                         }
                     }
@@ -348,14 +403,15 @@ __global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs 
                 mbar_wait(bar_empty + 8 * s, ph ^ 1); // slot free (first lap passes immediately)
                 if (lane < kNT) desc[s * kNT + lane] = make_int2((int)soff, flag);
                 const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
-                const bool all = __all_sync(0xffffffffu, flag == TR_FAST || lane >= kNT);
+                const bool all_fast = __all_sync(0xffffffffu, flag == TR_FAST || lane >= kNT);
+                const bool all_skip = __all_sync(0xffffffffu, flag == TR_SKIP || lane >= kNT);
                 __syncwarp();
                 if (lane == 0) {
-                    allfast[s] = all ? 1 : 0;
+                    stage_kind[s] = all_fast ? ST_ALL_FAST : (all_skip ? ST_ALL_SKIP : ST_MIXED);
                     mbar_arrive_expect_tx(bar_full + 8 * s, total);
                 }
                 __syncwarp();
-                if (flag == TR_FAST) bulk_g2s(dst, src, bytes, bar_full + 8 * s);
+                if (bytes) bulk_g2s(dst, src, bytes, bar_full + 8 * s);
             }
         }
     }

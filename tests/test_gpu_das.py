@@ -1,0 +1,205 @@
+"""GPU parity tests (run with -m gpu on the B200 box): CUDA DAS through the C ABI vs the CPU oracle.
+
+Bars (BASELINE.json north_star): bit-exact for nearest-neighbour indexing, <= 1e-5 relative L-inf vs the fp32
+oracle (kern/das_spec.m CPU semantics) for linear / cubic; the generic kernel is bit-exact for everything.
+"""
+import numpy as np
+import pytest
+
+from tests.util import small_problem, oracle_kwargs, rel_linf
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # relative L-inf vs max|b|, stated in BASELINE.json
+
+
+def _gpu(fun, P, interp, path, extra=(), x=None, t0=None, c=None, **kw):
+    import qups_b200
+    from qups_b200 import _lib
+    pth = {"generic": _lib.PATH_GENERIC, "tiled": _lib.PATH_TILED, "auto": _lib.PATH_AUTO}[path]
+    f32 = np.float32
+    out = qups_b200.das_spec(fun, P["Pi"].astype(f32), P["Pr"].astype(f32), P["Pv"].astype(f32), P["Nv"].astype(f32),
+                             P["x"] if x is None else x, P["t0"] if t0 is None else t0, P["fs"],
+                             P["c"] if c is None else c, *P["opts"], "interp", interp, *extra, _path=pth, **kw)
+    return out
+
+
+def _ora(oracle_c, fun, P, interp, x=None, t0=None, c=None, **kw):
+    okw = oracle_kwargs(P["opts"])
+    okw.update(kw)
+    xx = P["x"] if x is None else x
+    ref = oracle_c.das_spec(fun, P["Pi"], P["Pr"], P["Pv"], P["Nv"], xx,
+                            P["t0"] if t0 is None else t0, P["fs"], P["c"] if c is None else c, interp=interp, **okw)
+    if fun != "delays" and xx.ndim == 3:
+        ref = ref[..., 0]  # MATLAB drops the trailing singleton frame dim
+    return ref
+
+
+@pytest.mark.parametrize("kind", ["FC", "PW", "FSA", "DV"])
+@pytest.mark.parametrize("fun", ["DAS", "SYN", "MUL", "BF", "delays"])
+def test_generic_bitexact_all_funs(oracle_c, kind, fun):
+    P = small_problem(kind, nz=19, nx=13, N=7, M=5, T=150)
+    for interp in ("nearest", "linear", "cubic"):
+        ref = _ora(oracle_c, fun, P, interp)
+        got = _gpu(fun, P, interp, "generic")
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref), (fun, kind, interp, rel_linf(got, ref))
+
+
+def test_generic_lanczos3_close(oracle_c):
+    P = small_problem("FC", nz=19, nx=13, N=7, M=5, T=150)
+    ref = _ora(oracle_c, "DAS", P, "lanczos3")
+    got = _gpu("DAS", P, "lanczos3", "generic")
+    assert rel_linf(got, ref) < 1e-5
+
+
+def test_generic_apod_cinv_t0_frames_transpose(oracle_c):
+    P = small_problem("FC", nz=11, nx=9, ny=2, N=6, M=4, T=150, F=3)
+    rng = np.random.default_rng(3)
+    Isz = P["Pi"].shape[1:]
+    apods = [rng.uniform(0, 1, Isz + (6, 1)).astype(np.float32), rng.uniform(0, 1, (1, 1, 1, 1, 4)).astype(np.float32),
+             (rng.uniform(0, 1, (Isz[0], 1, 1, 6, 4)) > 0.3).astype(np.float32)]
+    c = rng.uniform(1500, 1580, Isz).astype(np.float32)
+    t0 = rng.uniform(-2e-7, 2e-7, 4)
+    extra = sum((("apod", a) for a in apods), ())
+    for fun in ("DAS", "SYN", "MUL", "BF"):
+        ref = _ora(oracle_c, fun, P, "cubic", t0=t0, c=c, apod=apods)
+        got = _gpu(fun, P, "cubic", "generic", extra, t0=t0, c=c)
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref), fun
+    xt = np.asfortranarray(np.swapaxes(P["x"], 1, 2))
+    ref = _ora(oracle_c, "DAS", P, "linear", t0=t0)
+    got = _gpu("DAS", P, "linear", "generic", ("transpose", True), x=xt, t0=t0)
+    assert np.array_equal(got, ref)
+    # complex apodization (the reference GPU path forces complex weights: kern/das_spec.m:237-243)
+    ac = [(apods[0] * np.exp(1j * 0.3)).astype(np.complex64)]
+    ref = _ora(oracle_c, "DAS", P, "linear", apod=ac)
+    got = _gpu("DAS", P, "linear", "generic", ("apod", ac[0]))
+    assert np.array_equal(got, ref)
+
+
+def test_generic_fp64_and_fp16(oracle_c):
+    P = small_problem("PW", nz=13, nx=9, N=6, M=4, T=150)
+    import qups_b200
+    ref = _ora(oracle_c, "DAS", P, "cubic", dtype=np.float64)
+    got = qups_b200.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"].astype(np.complex128), P["t0"], P["fs"],
+                             P["c"], *P["opts"], "interp", "cubic", "input-precision", "double")
+    assert got.dtype == np.complex128
+    assert rel_linf(got, ref) < 1e-12
+    # fp16 parity definition: oracle on fp16-rounded inputs, fp32 math
+    xh = (P["x"].real.astype(np.float16).astype(np.float32) + 1j * P["x"].imag.astype(np.float16).astype(np.float32)).astype(np.complex64)
+    ref = _ora(oracle_c, "DAS", P, "cubic", x=xh)
+    got = _gpu("DAS", P, "cubic", "auto", ("input-precision", "halfT"), _y_f32=True)
+    assert np.array_equal(got, ref)
+    got16 = _gpu("DAS", P, "cubic", "auto", ("input-precision", "halfT"))
+    assert rel_linf(got16, ref) < 2e-3  # half2 output rounding (reference DASh writes half2)
+
+
+def test_generic_modulation(oracle_c):
+    P = small_problem("PW", nz=13, nx=9, N=6, M=4, T=150)
+    t0 = np.array([1e-7, -1e-7, 2e-7, 0.0])
+    ref = _ora(oracle_c, "DAS", P, "cubic", t0=t0, fmod=5e6)
+    for path in ("generic", "tiled"):
+        got = _gpu("DAS", P, "cubic", path, ("modulation", 5e6), t0=t0)
+        assert rel_linf(got, ref) < 5e-6, path
+
+
+@pytest.mark.parametrize("kind", ["FC", "PW", "FSA", "DV"])
+@pytest.mark.parametrize("shape", [(40, 70, 1), (33, 37, 1), (16, 32, 3), (5, 3, 2), (1, 100, 1), (100, 1, 1)])
+def test_tiled_nearest_bitexact_integer_data(oracle_c, kind, shape):
+    """Integer-valued samples make every partial sum exact in fp32, so any tap-index mismatch shows as a
+    bit difference: the tiled kernel must pick exactly the oracle's sample for every (pixel, rx, tx)."""
+    import qups_b200
+    nz, nx, ny = shape
+    P = small_problem(kind, nz=nz, nx=nx, ny=ny, N=21, M=6, T=300, int_data=True, zlim=(2e-3, 14e-3))
+    ref = _ora(oracle_c, "DAS", P, "nearest")
+    got = _gpu("DAS", P, "nearest", "tiled")
+    assert qups_b200.last_das_kernel() == "das_tiled"
+    assert np.abs(ref).max() > 0
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("kind", ["FC", "PW", "FSA", "DV"])
+@pytest.mark.parametrize("interp", ["linear", "cubic"])
+def test_tiled_vs_oracle_tolerance(oracle_c, kind, interp):
+    P = small_problem(kind, nz=70, nx=45, N=37, M=9, T=400, zlim=(2e-3, 14e-3))
+    t0 = np.linspace(-3e-7, 3e-7, 9)
+    ref = _ora(oracle_c, "DAS", P, interp, t0=t0)
+    got = _gpu("DAS", P, interp, "tiled", t0=t0)
+    gen = _gpu("DAS", P, interp, "generic", t0=t0)
+    assert np.array_equal(gen, ref)
+    assert rel_linf(got, ref) < TOL, rel_linf(got, ref)
+
+
+@pytest.mark.parametrize("interp", ["nearest", "linear", "cubic"])
+def test_tiled_edges_out_of_range_and_small_windows(oracle_c, interp, monkeypatch):
+    """Pixels whose delays fall before sample 1 / after sample T (extrapval 0), traces only partly in range,
+    the cubic end-padding zone, and windows larger than the smem slot (slow path) must all match."""
+    P = small_problem("FSA", nz=64, nx=40, N=20, M=5, T=96, zlim=(0.2e-3, 9e-3), pad=0, int_data=(interp == "nearest"))
+    ref = _ora(oracle_c, "DAS", P, interp, t0=2e-6)  # t0 > 0 pushes shallow pixels before the first sample
+    got = _gpu("DAS", P, interp, "tiled", t0=2e-6)
+    if interp == "nearest":
+        assert np.array_equal(got, ref)
+    else:
+        assert rel_linf(got, ref) < TOL
+    monkeypatch.setenv("QUPS_B200_WMAX", "8")  # force most traces through the slow path
+    got = _gpu("DAS", P, interp, "tiled", t0=2e-6)
+    assert (np.array_equal(got, ref) if interp == "nearest" else rel_linf(got, ref) < TOL)
+    monkeypatch.setenv("QUPS_B200_LANE_AXIS", "1")
+    got = _gpu("DAS", P, interp, "tiled", t0=2e-6)
+    assert (np.array_equal(got, ref) if interp == "nearest" else rel_linf(got, ref) < TOL)
+
+
+def test_tiled_nan_pixel_and_frames(oracle_c):
+    P = small_problem("DV", nz=40, nx=33, N=17, M=4, T=300, F=2, zlim=(2e-3, 14e-3))
+    P["Pi"] = P["Pi"].copy()
+    P["Pi"][:, 7, 5, 0] = np.nan
+    ref = _ora(oracle_c, "DAS", P, "cubic")
+    got = _gpu("DAS", P, "cubic", "tiled")
+    assert got.shape == ref.shape
+    assert ref[7, 5, 0].max() == 0 and np.all(got[7, 5, 0] == 0)
+    assert rel_linf(got, ref) < TOL
+
+
+def test_auto_dispatch_and_errors():
+    import qups_b200
+    from qups_b200 import QupsError
+    P = small_problem("FC", nz=40, nx=33, N=17, M=4, T=300)
+    _gpu("DAS", P, "cubic", "auto")
+    assert qups_b200.last_das_kernel() == "das_tiled"
+    _gpu("SYN", P, "cubic", "auto")
+    assert qups_b200.last_das_kernel() == "das_generic"
+    with pytest.raises(QupsError):
+        _gpu("SYN", P, "cubic", "tiled")
+    with pytest.raises(ValueError):
+        _gpu("DAS", P, "spline", "auto")
+    with pytest.raises(AssertionError):
+        _gpu("DAS", P, "cubic", "auto", ("apod", np.ones((3, 3))))
+
+
+def test_host_entry_point_matches_device_entry_point(oracle_c):
+    """qups_das_host (host buffers, copies inside) == qups_das (device buffers)."""
+    import ctypes as C
+    from qups_b200 import _lib
+    P = small_problem("FC", nz=40, nx=33, N=17, M=4, T=300)
+    ref = _ora(oracle_c, "DAS", P, "cubic")
+    f32 = np.float32
+    Pi = np.asfortranarray(P["Pi"].reshape(3, -1, order="F").astype(f32))
+    Pr = np.asfortranarray(P["Pr"].astype(f32))
+    Pv4 = np.asfortranarray(np.concatenate([P["Pv"], np.zeros((1, 4))], 0).astype(f32))
+    Nv = np.asfortranarray(P["Nv"].astype(f32))
+    cinv = np.array([1.0 / f32(1540.0)], dtype=f32)
+    x = np.asfortranarray(P["x"])
+    p = _lib.DasParams()
+    p.struct_size = C.sizeof(_lib.DasParams)
+    p.dtype = _lib.F32
+    p.I1, p.I2, p.I3 = P["Pi"].shape[1:]
+    p.N, p.M, p.T, p.F, p.S = 17, 4, 300, 1, 0
+    p.flag, p.vs, p.dv = _lib.CUBIC, 1, 0
+    p.fs = P["fs"]
+    y = np.empty(P["Pi"].shape[1:], dtype=np.complex64, order="F")
+    acs = (C.c_uint64 * 6)(*([0] * 6))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = _lib.lib().qups_das_host(C.byref(p), vp(y), vp(Pi), vp(Pr), vp(Pv4), vp(Nv), None, 0, vp(cinv), 1, acs, vp(x), 0)
+    assert rc == 0, _lib.lib().qups_last_error()
+    assert rel_linf(y.reshape(ref.shape, order="F"), ref) < TOL
