@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqups_b200.so")
+LIB_PATH = os.environ.get("QUPS_B200_LIB") or os.path.join(_HERE, "libqups_b200.so")  # override: tuning builds
 
 F32, F16, F64 = 0, 1, 2
 NEAREST, LINEAR, CUBIC, LANCZOS3 = 0, 1, 2, 3

@@ -39,7 +39,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """defines: extra -D macros for tuning experiments (QUPS_NT, QUPS_CW, QUPS_STAGES, QUPS_MINBLOCKS, QUPS_WMAX);
+    out: alternative .so path (select at run time with QUPS_B200_LIB)."""
+    global OBJ
+    if defines:
+        OBJ = os.path.join(HERE, "csrc", "_obj_" + "_".join(d.replace("=", "") for d in defines))
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "qups_b200.h"))
@@ -52,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = ["nvcc", *ARCH, *COMMON, *extra, "-c", src, "-o", obj]
+            cmd = ["nvcc", *ARCH, *COMMON, *extra, *["-D" + d for d in defines], "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)
@@ -61,16 +67,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {unit}")
-    if force or _stale(OUT, objs):
-        cmd = ["nvcc", *ARCH, "-shared", "-o", OUT, *objs, "-Xlinker", "--exclude-libs,ALL", "-cudart", "shared"]
+    if force or _stale(out, objs):
+        cmd = ["nvcc", *ARCH, "-shared", "-o", out, *objs, "-Xlinker", "--exclude-libs,ALL", "-cudart", "shared"]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outp = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), OUT)
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outp))

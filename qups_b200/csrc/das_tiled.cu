@@ -33,16 +33,32 @@
 
 namespace qups {
 
-constexpr int kNT = 16;     // traces (receives) per stage
-constexpr int kR = 2;       // pixel rows per thread
-constexpr int kCW = 8;      // consumer warps
-constexpr int kStages = 4;  // smem ring depth
+#ifndef QUPS_NT
+#define QUPS_NT 16
+#endif
+#ifndef QUPS_CW
+#define QUPS_CW 8
+#endif
+#ifndef QUPS_STAGES
+#define QUPS_STAGES 4
+#endif
+#ifndef QUPS_MINBLOCKS
+#define QUPS_MINBLOCKS 2
+#endif
+#ifndef QUPS_WMAX
+#define QUPS_WMAX 128
+#endif
+constexpr int kNT = QUPS_NT;          // traces (receives) per stage
+constexpr int kR = 2;                 // pixel rows per thread
+constexpr int kCW = QUPS_CW;          // consumer warps
+constexpr int kStages = QUPS_STAGES;  // smem ring depth
 constexpr int kThreads = (kCW + 1) * 32;
+constexpr int kBarBytes = ((2 * kStages * 8 + 63) / 64) * 64;  // full[] + empty[] mbarriers
 constexpr int kTA = 32;        // tile extent along the lane axis
 constexpr int kTB = kCW * kR;  // tile extent along the row axis
 
 enum { TR_FAST = 0, TR_SKIP = 1, TR_SLOW = 2, TR_EDGE = 3 };   // per (n,m) trace
-enum { ST_MIXED = 0, ST_ALL_FAST = 1, ST_ALL_SKIP = 2 };        // per stage of kNT traces
+enum { ST_MIXED = 0, ST_ALL_FAST = 1, ST_END = 2 };             // per published stage of kNT traces
 
 struct TiledArgs {
     const float *Pi, *Pr, *Pv4, *Nv, *cinv;
@@ -198,20 +214,54 @@ template <int INTERP> __device__ __forceinline__ bool interior(float xq, float T
     return (xq >= 1.0f) && (xq <= Tf);
 }
 
+// One (pixel, trace) pair of an EDGE / FAST trace in a mixed stage.  The staged window holds every tap an
+// in-range pixel can touch, including the first / last three samples the interp1 end padding needs
+// (v(0) = 3v(1)-3v(2)+v(3), v(T+1) = 3v(T)-3v(T-1)+v(T-2)), so the trace ends are served from shared
+// memory too; out-of-range pixels contribute exactly 0 (extrapval).
 template <int INTERP>
-__global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs a) {
+__device__ __forceinline__ void edge_pair(float xq, uint32_t soff, float Tf, int T, float &ar, float &ai) {
+    if (interior<INTERP>(xq, Tf)) { fast_pair<INTERP>(xq, soff, ar, ai); return; }
+    if (!(xq >= 1.0f && xq <= Tf)) return;
+    if (INTERP == 2) {
+        int k = (int)floorf(xq);
+        k = min(k, T - 1);
+        const float u = xq - (float)k;
+        float w[4];
+        cubic_weights(u, w[0], w[1], w[2], w[3]);
+        // 1-based sample q lives at soff + 8*(q+1) (first tap of floor index k is q = k-1 at soff + 8k)
+        const uint32_t e0 = (k <= 1) ? 1u : (uint32_t)T; // padded end: samples e0, e0 +- 1, e0 +- 2
+        const int dir = (k <= 1) ? 1 : -1;
+        const float2 a = lds64(soff + 8u * (e0 + 1u)), b = lds64(soff + 8u * (uint32_t)((int)e0 + dir + 1)),
+                     c = lds64(soff + 8u * (uint32_t)((int)e0 + 2 * dir + 1));
+        const float2 pad = make_float2(fmaf(3.f, a.x, fmaf(-3.f, b.x, c.x)), fmaf(3.f, a.y, fmaf(-3.f, b.y, c.y)));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = k - 1 + j;
+            const float2 v = (q >= 1 && q <= T) ? lds64(soff + 8u * (uint32_t)(q + 1)) : pad;
+            ar = fmaf(w[j], v.x, ar);
+            ai = fmaf(w[j], v.y, ai);
+        }
+    } else if (INTERP == 1) { // only xq == T lands here: k clamps to T-1, s = 1  (first tap of index k at soff + 8k)
+        const float2 v0 = lds64(soff + 8u * (uint32_t)(T - 1)), v1 = lds64(soff + 8u * (uint32_t)T);
+        ar += fmaf(1.0f, v1.x - v0.x, v0.x);
+        ai += fmaf(1.0f, v1.y - v0.y, v0.y);
+    }
+}
+
+template <int INTERP>
+__global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(const TiledArgs a) {
     static_assert(kR == 2, "the packed fp32x2 inner loop assumes two pixel rows per thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [0,64) full/empty mbarriers | desc[kStages][kNT] int2 | stage_kind[kStages] |
+    // layout: [0,64) full/empty mbarriers | stage_hdr[kStages] int4 | desc[kStages][kNT] int2 |
     //         dvmin[M] dvmax[M] drmin[N] drmax[N] (ordered ints) | 128B-aligned stage ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-    int2 *desc = reinterpret_cast<int2 *>(smem_raw + 64);
-    int *stage_kind = reinterpret_cast<int *>(smem_raw + 64 + sizeof(int2) * kStages * kNT);
-    int *s_dvmin = stage_kind + kStages;
+    int4 *stage_hdr = reinterpret_cast<int4 *>(smem_raw + kBarBytes);
+    int2 *desc = reinterpret_cast<int2 *>(smem_raw + kBarBytes + sizeof(int4) * kStages);
+    int *s_dvmin = reinterpret_cast<int *>(smem_raw + kBarBytes + sizeof(int4) * kStages + sizeof(int2) * kStages * kNT);
     int *s_dvmax = s_dvmin + a.M;
     int *s_drmin = s_dvmax + a.M;
     int *s_drmax = s_drmin + a.N;
-    const uint32_t ring_off = (uint32_t)((64 + sizeof(int2) * kStages * kNT + sizeof(int) * (kStages + 2 * a.M + 2 * a.N) + 127) & ~127u);
+    const uint32_t ring_off = (uint32_t)((kBarBytes + sizeof(int4) * kStages + sizeof(int2) * kStages * kNT + sizeof(int) * (2 * a.M + 2 * a.N) + 127) & ~127u);
     const uint32_t ring = smem_u32(smem_raw) + ring_off;
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
 
@@ -285,68 +335,69 @@ __global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs 
         }
         __syncthreads();
 
-        // ---- phase 1: main loop -----------------------------------------------------------
+        // ---- phase 1: main loop over the stages the producer publishes ----------------------
+        // The ring carries only stages with work: (receive tile nt, transmit m) pairs whose 16 traces
+        // are all outside the data for this tile are dropped by the producer and never cost a handshake.
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
         Pack2 pk;
         pk.cinv = cinv;
         pk.fs = fs;
-        uint32_t it = 0;
-        for (uint32_t nt = 0; nt < a.numNT; ++nt) {
-            float2 dr[kNT]; // .x = pixel row 0, .y = pixel row 1
+        float2 dr[kNT]; // .x = pixel row 0, .y = pixel row 1
 #pragma unroll
-            for (int j = 0; j < kNT; ++j) {
-                const uint32_t n = min(nt * kNT + j, a.N - 1);
-                const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
-                dr[j].x = rx_dist(px[0], py[0], pz[0], rx, ry, rz);
-                dr[j].y = rx_dist(px[1], py[1], pz[1], rx, ry, rz);
+        for (int j = 0; j < kNT; ++j) dr[j] = make_float2(0.f, 0.f);
+        int cur_nt = -1;
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            const int4 hdr = stage_hdr[s]; // kind, m, nt
+            if (hdr.x == ST_END) break;
+            const uint32_t m = (uint32_t)hdr.y, nt = (uint32_t)hdr.z;
+            const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
+            const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
+            if ((int)nt != cur_nt) { // new receive tile: dr(i,n) for its 16 receives goes to registers
+                cur_nt = (int)nt;
+#pragma unroll
+                for (int j = 0; j < kNT; ++j) {
+                    const uint32_t n = min(nt * kNT + j, a.N - 1);
+                    const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
+                    dr[j].x = rx_dist(px[0], py[0], pz[0], rx, ry, rz);
+                    dr[j].y = rx_dist(px[1], py[1], pz[1], rx, ry, rz);
+                }
             }
-            // transmit parameters are prefetched one iteration ahead (hides the L1/L2 latency)
-            float4 pv_n = __ldg(reinterpret_cast<const float4 *>(a.Pv4));
-            float nx_n = __ldg(a.Nv), ny_n = __ldg(a.Nv + 1), nz_n = __ldg(a.Nv + 2);
-            for (uint32_t m = 0; m < a.M; ++m, ++it) {
-                const float4 pv = pv_n;
-                const float nx = nx_n, ny = ny_n, nz = nz_n;
-                const uint32_t mn = min(m + 1, a.M - 1);
-                pv_n = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + mn);
-                nx_n = __ldg(a.Nv + 3 * mn); ny_n = __ldg(a.Nv + 3 * mn + 1); nz_n = __ldg(a.Nv + 3 * mn + 2);
-                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                mbar_wait(bar_full + 8 * s, ph);
-                const int kind = stage_kind[s];
-                if (kind != ST_ALL_SKIP) {
-                    pk.dv.x = tx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
-                    pk.dv.y = tx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
-                    const float t0m = pv.w;
-                    pk.t0 = t0m;
-                    const int2 *dsc = desc + s * kNT;
-                    if (kind == ST_ALL_FAST) {
+            pk.dv.x = tx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+            pk.dv.y = tx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+            const float t0m = pv.w;
+            pk.t0 = t0m;
+            const int2 *dsc = desc + s * kNT;
+            if (hdr.x == ST_ALL_FAST) {
 #pragma unroll
-                        for (int j = 0; j < kNT; ++j)
-                            fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, acc0, acc1);
-                    } else {
+                for (int j = 0; j < kNT; ++j)
+                    fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, acc0, acc1);
+            } else {
+                // mixed stage: per-trace flags; dr is read through a local-memory copy so the loop stays rolled
+                float2 drl[kNT];
+#pragma unroll
+                for (int j = 0; j < kNT; ++j) drl[j] = dr[j];
 #pragma unroll 1
-                        for (int j = 0; j < kNT; ++j) {
-                            const int2 d = dsc[j];
-                            if (d.y == TR_SKIP) continue;
-                            const uint32_t n = nt * kNT + j;
-                            const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
-                            const uint64_t nm = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
-                            const float xq0 = sample_pos(pk.dv.x, rx_dist(px[0], py[0], pz[0], rx, ry, rz), cinv, t0m, fs);
-                            const float xq1 = sample_pos(pk.dv.y, rx_dist(px[1], py[1], pz[1], rx, ry, rz), cinv, t0m, fs);
-                            // FAST: window proven; EDGE: window holds every interior tap, the rest goes the slow way
-                            if (d.y == TR_FAST || (d.y == TR_EDGE && interior<INTERP>(xq0, Tf)))
-                                fast_pair<INTERP>(xq0, (uint32_t)d.x, acc0.x, acc0.y);
-                            else if (d.y == TR_SLOW || (xq0 >= 1.0f && xq0 <= Tf))
-                                slow_pair(a.x + nm * a.T, a.T, xq0, INTERP, acc0.x, acc0.y);
-                            if (d.y == TR_FAST || (d.y == TR_EDGE && interior<INTERP>(xq1, Tf)))
-                                fast_pair<INTERP>(xq1, (uint32_t)d.x, acc1.x, acc1.y);
-                            else if (d.y == TR_SLOW || (xq1 >= 1.0f && xq1 <= Tf))
-                                slow_pair(a.x + nm * a.T, a.T, xq1, INTERP, acc1.x, acc1.y);
-                        }
+                for (int j = 0; j < kNT; ++j) {
+                    const int2 d = dsc[j];
+                    if (d.y == TR_SKIP) continue;
+                    const float2 drj = drl[j];
+                    const float xq0 = sample_pos(pk.dv.x, drj.x, cinv, t0m, fs);
+                    const float xq1 = sample_pos(pk.dv.y, drj.y, cinv, t0m, fs);
+                    if (d.y != TR_SLOW) { // FAST or EDGE: everything comes from the staged window
+                        edge_pair<INTERP>(xq0, (uint32_t)d.x, Tf, (int)a.T, acc0.x, acc0.y);
+                        edge_pair<INTERP>(xq1, (uint32_t)d.x, Tf, (int)a.T, acc1.x, acc1.y);
+                    } else {              // window does not fit the slot / NaN bound: full interp1 from global memory
+                        const uint32_t n = nt * kNT + j;
+                        const uint64_t nm = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
+                        slow_pair(a.x + nm * a.T, a.T, xq0, INTERP, acc0.x, acc0.y);
+                        slow_pair(a.x + nm * a.T, a.T, xq1, INTERP, acc1.x, acc1.y);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8 * s);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         }
         if (valid[0]) a.y[pix[0]] = acc0;
         if (valid[1]) a.y[pix[1]] = acc1;
@@ -358,60 +409,94 @@ __global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs 
         for (uint32_t nt = 0; nt < a.numNT; ++nt) {
             const uint32_t n = nt * kNT + lane;
             const bool has = (lane < kNT) && (n < a.N);
-            float rlo = 0.f, rhi = 0.f;
-            if (has) { rlo = o2f(s_drmin[n]); rhi = o2f(s_drmax[n]); }
-            for (uint32_t m = 0; m < a.M; ++m, ++it) {
-                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                int flag = TR_SKIP;
-                uint32_t bytes = 0, soff = 0, dst = 0;
-                const float2 *src = nullptr;
-                if (has) {
-                    const float t0m = __ldg(a.Pv4 + 4 * m + 3);
-                    const float xlo = sample_pos(o2f(s_dvmin[m]), rlo, cinv, t0m, fs);
-                    const float xhi = sample_pos(o2f(s_dvmax[m]), rhi, cinv, t0m, fs);
-                    flag = TR_SLOW;
-                    if (cinv_ok && xlo <= xhi) {
-                        if (xhi < 1.0f || xlo > Tf) {
-                            flag = TR_SKIP; // every pixel of the tile is outside the trace: contributes 0
-                        } else {
-                            // every delay operation is monotone and individually rounded, so all tap
-                            // indices of the tile lie in [k(xlo), k(xhi)]; clip to the trace for EDGE
-                            const bool inr = interior<INTERP>(xlo, Tf) && interior<INTERP>(xhi, Tf);
-                            const float xl = fmaxf(xlo, 1.0f), xh = fminf(xhi, Tf);
-                            int klo, khi, tap0, tap1;
-                            if (INTERP == 2)      { klo = (int)floorf(xl); khi = (int)floorf(xh); tap0 = 2; tap1 = 1; }
-                            else if (INTERP == 1) { klo = (int)floorf(xl); khi = (int)floorf(xh); tap0 = 1; tap1 = 0; }
-                            else { klo = (int)floorf(__fadd_rn(xl, 0.5f)); khi = (int)floorf(__fadd_rn(xh, 0.5f)); tap0 = 1; tap1 = -1; }
-                            int t_lo = klo - tap0, t_hi = khi + tap1; // 0-based first / last tap
-                            if (!inr) { t_lo = max(t_lo, 0); t_hi = min(t_hi, (int)a.T - 1); }
-                            const uint64_t tr = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
-                            const int64_t abs_lo = (int64_t)(tr * a.T) + t_lo;
-                            const int64_t abs_al = abs_lo & ~(int64_t)1; // 16-byte aligned element
-                            const int w0 = t_lo - (int)(abs_lo - abs_al);
-                            int wlen = t_hi - w0 + 1;
-                            wlen = (wlen + 1) & ~1;
-                            if (wlen > 0 && wlen <= (int)a.wmax && abs_al >= 0 && (uint64_t)(abs_al + wlen) <= a.total_elems) {
-                                flag = inr ? TR_FAST : TR_EDGE;
-                                bytes = (uint32_t)wlen * 8u;
-                                dst = ring + (s * kNT + lane) * a.wmax * 8u;
-                                soff = dst - (uint32_t)(w0 + tap0) * 8u;
-                                src = a.x + abs_al;
+            int olo = INT_MAX, ohi = INT_MIN;
+            if (has) { olo = s_drmin[n]; ohi = s_drmax[n]; }
+            const float rlo = o2f(olo), rhi = o2f(ohi);
+            // receive-tile bounds of dr: one conservative skip test per transmit, 32 transmits per pass
+            const float rlo_t = o2f(__reduce_min_sync(0xffffffffu, olo)), rhi_t = o2f(__reduce_max_sync(0xffffffffu, ohi));
+            for (uint32_t m0 = 0; m0 < a.M; m0 += 32) {
+                const uint32_t ml = m0 + lane;
+                bool skip = true;
+                if (ml < a.M) {
+                    const float t0l = __ldg(a.Pv4 + 4 * ml + 3);
+                    const float xl = sample_pos(o2f(s_dvmin[ml]), rlo_t, cinv, t0l, fs);
+                    const float xh = sample_pos(o2f(s_dvmax[ml]), rhi_t, cinv, t0l, fs);
+                    skip = cinv_ok && (xl <= xh) && (xh < 1.0f || xl > Tf);
+                }
+                uint32_t todo = ~__ballot_sync(0xffffffffu, skip);
+                while (todo) {
+                    const uint32_t m = m0 + (uint32_t)(__ffs((int)todo) - 1);
+                    todo &= todo - 1;
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                    int flag = TR_SKIP;
+                    uint32_t bytes = 0, soff = 0, dst = 0;
+                    const float2 *src = nullptr;
+                    if (has) {
+                        const float t0m = __ldg(a.Pv4 + 4 * m + 3);
+                        const float xlo = sample_pos(o2f(s_dvmin[m]), rlo, cinv, t0m, fs);
+                        const float xhi = sample_pos(o2f(s_dvmax[m]), rhi, cinv, t0m, fs);
+                        flag = TR_SLOW;
+                        if (cinv_ok && xlo <= xhi) {
+                            if (xhi < 1.0f || xlo > Tf) {
+                                flag = TR_SKIP; // every pixel of the tile is outside the trace: contributes 0
+                            } else {
+                                // every delay operation is monotone and individually rounded, so all tap
+                                // indices of the tile lie in [k(xlo), k(xhi)]; clip to the trace for EDGE
+                                const bool inr = interior<INTERP>(xlo, Tf) && interior<INTERP>(xhi, Tf);
+                                const float xl = fmaxf(xlo, 1.0f), xh = fminf(xhi, Tf);
+                                int klo, khi, tap0, tap1;
+                                if (INTERP == 2)      { klo = (int)floorf(xl); khi = (int)floorf(xh); tap0 = 2; tap1 = 1; }
+                                else if (INTERP == 1) { klo = (int)floorf(xl); khi = (int)floorf(xh); tap0 = 1; tap1 = 0; }
+                                else { klo = (int)floorf(__fadd_rn(xl, 0.5f)); khi = (int)floorf(__fadd_rn(xh, 0.5f)); tap0 = 1; tap1 = -1; }
+                                int t_lo = klo - tap0, t_hi = khi + tap1; // 0-based first / last tap
+                                if (!inr) {
+                                    // EDGE: keep the three end samples the interp1 padding needs (edge_pair), then clip
+                                    if (INTERP == 2) {
+                                        if (klo <= 1) t_hi = max(t_hi, 2);
+                                        if (khi >= (int)a.T - 1) t_lo = min(t_lo, (int)a.T - 3);
+                                    } else if (INTERP == 1) {
+                                        if (khi >= (int)a.T) t_lo = min(t_lo, (int)a.T - 2);
+                                    }
+                                    t_lo = max(t_lo, 0);
+                                    t_hi = min(t_hi, (int)a.T - 1);
+                                }
+                                const uint64_t tr = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
+                                const int64_t abs_lo = (int64_t)(tr * a.T) + t_lo;
+                                const int64_t abs_al = abs_lo & ~(int64_t)1; // 16-byte aligned element
+                                const int w0 = t_lo - (int)(abs_lo - abs_al);
+                                int wlen = t_hi - w0 + 1;
+                                wlen = (wlen + 1) & ~1;
+                                if (wlen > 0 && wlen <= (int)a.wmax && abs_al >= 0 && (uint64_t)(abs_al + wlen) <= a.total_elems) {
+                                    flag = inr ? TR_FAST : TR_EDGE;
+                                    bytes = (uint32_t)wlen * 8u;
+                                    dst = ring + (s * kNT + lane) * a.wmax * 8u;
+                                    soff = dst - (uint32_t)(w0 + tap0) * 8u;
+                                    src = a.x + abs_al;
+                                }
                             }
                         }
                     }
+                    if (__all_sync(0xffffffffu, flag == TR_SKIP)) continue; // exact per-trace test: nothing to do
+                    const bool all_fast = __all_sync(0xffffffffu, flag == TR_FAST || lane >= kNT);
+                    const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1); // slot free (first lap passes immediately)
+                    if (lane < kNT) desc[s * kNT + lane] = make_int2((int)soff, flag);
+                    if (lane == 0) stage_hdr[s] = make_int4(all_fast ? ST_ALL_FAST : ST_MIXED, (int)m, (int)nt, 0);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * s, total);
+                    __syncwarp();
+                    if (bytes) bulk_g2s(dst, src, bytes, bar_full + 8 * s);
+                    ++it;
                 }
-                mbar_wait(bar_empty + 8 * s, ph ^ 1); // slot free (first lap passes immediately)
-                if (lane < kNT) desc[s * kNT + lane] = make_int2((int)soff, flag);
-                const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
-                const bool all_fast = __all_sync(0xffffffffu, flag == TR_FAST || lane >= kNT);
-                const bool all_skip = __all_sync(0xffffffffu, flag == TR_SKIP || lane >= kNT);
-                __syncwarp();
-                if (lane == 0) {
-                    stage_kind[s] = all_fast ? ST_ALL_FAST : (all_skip ? ST_ALL_SKIP : ST_MIXED);
-                    mbar_arrive_expect_tx(bar_full + 8 * s, total);
-                }
-                __syncwarp();
-                if (bytes) bulk_g2s(dst, src, bytes, bar_full + 8 * s);
+            }
+        }
+        // end-of-work marker
+        {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            if (lane == 0) {
+                stage_hdr[s] = make_int4(ST_END, 0, 0, 0);
+                mbar_arrive(bar_full + 8 * s);
             }
         }
     }
@@ -419,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 2) das_tiled_kernel(const TiledArgs 
 
 // ---- host side ------------------------------------------------------------------------
 static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax) {
-    size_t head = 64 + sizeof(int2) * kStages * kNT + sizeof(int) * (kStages + 2 * (size_t)M + 2 * (size_t)N);
+    size_t head = kBarBytes + sizeof(int4) * kStages + sizeof(int2) * kStages * kNT + sizeof(int) * (2 * (size_t)M + 2 * (size_t)N);
     head = (head + 127) & ~(size_t)127;
     return head + (size_t)kStages * kNT * wmax * 8;
 }
@@ -461,9 +546,9 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     t.IC = (uint32_t)a.I3; t.sC = a.I1 * a.I2;
     t.tilesA = (t.IA + kTA - 1) / kTA;
     t.tilesB = (t.IB + kTB - 1) / kTB;
-    uint32_t wmax = 128;
+    uint32_t wmax = QUPS_WMAX;
     if (const char *e = getenv("QUPS_B200_WMAX")) { int v = atoi(e); if (v >= 8 && v <= 1024) wmax = (uint32_t)(v & ~1); }
-    while (wmax > 16 && tiled_smem_bytes(t.N, t.M, wmax) > 100 * 1024) wmax -= 16;
+    while (wmax > 16 && tiled_smem_bytes(t.N, t.M, wmax) > 200 * 1024 / QUPS_MINBLOCKS) wmax -= 16;
     t.wmax = wmax;
     const size_t smem = tiled_smem_bytes(t.N, t.M, wmax);
     const uint64_t tiles = (uint64_t)t.tilesA * t.tilesB * t.IC;
