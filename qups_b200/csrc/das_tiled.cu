@@ -53,6 +53,10 @@ constexpr int kR = 2;                 // pixel rows per thread
 constexpr int kCW = QUPS_CW;          // consumer warps
 constexpr int kStages = QUPS_STAGES;  // smem ring depth
 constexpr int kThreads = (kCW + 1) * 32;
+#ifndef QUPS_LPA
+#define QUPS_LPA 8
+#endif
+constexpr int kLPA = QUPS_LPA;        // lanes of a warp along the lane axis (32, 16 or 8)
 constexpr int kBarBytes = ((2 * kStages * 8 + 63) / 64) * 64;  // full[] + empty[] mbarriers
 constexpr int kTA = 32;        // tile extent along the lane axis
 constexpr int kTB = kCW * kR;  // tile extent along the row axis
@@ -270,7 +274,11 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
     // ---- tile coordinates -------------------------------------------------------
     const uint32_t tile = blockIdx.x;
     const uint32_t ta = tile % a.tilesA, tb = (tile / a.tilesA) % a.tilesB, tc = tile / (a.tilesA * a.tilesB);
-    const uint32_t ia = ta * kTA + lane;
+    // lane patch: a warp covers kLPA pixels along the lane axis x (32/kLPA) pixel-row pairs; a compact 2-D
+    // patch keeps the tap addresses of a half-warp inside one 128-byte row of shared memory
+    constexpr int kWA = kTA / kLPA, kLPB = 32 / kLPA;
+    static_assert(kCW % kWA == 0, "consumer warps must tile the lane axis");
+    const uint32_t ia = ta * kTA + (warp % kWA) * kLPA + (lane % kLPA);
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
         bool valid[kR];
 #pragma unroll
         for (int r = 0; r < kR; ++r) {
-            const uint32_t ib = tb * kTB + warp * kR + r;
+            const uint32_t ib = tb * kTB + ((warp / kWA) * kLPB + (lane / kLPA)) * kR + r;
             valid[r] = (ia < a.IA) && (ib < a.IB);
             // out-of-image lanes shadow a valid pixel so they never widen the windows
             const uint32_t ca = ia < a.IA ? ia : a.IA - 1, cb = ib < a.IB ? ib : a.IB - 1;

@@ -1,0 +1,203 @@
+"""ultrasound.py — thin mirror of the reference's L4 boundary for the hot path.
+
+    UltrasoundSystem.DAS      src/UltrasoundSystem.m:3172-3372   -> das_spec
+    UltrasoundSystem.bfDAS    src/UltrasoundSystem.m:4334-4474   -> bfDASLUT -> ChannelData.sample2sep -> wsinterpd2
+    UltrasoundSystem.greens   src/UltrasoundSystem.m:463-882     -> greens kernel (+ focusTx identity for FSA)
+    ChannelData               src/ChannelData.m:36-61            (data T x N x M x F, t0, fs)
+
+Only the argument assembly the reference performs at these call sites is restated (geometry providers are the
+minimal ones in synth.py); all arithmetic runs in libqups_b200.so.  MATLAB scripts keep using the reference's
+own classes — this module exists so that the parity tests and bench can drive the same boundary from Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, kern, synth
+from ._lib import GreensParams
+
+
+@dataclass
+class ChannelData:
+    """T x N x M (x F) data cube with start time t0 (scalar or one per transmit) and sampling frequency fs."""
+    data: object
+    t0: object = 0.0
+    fs: float = 1.0
+
+    @property
+    def T(self): return self.data.shape[0]
+    @property
+    def N(self): return self.data.shape[1]
+    @property
+    def M(self): return self.data.shape[2]
+
+
+@dataclass
+class Sequence:
+    """type in {'FSA','PW','FC','VS','DV'}; focus = 3 x M foci (FC/VS/DV) or unit normals (PW)."""
+    type: str = "FSA"
+    focus: Optional[np.ndarray] = None
+    c0: float = 1540.0
+
+
+@dataclass
+class UltrasoundSystem:
+    tx: np.ndarray                     # 3 x M transmit element positions
+    rx: np.ndarray                     # 3 x N receive element positions
+    seq: Sequence
+    scan: np.ndarray                   # 3 x I1 x I2 x I3 pixel positions (Scan.positions())
+    fs: float
+    fc: float = 5e6
+    bw_frac: float = 0.6
+    tx_offset: np.ndarray = field(default_factory=lambda: np.zeros((3, 1)))
+    tx_normal: np.ndarray = field(default_factory=lambda: np.array([[0.0], [0.0], [1.0]]))
+
+    # ---- DAS ------------------------------------------------------------------------------
+    def _pos_args(self):
+        """src/UltrasoundSystem.m:3341-3351 (DAS) / :4436-4440 (bfDAS)."""
+        t = self.seq.type
+        if t == "FSA":
+            return self.tx, np.broadcast_to(self.tx_normal, self.tx.shape), ("diverging-waves",)
+        if t == "PW":
+            return np.zeros((3, 1)), np.asarray(self.seq.focus), ("plane-waves",)
+        if t in ("VS", "FC", "DV"):
+            nf = np.asarray(self.seq.focus) - self.tx_offset
+            nv = nf / np.linalg.norm(nf, 2)  # matrix 2-norm, as the reference (harmless: only the sign is used)
+            return np.asarray(self.seq.focus), nv, (("diverging-waves",) if t == "DV" else ())
+        raise ValueError(f"unknown sequence type {t}")
+
+    def DAS(self, chd: ChannelData, *apod, c0=None, fmod=0.0, interp="cubic", keep_tx=False, keep_rx=False,
+            prec="single", **kw):
+        """b = DAS(us, chd, A1..An, 'c0', 'fmod', 'prec', 'interp', 'keep_tx', 'keep_rx')  (:3172-3295)."""
+        fun = {(False, False): "DAS", (True, False): "SYN", (False, True): "MUL", (True, True): "BF"}[(keep_rx, keep_tx)]
+        Pv, Nv, ext = self._pos_args()
+        rt = np.float64 if prec == "double" else np.float32
+        opts = list(ext) + ["interp", interp, "input-precision", prec]
+        for a in apod:
+            opts += ["apod", a]
+        if fmod:
+            opts += ["modulation", float(fmod)]
+        c = self.seq.c0 if c0 is None else c0
+        f = lambda v: np.asarray(v, dtype=rt)
+        b = kern.das_spec(fun, f(self.scan), f(self.rx), f(Pv), f(Nv), chd.data, chd.t0, chd.fs, c, *opts, **kw)
+        # permute(b, [1:3, 6:D+2, 4:5]) -> I1 x I2 x I3 x F... x [N] x [M]   (:3361)
+        nd = b.ndim
+        order = [0, 1, 2] + list(range(5, nd)) + [3, 4]
+        return b.permute(*order) if isinstance(b, torch.Tensor) else np.transpose(b, order)
+
+    # ---- bfDAS (separable delay tables) -------------------------------------------------------
+    def bfDAS(self, chd: ChannelData, c0=None, fmod=0.0, interp="cubic", apod=1, keep_tx=False, keep_rx=False):
+        """tau_rx = |Pi-Pr|/c0 (I x N), tau_tx = dv/c0 (I x 1 x M) -> sample2sep -> wsinterpd2  (:4431-4473)."""
+        c = self.seq.c0 if c0 is None else c0
+        Pv, Nv, ext = self._pos_args()
+        Isz = tuple(self.scan.shape[1:]) + (1,) * (4 - self.scan.ndim)
+        Pi = np.asarray(self.scan, np.float64).reshape(3, -1, order="F")
+        Pr = np.asarray(self.rx, np.float64)
+        Pv = np.broadcast_to(np.asarray(Pv, np.float64), (3, chd.M))
+        rv = Pi[:, :, None] - Pv[:, None, :]
+        t = self.seq.type
+        if t in ("DV", "FSA"):
+            dv = np.linalg.norm(rv, axis=0)
+        elif t == "PW":
+            dv = (rv * np.asarray(Nv, np.float64)[:, None, :]).sum(0)
+        else:  # VS / FC: normalize(focus - offset, 1, "norm") per column (:4439)
+            nf = np.asarray(self.seq.focus, np.float64) - self.tx_offset
+            nf = nf / np.linalg.norm(nf, axis=0, keepdims=True)
+            dv = np.linalg.norm(rv, axis=0) * np.sign((rv * nf[:, None, :]).sum(0))
+        dr = np.linalg.norm(Pi[:, :, None] - Pr[:, None, :], axis=0)
+        rt = np.float32 if np.asarray(chd.data).dtype in (np.complex64, np.float32) else np.float64
+        tau_rx = (dr / c).astype(rt).reshape(Isz + (chd.N, 1), order="F")
+        tau_tx = (dv / c).astype(rt).reshape(Isz + (1, chd.M), order="F")
+        # ChannelData.sample2sep (src/ChannelData.m:1414-1445): data lifted to T x 1 x 1 x N x M
+        fs, t0 = rt(chd.fs), np.asarray(chd.t0, dtype=rt).reshape(-1)
+        t0b = t0.reshape((1, 1, 1, 1, -1)) if t0.size > 1 else t0.reshape((1,) * 5)
+        ntau_rx = (tau_rx * fs).reshape((1,) + tau_rx.shape, order="F")
+        ntau_tx = ((tau_tx - t0b) * fs).reshape((1,) + tau_tx.shape, order="F")
+        x = np.asarray(chd.data)
+        x6 = x.reshape((x.shape[0], 1, 1, 1) + x.shape[1:3], order="F")
+        sdim = tuple(d for d, keep in ((5, keep_rx), (6, keep_tx)) if not keep)
+        w = np.asarray(apod)
+        w = w.reshape((1,) + tuple(w.shape) + (1,) * (5 - w.ndim), order="F") if w.ndim else w
+        omega = 2j * np.pi * fmod / float(chd.fs)
+        y = kern.wsinterpd2(x6, ntau_rx, ntau_tx, 1, w, sdim, interp, 0, omega)
+        return y.reshape(y.shape[1:], order="F") if isinstance(y, np.ndarray) else y[0]
+
+    # ---- greens ---------------------------------------------------------------------------------
+    def greens(self, scat_pos, scat_amp, c0=None, interp="cubic", R0=None, fsk=None, device=None, sort=True):
+        """chd = greens(us, scat)  (src/UltrasoundSystem.m:463-882), FSA simulation on the GPU.
+
+        Returns ChannelData with data T x N x M truncated to its non-zero time support (:871-874).
+        """
+        c0 = self.seq.c0 if c0 is None else c0
+        fs = float(self.fs)
+        fsk = fs if fsk is None else float(fsk)
+        R0 = (c0 / self.fc) if R0 is None else R0      # default max(us.lambda)  (:550)
+        ps = np.asarray(scat_pos, np.float64).reshape(3, -1)
+        amp = np.asarray(scat_amp, np.float64).reshape(-1)
+        pv, pn = np.asarray(self.tx, np.float64), np.asarray(self.rx, np.float64)
+        kern_s, wv_t0, wv_tend = synth.greens_kernel(self.fc, self.bw_frac, fsk)
+        # time bounds from the aperture bounding boxes (:567-580, 608-615)
+        def box(p):
+            lo, hi = p.min(1), p.max(1)
+            c = np.array([[(hi if (i >> d) & 1 else lo)[d] for i in range(8)] for d in range(3)])
+            return c, np.linalg.norm(hi - lo)
+        txb, txr = box(pv)
+        rxb, rxr = box(pn)
+        dist = lambda b: np.linalg.norm(ps[:, :, None] - b[:, None, :], axis=0)
+        dtx, drx = dist(txb), dist(rxb)
+        taumax = (dtx.max() + drx.max() + txr + rxr) / c0
+        taumin = (dtx.min() + drx.min() - txr - rxr) / c0
+        tmin = taumin + wv_t0 - (wv_tend - wv_t0)
+        tmax = taumax + wv_tend
+        n0, ne = int(np.floor(tmin * fs)), int(np.ceil(tmax * fs))
+        T = ne - n0 + 1
+        if sort:  # sort scatterers by rmin*rmax (:630-647)
+            rs = np.linalg.norm(ps[:, :, None] - pv[:, None, :], axis=0)
+            rmin, rmax = 2 * rs.min(1), 2 * rs.max(1)
+            if not np.array_equal(pv, pn):
+                rr = np.linalg.norm(ps[:, :, None] - pn[:, None, :], axis=0)
+                rmin, rmax = rs.min(1) + rr.min(1), rs.max(1) + rr.max(1)
+            order = np.argsort(rmin * rmax, kind="stable")
+            ps, amp = ps[:, order], amp[order]
+        x = greens_raw(ps, amp, pn, pv, kern_s, n0, T, fs, c0, wv_t0, fsk / fs, R0, interp, device=device)
+        # truncate the all-zero head/tail (:871-874)
+        nz = (x != 0).reshape(T, -1).any(dim=1)
+        idx = torch.nonzero(nz).reshape(-1)
+        if idx.numel():
+            a, b = int(idx[0]), int(idx[-1])
+            x, n0 = x[a:b + 1], n0 + a
+        chd = ChannelData(x, n0 / fs, fs)
+        # focusTx is the identity for a pure FSA sequence (:3453-3455); other sequences are a "next" row
+        if self.seq.type != "FSA":
+            raise _lib.QupsError(-3, "greens + focusTx for non-FSA sequences is not implemented in this round")
+        return chd
+
+
+def greens_raw(ps, amp, pn, pv, kern_s, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, interp="cubic", device=None,
+               dtype=np.float32):
+    """Direct call of the qups_greens C ABI; returns a CUDA tensor of logical shape (T, N, M)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    rt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    ct = torch.complex64 if rt == torch.float32 else torch.complex128
+    col = lambda a_: torch.from_numpy(np.ascontiguousarray(np.asarray(a_, np.float64).T)).to(dev, rt).contiguous()
+    dPs, dPn, dPv = col(ps), col(pn), col(pv)
+    dA = torch.from_numpy(np.asarray(amp, np.float64)).to(dev, rt).contiguous()
+    dK = torch.from_numpy(np.asarray(kern_s, np.complex128)).to(dev, ct).contiguous()
+    N, M = dPn.shape[0], dPv.shape[0]
+    y = torch.empty((M, N, T), dtype=ct, device=dev)
+    p = GreensParams()
+    p.struct_size = C.sizeof(GreensParams)
+    p.dtype = _lib.F32 if rt == torch.float32 else _lib.F64
+    p.I, p.S, p.T, p.N, p.M, p.E = dPs.shape[0], T, dK.shape[0], N, M, 1
+    p.n0, p.interp = int(n0), _lib.INTERP[interp]
+    p.t0x, p.fs, p.fsr, p.c0, p.R0 = float(wv_t0), float(fs), float(fsr), float(c0), float(R0)
+    vp = lambda t_: C.c_void_p(t_.data_ptr())
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(_lib.lib().qups_greens(C.byref(p), vp(y), vp(dPs), vp(dA), vp(dPn), vp(dPv), vp(dK), st))
+    return y.permute(2, 1, 0)

@@ -23,7 +23,11 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--config", default="c2")
 a = ap.parse_args()
 
-P = {"c2": synth.config_c2, "c3": synth.config_c3}[a.config](a.nz, a.nx, a.N, a.M, a.T, a.interp)
+if a.config == "c5":
+    P = synth.config_c5_das(a.nz, a.nx, a.N, a.T)
+    P.interp = a.interp
+else:
+    P = {"c2": synth.config_c2, "c3": synth.config_c3}[a.config](a.nz, a.nx, a.N, a.M, a.T, a.interp)
 t = time.time()
 x = torch.from_numpy(synth.noise_cube(P.T, P.N, P.M)).cuda()
 print(f"data gen {time.time()-t:.1f}s", flush=True)

@@ -1,0 +1,118 @@
+"""GPU parity: greens, wsinterpd2 / bfDAS through the C ABI vs the CPU oracle, plus the reference's physical
+known-answer checks (test/BFTest.m:230-317, test/SimTest.m:299-357) run end to end on the GPU path."""
+import numpy as np
+import pytest
+
+from tests.util import small_problem, oracle_kwargs, rel_linf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("interp", ["nearest", "linear", "cubic"])
+@pytest.mark.parametrize("R0", [0.0, 3e-4])
+def test_greens_bitexact_vs_oracle(oracle_c, interp, R0):
+    from qups_b200 import synth
+    from qups_b200.ultrasound import greens_raw
+    fs, fc, c0 = 20e6, 5e6, 1500.0
+    kern, wt0, _ = synth.greens_kernel(fc, 0.6, fs)
+    pn = synth.linear_array(7, 0.3e-3)
+    pv = synth.linear_array(5, 0.4e-3)
+    rng = np.random.default_rng(2)
+    S = 300  # more than one smem chunk is exercised in the large test below; this one pins the arithmetic
+    ps = np.stack([rng.uniform(-3e-3, 3e-3, S), rng.uniform(-1e-3, 1e-3, S), rng.uniform(3e-3, 12e-3, S)], 0)
+    amp = rng.standard_normal(S)
+    n0, T = 40, 2600
+    ref = oracle_c.greens(ps, amp, pn, pv, kern, n0, T, fs, c0, wt0, 1.0, R0, interp)
+    got = greens_raw(ps, amp, pn, pv, kern, n0, T, fs, c0, wt0, 1.0, R0, interp).cpu().numpy()
+    assert np.abs(ref).max() > 0
+    assert np.array_equal(got, ref), rel_linf(got, ref)
+
+
+def test_greens_many_scatterers_fsr_and_fp64(oracle_c):
+    from qups_b200 import synth
+    from qups_b200.ultrasound import greens_raw
+    fs, fc, c0 = 20e6, 5e6, 1540.0
+    kern, wt0, _ = synth.greens_kernel(fc, 0.6, 2 * fs)   # kernel sampled at 2x the output rate: fsr = 2
+    pn = synth.linear_array(4, 0.3e-3)
+    rng = np.random.default_rng(5)
+    S = 5000
+    ps = np.stack([rng.uniform(-3e-3, 3e-3, S), np.zeros(S), rng.uniform(3e-3, 12e-3, S)], 0)
+    amp = rng.standard_normal(S)
+    ref = oracle_c.greens(ps, amp, pn, pn, kern, 60, 400, fs, c0, wt0, 2.0, 2e-4, "cubic")
+    got = greens_raw(ps, amp, pn, pn, kern, 60, 400, fs, c0, wt0, 2.0, 2e-4, "cubic").cpu().numpy()
+    assert np.array_equal(got, ref)
+    ref64 = oracle_c.greens(ps, amp, pn, pn, kern, 60, 400, fs, c0, wt0, 2.0, 2e-4, "cubic", dtype=np.float64)
+    got64 = greens_raw(ps, amp, pn, pn, kern, 60, 400, fs, c0, wt0, 2.0, 2e-4, "cubic", dtype=np.float64).cpu().numpy()
+    assert rel_linf(got64, ref64) < 1e-12
+    assert rel_linf(got, ref64) < 1e-3   # the reference's own CPU-vs-GPU greens tolerance (test/SimTest.m:327-357)
+
+
+def test_wsinterpd_interptest_shapes(oracle_np):
+    """test/interpTest.m:28-47 generator, :96-143 check, on the GPU kernel."""
+    import qups_b200
+    I, T, N, M, F = 16, 32, 4, 3, 2
+    t = np.arange(T)[:, None, None]
+    n = np.arange(N)[None, :, None]
+    f = np.arange(F)[None, None, :]
+    x = np.exp(2j * np.pi * (0.5 + f / 2 * n / 4) * t / T).astype(np.complex64)[:, :, None, :]   # T x N x 1 x F
+    rng = np.random.default_rng(11)
+    tau = rng.uniform(-2, T + 1, (I, N, M, 1)).astype(np.float32)
+    w = rng.uniform(0, 1, (I, N, M, 1)).astype(np.float32)
+    for terp in ("cubic", "nearest", "linear"):
+        for dsum in ((), (2,), (3,), (2, 3), (4,)):
+            ref = oracle_np.wsinterpd(x, tau, 1, w, dsum, terp, 0)
+            got = qups_b200.wsinterpd(x, tau, 1, w, dsum, terp, 0)
+            assert got.shape == ref.shape, (terp, dsum)
+            assert rel_linf(got, ref) < 1e4 * np.finfo(np.float32).eps, (terp, dsum)   # tolerance of test/interpTest.m:126
+    # two-table form with a phasor and time along dim 2
+    x2 = np.ascontiguousarray(np.swapaxes(x, 0, 1))                                               # N x T x 1 x F
+    t1 = np.swapaxes(tau, 0, 1)
+    t2 = rng.uniform(-1, 1, (1, 1, M, 1)).astype(np.float32)
+    ref = oracle_np.wsinterpd2(x2, t1, t2, 2, np.swapaxes(w, 0, 1), (3,), "linear", 0, 0.7j)
+    got = qups_b200.wsinterpd2(x2, t1, t2, 2, np.swapaxes(w, 0, 1), (3,), "linear", 0, 0.7j)
+    assert got.shape == ref.shape and rel_linf(got, ref) < 2e-6
+
+
+@pytest.mark.parametrize("kind,seq", [("FC", "FC"), ("PW", "PW"), ("FSA", "FSA"), ("DV", "DV")])
+def test_bfdas_matches_das_and_oracle(oracle_c, kind, seq):
+    from qups_b200.ultrasound import UltrasoundSystem, Sequence, ChannelData
+    P = small_problem(kind, nz=21, nx=15, N=8, M=5, T=200)
+    focus = P["Nv"] if seq == "PW" else P["Pv"]
+    us = UltrasoundSystem(tx=P["Pv"] if seq == "FSA" else P["Pr"], rx=P["Pr"], seq=Sequence(seq, focus, P["c"]),
+                          scan=P["Pi"], fs=P["fs"])
+    chd = ChannelData(P["x"], 1e-7, P["fs"])
+    b1 = us.DAS(chd, interp="cubic")
+    b2 = us.bfDAS(chd, interp="cubic")
+    ref = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], 1e-7, P["fs"], P["c"], interp="cubic",
+                            dtype=np.float64, **oracle_kwargs(P["opts"]))[..., 0]
+    ref32 = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], 1e-7, P["fs"], P["c"], interp="cubic",
+                              **oracle_kwargs(P["opts"]))[..., 0]
+    assert rel_linf(np.asarray(b1).reshape(ref.shape), ref32) < 1e-5
+    if kind != "FC":  # focused waves: sign(rv . Nv) flips between fp32 and fp64 for pixels at the focal depth
+        assert rel_linf(np.asarray(b1).reshape(ref.shape), ref) < 2e-3  # fp32 vs the fp64 arbiter on white noise
+    assert rel_linf(np.asarray(b2).reshape(ref.shape), ref) < 5e-3     # table path rounds tau twice (fp32 tables)
+
+
+def test_physical_known_answers_on_gpu():
+    """greens -> DAS round trip: SimTest echo time and BFTest PSF location, all on the GPU path."""
+    from qups_b200 import synth
+    from qups_b200.ultrasound import UltrasoundSystem, Sequence
+    c0 = 1500.0
+    pn = synth.linear_array(5, 0.3e-3)
+    us = UltrasoundSystem(tx=pn, rx=pn, seq=Sequence("FSA", None, c0), scan=synth.scan_cartesian([0.0], [15e-3]),
+                          fs=40e6, fc=5e6)
+    chd = us.greens(np.array([[0.0], [0.0], [15e-3]]), np.ones(1), c0=c0)
+    tr = chd.data[:, 2, 2].abs().cpu().numpy()
+    assert abs(chd.t0 + np.argmax(tr) / chd.fs - 20e-6) <= 1.1 / chd.fs
+    N = 32
+    pn = synth.linear_array(N, 0.3e-3)
+    xs, zs = np.linspace(-4e-3, 6e-3, 41), np.linspace(11e-3, 19e-3, 33)
+    us = UltrasoundSystem(tx=pn, rx=pn, seq=Sequence("FSA", None, c0), scan=synth.scan_cartesian(xs, zs), fs=25e6,
+                          fc=6.25e6)
+    chd = us.greens(np.array([[2e-3], [0.0], [15e-3]]), np.ones(1), c0=c0, interp="linear")
+    b = us.DAS(chd, interp="cubic")
+    b = b.cpu().numpy() if hasattr(b, "cpu") else np.asarray(b)
+    b = np.abs(b).reshape(len(zs), len(xs), order="F")
+    assert b.max() > 0
+    iz, ix = np.unravel_index(np.argmax(b), b.shape)
+    assert abs(zs[iz] - 15e-3) <= 1.1e-3 and abs(xs[ix] - 2e-3) <= 1.1e-3
