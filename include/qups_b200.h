@@ -86,6 +86,8 @@ typedef struct {
     int32_t apod_real;    /* extension: apod arrays are real (the reference forces complex, :237-243) */
     int32_t y_f32;        /* extension: with dtype F16 write float2 output instead of half2 */
     int32_t path;         /* qups_path; AUTO picks the tiled kernel when eligible */
+    int32_t accumulate;   /* extension: y += result instead of y = result (transmit-chunked pipelines) */
+    int32_t host_chunks;  /* qups_das_host only: transmit chunks of the copy/compute pipeline (0 = automatic) */
     double fs;            /* sampling frequency */
     double fmod;          /* modulation frequency (data re-modulated at absolute time, kern/das_spec.m:413-417) */
     uint64_t x_frame_stride; /* complex elements between frames of x; 0 -> T*N*M */
@@ -110,10 +112,16 @@ QUPS_API int qups_delays(const qups_das_params *p, void *tau, const void *Pi, co
                 const void *cinv, const uint64_t *cstride, qups_stream_t stream);
 
 /* Same as qups_das but every array pointer is a HOST pointer; performs H2D, compute, D2H and synchronises.
- * Pinned host memory is used at full PCIe rate; pageable memory works but is slower. */
+ * Pinned host memory is used at full PCIe rate; pageable memory works but is slower.
+ * When the call is eligible for the staged kernel the transmit axis is cut into chunks whose H2D copies overlap
+ * the beamforming of the previous chunk (two streams), so end-to-end time ~ max(copy, compute). */
 QUPS_API int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
                   const void *apod, uint64_t apod_elems, const void *cinv, uint64_t cinv_elems,
                   const uint64_t *acstride, const void *x, int device);
+
+/* qups_das_host keeps its device staging buffers and streams per host thread between calls (the cube is ~1 GB;
+ * re-allocating it every call costs more than the beamforming). Release them explicitly with this call. */
+QUPS_API void qups_host_release(void);
 
 /* x(t,n,m) *= exp(2i*pi*fmod*(t0(m) + t/fs))  out-of-place; t0 : M reals (device). kern/das_spec.m:413-417 */
 QUPS_API int qups_modulate(int32_t dtype, void *xout, const void *x, const void *t0, uint64_t T, uint64_t N, uint64_t M,

@@ -19,7 +19,7 @@ INTERP = {"nearest": NEAREST, "linear": LINEAR, "cubic": CUBIC, "lanczos3": LANC
 
 EXPORTS = (
     "qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
-    "qups_greens", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
+    "qups_greens", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
 )
 
 
@@ -39,6 +39,7 @@ class DasParams(C.Structure):
         ("F", C.c_uint64), ("S", C.c_uint64),
         ("flag", C.c_int32), ("vs", C.c_int32), ("dv", C.c_int32),
         ("apod_real", C.c_int32), ("y_f32", C.c_int32), ("path", C.c_int32),
+        ("accumulate", C.c_int32), ("host_chunks", C.c_int32),
         ("fs", C.c_double), ("fmod", C.c_double),
         ("x_frame_stride", C.c_uint64), ("y_frame_stride", C.c_uint64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),

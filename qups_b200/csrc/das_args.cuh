@@ -12,7 +12,7 @@ constexpr int MAX_APOD = 8;
 template <typename R> struct DasArgs {
     uint64_t I1, I2, I3, I, N, M, T;
     int S, interp;
-    int keep_rx, keep_tx, tpose, VS, DV, apod_real;
+    int keep_rx, keep_tx, tpose, VS, DV, apod_real, accumulate;
     R fs;
     const R *Pi;   // 3 x I
     const R *Pr;   // 3 x N

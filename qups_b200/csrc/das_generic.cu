@@ -123,6 +123,11 @@ __global__ void __launch_bounds__(128) das_generic_kernel(const DasArgs<R> a) {
                 acc.im = add_rn(acc.im, yn.im);
             }
         }
+        if (a.accumulate) { // y += result (transmit-chunked callers); not for BF (nothing is summed there)
+            const auto old = data_traits<DOUT>::load(y, i + a.I * o);
+            acc.re = add_rn((R)old.re, acc.re);
+            acc.im = add_rn((R)old.im, acc.im);
+        }
         data_traits<DOUT>::store(y, i + a.I * o, {(typename data_traits<DOUT>::real)acc.re,
                                                   (typename data_traits<DOUT>::real)acc.im});
     }

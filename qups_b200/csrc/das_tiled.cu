@@ -75,7 +75,7 @@ struct TiledArgs {
     uint32_t wmax;          // samples per smem slot (even)
     uint32_t numNT;
     float fs;
-    int VS, DV, tpose;
+    int VS, DV, tpose, accumulate;
     uint64_t total_elems;   // T*N*M
 };
 
@@ -407,6 +407,10 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         }
+        if (a.accumulate) {
+            if (valid[0]) { const float2 o = a.y[pix[0]]; acc0.x += o.x; acc0.y += o.y; }
+            if (valid[1]) { const float2 o = a.y[pix[1]]; acc1.x += o.x; acc1.y += o.y; }
+        }
         if (valid[0]) a.y[pix[0]] = acc0;
         if (valid[1]) a.y[pix[1]] = acc1;
     } else {
@@ -542,7 +546,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     t.x = reinterpret_cast<const float2 *>(a.x);
     t.y = reinterpret_cast<float2 *>(a.y);
     t.N = (uint32_t)a.N; t.M = (uint32_t)a.M; t.T = (uint32_t)a.T;
-    t.fs = a.fs; t.VS = a.VS; t.DV = a.DV; t.tpose = a.tpose;
+    t.fs = a.fs; t.VS = a.VS; t.DV = a.DV; t.tpose = a.tpose; t.accumulate = a.accumulate;
     t.total_elems = a.T * a.N * a.M;
     t.numNT = (t.N + kNT - 1) / kNT;
     // axis assignment: lanes along I2 (the slow axis of a ZXY ScanCartesian, src/ScanCartesian.m:11) when

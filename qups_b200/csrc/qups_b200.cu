@@ -41,6 +41,7 @@ static int fill_args(DasArgs<R> &a, const qups_das_params *p, const void *Pi, co
     a.tpose = (p->flag & QUPS_FLAG_TRANSPOSE) != 0;
     a.VS = p->vs != 0; a.DV = p->dv != 0;
     a.apod_real = p->apod_real != 0;
+    a.accumulate = p->accumulate != 0;
     a.fs = (R)p->fs;
     a.Pi = (const R *)Pi; a.Pr = (const R *)Pr; a.Pv4 = (const R *)Pv4; a.Nv = (const R *)Nv;
     a.cinv = (const R *)cinv;
@@ -183,12 +184,6 @@ static int das_impl(const qups_das_params *p, void *y, const void *Pi, const voi
     }
 }
 
-template <typename T> struct DevBuf {
-    T *p = nullptr;
-    cudaError_t alloc(size_t bytes) { return bytes ? cudaMalloc((void **)&p, bytes) : cudaSuccess; }
-    ~DevBuf() { if (p) cudaFree(p); }
-};
-
 } // namespace qups
 
 using namespace qups;
@@ -239,13 +234,64 @@ int qups_modulate(int32_t dtype, void *xout, const void *x, const void *t0, uint
     return 0;
 }
 
+// ---- host-buffer entry point -------------------------------------------------------------------
+namespace qups {
+// per-host-thread staging state, kept between calls (see qups_host_release)
+struct HostWs {
+    static constexpr int NB = 8, NEV = 32;
+    int dev = -1;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev[NEV] = {};
+    void *buf[NB] = {};
+    size_t cap[NB] = {};
+    void release() {
+        if (dev >= 0) cudaSetDevice(dev);
+        for (int i = 0; i < NB; ++i) { if (buf[i]) cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
+        for (int i = 0; i < NEV; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+        if (s_copy) cudaStreamDestroy(s_copy);
+        if (s_comp) cudaStreamDestroy(s_comp);
+        s_copy = s_comp = nullptr;
+        dev = -1;
+    }
+    int ensure(int device) {
+        if (dev == device && s_copy) return 0;
+        release();
+        cudaError_t e;
+        if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+        if ((e = cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+        if ((e = cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+        for (int i = 0; i < NEV; ++i)
+            if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+        dev = device;
+        return 0;
+    }
+    int get(int i, size_t bytes, void **out) {
+        *out = nullptr;
+        if (bytes == 0) return 0;
+        if (cap[i] < bytes) {
+            if (buf[i]) cudaFree(buf[i]);
+            buf[i] = nullptr; cap[i] = 0;
+            cudaError_t e = cudaMalloc(&buf[i], bytes);
+            if (e != cudaSuccess) return fail(QUPS_ERR_ALLOC, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+            cap[i] = bytes;
+        }
+        *out = buf[i];
+        return 0;
+    }
+    ~HostWs() { /* process teardown: the CUDA context may already be gone; leak by design */ }
+};
+static thread_local HostWs g_ws;
+} // namespace qups
+
+void qups_host_release(void) { g_ws.release(); }
+
 int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
                   const void *apod, uint64_t apod_elems, const void *cinv, uint64_t cinv_elems,
                   const uint64_t *acstride, const void *x, int device) {
     g_err[0] = 0;
     if (int rc = validate(p, false)) return rc;
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if (int rc = g_ws.ensure(device)) return rc;
+    cudaError_t e;
     const size_t rsz = (p->dtype == QUPS_F64) ? 8 : 4;                       // geometry element
     const size_t csz = (p->dtype == QUPS_F64) ? 16 : (p->dtype == QUPS_F16 ? 4 : 8); // complex data element
     const size_t ysz = (p->dtype == QUPS_F16 && p->y_f32) ? 8 : csz;
@@ -255,28 +301,60 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
     const uint64_t xfs = p->x_frame_stride ? p->x_frame_stride : p->T * p->N * p->M;
     const uint64_t yfs = p->y_frame_stride ? p->y_frame_stride : I * On * Om;
     const size_t xb = csz * ((F - 1) * xfs + p->T * p->N * p->M), yb = ysz * ((F - 1) * yfs + I * On * Om);
-    cudaStream_t st;
-    if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-    DevBuf<char> dPi, dPr, dPv, dNv, dA, dC, dX, dY;
+    void *dX, *dPi, *dPr, *dPv, *dNv, *dA, *dC, *dY;
     int rc = 0;
-#define QUPS_UP(buf, src, bytes)                                                                        \
-    if (rc == 0 && (bytes)) {                                                                           \
-        if ((e = buf.alloc(bytes)) != cudaSuccess) rc = fail(QUPS_ERR_ALLOC, "cudaMalloc(%zu): %s", (size_t)(bytes), cudaGetErrorString(e)); \
-        else if ((e = cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) rc = cuda_fail(e, "H2D copy"); \
-    }
-    QUPS_UP(dX, x, xb)
+    if ((rc = g_ws.get(0, xb, &dX)) || (rc = g_ws.get(1, rsz * 3 * I, &dPi)) || (rc = g_ws.get(2, rsz * 3 * p->N, &dPr)) ||
+        (rc = g_ws.get(3, rsz * 4 * p->M, &dPv)) || (rc = g_ws.get(4, rsz * 3 * p->M, &dNv)) ||
+        (rc = g_ws.get(5, asz * apod_elems, &dA)) || (rc = g_ws.get(6, rsz * cinv_elems, &dC)) || (rc = g_ws.get(7, yb, &dY)))
+        return rc;
+    cudaStream_t sc = g_ws.s_copy, sx = g_ws.s_comp;
+#define QUPS_UP(dst, src, bytes) \
+    if (rc == 0 && (bytes) && (e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sc)) != cudaSuccess) rc = cuda_fail(e, "H2D copy");
     QUPS_UP(dPi, Pi, rsz * 3 * I)
     QUPS_UP(dPr, Pr, rsz * 3 * p->N)
     QUPS_UP(dPv, Pv4, rsz * 4 * p->M)
     QUPS_UP(dNv, Nv, rsz * 3 * p->M)
     QUPS_UP(dA, apod, asz * apod_elems)
     QUPS_UP(dC, cinv, rsz * cinv_elems)
+    // transmit-chunked pipeline: DAS is a plain sum over transmits (kern/das_spec.m:480), so chunk c+1 is copied
+    // while chunk c is beamformed and accumulated.  Only for the contiguous-in-m layout and summed transmits.
+    const bool chunkable = rc == 0 && F == 1 && !(p->flag & (QUPS_FLAG_TRANSPOSE | QUPS_FLAG_KEEP_TX)) && p->fmod == 0.0 &&
+                           p->S == 0 && !p->accumulate &&
+                           ((p->M >= 16 && p->T * p->N * p->M * csz >= (64u << 20)) || (p->host_chunks > 1 && p->M >= (uint64_t)p->host_chunks));
+    if (chunkable) {
+        bool scalar_c = true;
+        for (int d = 0; d < 5; ++d) scalar_c = scalar_c && (!acstride || acstride[d] == 0);
+        uint64_t nch = scalar_c ? ((p->M >= 128) ? 16 : 4) : 1;
+        if (scalar_c && p->host_chunks > 1) nch = (uint64_t)p->host_chunks < 16 ? (uint64_t)p->host_chunks : 16;
+        if (nch > 1) {
+            if ((e = cudaEventRecord(g_ws.ev[HostWs::NEV - 1], sc)) != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord");
+            if (rc == 0 && (e = cudaStreamWaitEvent(sx, g_ws.ev[HostWs::NEV - 1], 0)) != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent");
+            for (uint64_t c = 0; c < nch && rc == 0; ++c) {
+                const uint64_t m0 = p->M * c / nch, m1 = p->M * (c + 1) / nch;
+                const size_t off = csz * p->T * p->N * m0, len = csz * p->T * p->N * (m1 - m0);
+                if ((e = cudaMemcpyAsync((char *)dX + off, (const char *)x + off, len, cudaMemcpyHostToDevice, sc)) != cudaSuccess) { rc = cuda_fail(e, "H2D copy"); break; }
+                cudaEventRecord(g_ws.ev[c], sc);
+                cudaStreamWaitEvent(sx, g_ws.ev[c], 0);
+                qups_das_params q = *p;
+                q.M = m1 - m0;
+                q.accumulate = c > 0;
+                rc = das_impl(&q, dY, dPi, dPr, (char *)dPv + rsz * 4 * m0, (char *)dNv + rsz * 3 * m0, dA, dC, acstride,
+                              (char *)dX + off, sx);
+            }
+            if (rc == 0 && yb && (e = cudaMemcpyAsync(y, dY, yb, cudaMemcpyDeviceToHost, sx)) != cudaSuccess) rc = cuda_fail(e, "D2H copy");
+            if ((e = cudaStreamSynchronize(sx)) != cudaSuccess && rc == 0) rc = cuda_fail(e, "cudaStreamSynchronize");
+            cudaStreamSynchronize(sc);
+            return rc;
+        }
+    }
+    QUPS_UP(dX, x, xb)
 #undef QUPS_UP
-    if (rc == 0 && yb && (e = dY.alloc(yb)) != cudaSuccess) rc = fail(QUPS_ERR_ALLOC, "cudaMalloc(%zu): %s", yb, cudaGetErrorString(e));
-    if (rc == 0) rc = das_impl(p, dY.p, dPi.p, dPr.p, dPv.p, dNv.p, dA.p, dC.p, acstride, dX.p, st);
-    if (rc == 0 && yb && (e = cudaMemcpyAsync(y, dY.p, yb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = cuda_fail(e, "D2H copy");
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess && rc == 0) rc = cuda_fail(e, "cudaStreamSynchronize");
-    cudaStreamDestroy(st);
+    if (rc == 0 && (e = cudaEventRecord(g_ws.ev[0], sc)) != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord");
+    if (rc == 0 && (e = cudaStreamWaitEvent(sx, g_ws.ev[0], 0)) != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent");
+    if (rc == 0) rc = das_impl(p, dY, dPi, dPr, dPv, dNv, dA, dC, acstride, dX, sx);
+    if (rc == 0 && yb && (e = cudaMemcpyAsync(y, dY, yb, cudaMemcpyDeviceToHost, sx)) != cudaSuccess) rc = cuda_fail(e, "D2H copy");
+    if ((e = cudaStreamSynchronize(sx)) != cudaSuccess && rc == 0) rc = cuda_fail(e, "cudaStreamSynchronize");
+    cudaStreamSynchronize(sc);
     return rc;
 }
 

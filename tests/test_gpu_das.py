@@ -200,6 +200,10 @@ def test_host_entry_point_matches_device_entry_point(oracle_c):
     y = np.empty(P["Pi"].shape[1:], dtype=np.complex64, order="F")
     acs = (C.c_uint64 * 6)(*([0] * 6))
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = _lib.lib().qups_das_host(C.byref(p), vp(y), vp(Pi), vp(Pr), vp(Pv4), vp(Nv), None, 0, vp(cinv), 1, acs, vp(x), 0)
-    assert rc == 0, _lib.lib().qups_last_error()
-    assert rel_linf(y.reshape(ref.shape, order="F"), ref) < TOL
+    for chunks in (0, 3):   # single shot, then the transmit-chunked copy/compute pipeline (accumulating launches)
+        p.host_chunks = chunks
+        y[:] = 0
+        rc = _lib.lib().qups_das_host(C.byref(p), vp(y), vp(Pi), vp(Pr), vp(Pv4), vp(Nv), None, 0, vp(cinv), 1, acs, vp(x), 0)
+        assert rc == 0, _lib.lib().qups_last_error()
+        assert rel_linf(y.reshape(ref.shape, order="F"), ref) < TOL
+    _lib.lib().qups_host_release()
