@@ -35,6 +35,10 @@ template <typename DIN, typename DOUT, typename R>
 int launch_modulate(DOUT *xo, const DIN *x, const R *t0, int t0_stride, uint64_t T, uint64_t N, uint64_t M, int tpose,
                     R fs, double fmod, cudaStream_t st);
 
+// element-wise precision conversion of a complex array (n complex elements)
+int launch_half2_to_float2(float2 *dst, const __half2 *src, uint64_t n, cudaStream_t st);
+int launch_float2_to_half2(__half2 *dst, const float2 *src, uint64_t n, cudaStream_t st);
+
 // tiled fast path (fp32 data, sum over both apertures, scalar cinv, no apodization arrays)
 struct TiledPlan {
     int eligible;      // 1 if the tiled kernel can take this call

@@ -216,4 +216,32 @@ template int launch_modulate<__half2, __half2, float>(__half2 *, const __half2 *
 template int launch_modulate<double2, double2, double>(double2 *, const double2 *, const double *, int, uint64_t,
                                                        uint64_t, uint64_t, int, double, double, cudaStream_t);
 
+// ---- half2 <-> float2 conversion (fp16 data through the staged fp32 kernel) ----
+__global__ void __launch_bounds__(256) h2f_kernel(float2 *dst, const __half2 *src, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = __half22float2(__ldg(src + i));
+}
+__global__ void __launch_bounds__(256) f2h_kernel(__half2 *dst, const float2 *src, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float2 v = __ldg(src + i);
+        dst[i] = __floats2half2_rn(v.x, v.y);
+    }
+}
+static unsigned conv_grid(uint64_t n) {
+    const uint64_t g = (n + 255) / 256;
+    return (unsigned)(g < 148ull * 16 ? (g ? g : 1) : 148ull * 16);
+}
+int launch_half2_to_float2(float2 *dst, const __half2 *src, uint64_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    h2f_kernel<<<conv_grid(n), 256, 0, st>>>(dst, src, n);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+int launch_float2_to_half2(__half2 *dst, const float2 *src, uint64_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    f2h_kernel<<<conv_grid(n), 256, 0, st>>>(dst, src, n);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 } // namespace qups

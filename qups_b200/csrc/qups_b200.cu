@@ -176,9 +176,39 @@ static int das_impl(const qups_das_params *p, void *y, const void *Pi, const voi
     switch (p->dtype) {
         case QUPS_F32:
             return run_das_typed<float2, float2, float2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 0, 0);
-        case QUPS_F16:
+        case QUPS_F16: {
+            // fp16 data on the hot configuration: widen the cube to fp32 once (exact) and run the staged kernel;
+            // fp32 geometry / accumulation either way, half2 output narrowed at the end.
+            if (p->path != QUPS_PATH_GENERIC && p->S == 0 && !(p->flag & (QUPS_FLAG_KEEP_RX | QUPS_FLAG_KEEP_TX)) && !p->accumulate) {
+                DasArgs<float> a;
+                fill_args<float>(a, p, Pi, Pr, Pv4, Nv, apod, cinv, acstride, 1);
+                a.x = (const void *)16; // alignment probe only: the scratch cube is 256-byte aligned
+                if (das_tiled_plan(a, 0, 0).eligible) {
+                    const uint64_t F = p->F ? p->F : 1, nel = p->T * p->N * p->M, I = p->I1 * p->I2 * p->I3;
+                    const uint64_t xfs = p->x_frame_stride ? p->x_frame_stride : nel, yfs = p->y_frame_stride ? p->y_frame_stride : I;
+                    float2 *xs = nullptr, *ys = nullptr;
+                    cudaError_t e = cudaMallocAsync((void **)&xs, sizeof(float2) * nel, st);
+                    if (e == cudaSuccess && !p->y_f32) e = cudaMallocAsync((void **)&ys, sizeof(float2) * I, st);
+                    if (e != cudaSuccess) { if (xs) cudaFreeAsync(xs, st); return fail(QUPS_ERR_ALLOC, "cudaMallocAsync: %s", cudaGetErrorString(e)); }
+                    qups_das_params q = *p;
+                    q.dtype = QUPS_F32; q.F = 1; q.path = QUPS_PATH_TILED;
+                    int rc = 0;
+                    for (uint64_t f = 0; f < F && rc == 0; ++f) {
+                        if (int ce = launch_half2_to_float2(xs, (const __half2 *)x + f * xfs, nel, st)) { rc = cuda_fail(ce, "half2->float2"); break; }
+                        void *yo = p->y_f32 ? (void *)((float2 *)y + f * yfs) : (void *)ys;
+                        rc = run_das_typed<float2, float2, float2, float>(&q, yo, Pi, Pr, Pv4, Nv, nullptr, cinv, acstride, xs, st, 0, 0);
+                        if (rc == 0 && !p->y_f32)
+                            if (int ce = launch_float2_to_half2((__half2 *)y + f * yfs, ys, I, st)) rc = cuda_fail(ce, "float2->half2");
+                    }
+                    cudaFreeAsync(xs, st);
+                    if (ys) cudaFreeAsync(ys, st);
+                    return rc;
+                }
+            }
+            if (p->path == QUPS_PATH_TILED) return fail(QUPS_ERR_UNSUPPORTED, "tiled DAS path not applicable to this fp16 call");
             if (p->y_f32) return run_das_typed<__half2, __half2, float2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 1, 0);
             return run_das_typed<__half2, __half2, __half2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 1, 1);
+        }
         default:
             return run_das_typed<double2, double2, double2, double>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 2, 2);
     }
@@ -329,8 +359,28 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
         if (nch > 1) {
             if ((e = cudaEventRecord(g_ws.ev[HostWs::NEV - 1], sc)) != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord");
             if (rc == 0 && (e = cudaStreamWaitEvent(sx, g_ws.ev[HostWs::NEV - 1], 0)) != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent");
-            for (uint64_t c = 0; c < nch && rc == 0; ++c) {
-                const uint64_t m0 = p->M * c / nch, m1 = p->M * (c + 1) / nch;
+            // chunk sizes grow geometrically (x1.6): the first copy that cannot overlap anything is short, and each
+            // later copy still finishes before the previous chunk's beamforming does (copy is faster than compute)
+            uint64_t bounds[HostWs::NEV];
+            uint64_t nb = 0, pos = 0;
+            if (p->host_chunks > 1) {
+                for (uint64_t c = 0; c <= nch; ++c) bounds[c] = p->M * c / nch;
+                nb = nch;
+            } else {
+                double sz = (double)p->M / 16.0;
+                if (sz < 8) sz = 8;
+                bounds[0] = 0;
+                while (pos < p->M && nb < HostWs::NEV - 3) {
+                    uint64_t step = (uint64_t)sz;
+                    if (p->M - pos < step + step / 2) step = p->M - pos;
+                    pos += step;
+                    bounds[++nb] = pos;
+                    sz *= 1.6;
+                }
+                bounds[nb] = p->M;
+            }
+            for (uint64_t c = 0; c < nb && rc == 0; ++c) {
+                const uint64_t m0 = bounds[c], m1 = bounds[c + 1];
                 const size_t off = csz * p->T * p->N * m0, len = csz * p->T * p->N * (m1 - m0);
                 if ((e = cudaMemcpyAsync((char *)dX + off, (const char *)x + off, len, cudaMemcpyHostToDevice, sc)) != cudaSuccess) { rc = cuda_fail(e, "H2D copy"); break; }
                 cudaEventRecord(g_ws.ev[c], sc);

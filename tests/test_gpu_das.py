@@ -89,10 +89,16 @@ def test_generic_fp64_and_fp16(oracle_c):
     # fp16 parity definition: oracle on fp16-rounded inputs, fp32 math
     xh = (P["x"].real.astype(np.float16).astype(np.float32) + 1j * P["x"].imag.astype(np.float16).astype(np.float32)).astype(np.complex64)
     ref = _ora(oracle_c, "DAS", P, "cubic", x=xh)
-    got = _gpu("DAS", P, "cubic", "auto", ("input-precision", "halfT"), _y_f32=True)
+    got = _gpu("DAS", P, "cubic", "generic", ("input-precision", "halfT"), _y_f32=True)
     assert np.array_equal(got, ref)
-    got16 = _gpu("DAS", P, "cubic", "auto", ("input-precision", "halfT"))
-    assert rel_linf(got16, ref) < 2e-3  # half2 output rounding (reference DASh writes half2)
+    import qups_b200 as qb
+    got = _gpu("DAS", P, "cubic", "auto", ("input-precision", "halfT"), _y_f32=True)   # widened + staged kernel
+    assert qb.last_das_kernel() == "das_tiled" and rel_linf(got, ref) < TOL
+    for path in ("auto", "generic"):
+        got16 = _gpu("DAS", P, "cubic", path, ("input-precision", "halfT"))
+        assert rel_linf(got16, ref) < 2e-3  # half2 output rounding (reference DASh writes half2)
+    gsyn = _gpu("SYN", P, "cubic", "auto", ("input-precision", "halfT"), _y_f32=True)           # generic mixed types
+    assert np.array_equal(gsyn, _ora(oracle_c, "SYN", P, "cubic", x=xh))
 
 
 def test_generic_modulation(oracle_c):
