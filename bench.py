@@ -143,6 +143,8 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--shard", default="tx", choices=["tx", "pixels"],
+                    help="N>1 decomposition: transmit partition + all-reduce (default) or pixel slabs without collective")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -188,15 +190,28 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     f32 = np.float32
 
-    # this rank's pixel slab (strong scaling over a fixed image)
-    Pi_slab, axis, s0, cnt = shard.pixel_shard(P.Pi, rank, world)
-    Isz = Pi_slab.shape[1:]
-    I_loc, I_tot = int(np.prod(Isz)), P.I
+    # N > 1 (strong scaling over the fixed image), two one-step decompositions:
+    #   tx (default): rank g holds x(:,:,m in M_g) — 1/N of the cube resident per GPU —, beamforms a full-size partial
+    #                 image and the images are summed by ONE NCCL all-reduce of 2*I floats inside the timed step;
+    #   pixels      : rank g beamforms a slab of x-columns from a replicated cube, no collective.
+    tx_mode = world > 1 and a.shard == "tx"
     x_np = synth.noise_cube(P.T, P.N, P.M, seed=0)
-
     t = lambda v: torch.from_numpy(np.ascontiguousarray(np.asarray(v, f32))).to(dev)
-    x_d = torch.from_numpy(x_np).to(dev)
-    args = (t(Pi_slab), t(P.Pr), t(P.Pv), t(P.Nv), x_d, float(P.t0), float(P.fs), float(P.c0), *P.opts, "interp", P.interp)
+    if tx_mode:
+        m0, mc = shard.tx_shard(P.M, rank, world)
+        Pi_slab, Isz = P.Pi, P.Pi.shape[1:]
+        Pv_l = np.broadcast_to(np.asarray(P.Pv, f32), (3, P.M))[:, m0:m0 + mc]
+        Nv_l = np.broadcast_to(np.asarray(P.Nv, f32), (3, P.M))[:, m0:m0 + mc]
+        x_d = torch.from_numpy(np.asfortranarray(x_np[:, :, m0:m0 + mc])).to(dev)
+        M_loc = mc
+        cfg["sharding"] = "transmits: each rank holds 1/N of the cube, full-size partial image, one NCCL all-reduce per step"
+    else:
+        Pi_slab, axis, s0, cnt = shard.pixel_shard(P.Pi, rank, world)
+        Isz = Pi_slab.shape[1:]
+        Pv_l, Nv_l, M_loc = P.Pv, P.Nv, P.M
+        x_d = torch.from_numpy(x_np).to(dev)
+    I_loc, I_tot = int(np.prod(Isz)), P.I
+    args = (t(Pi_slab), t(P.Pr), t(Pv_l), t(Nv_l), x_d, float(P.t0), float(P.fs), float(P.c0), *P.opts, "interp", P.interp)
 
     def barrier():
         if world > 1:
@@ -204,7 +219,10 @@ def main():
         torch.cuda.synchronize()
 
     def run_step():
-        return qups_b200.das_spec("DAS", *args)
+        b = qups_b200.das_spec("DAS", *args)
+        if tx_mode:  # the path's one exchange step: sum of the partial images (8 MB at 1024^2)
+            b = shard.allreduce_image(b.permute(*reversed(range(b.ndim))).contiguous().reshape(-1))
+        return b
 
     for _ in range(max(3, a.warmup)):
         y = run_step()
@@ -228,6 +246,12 @@ def main():
     launches = _lib.launch_count()
     ms_total = e_all0.elapsed_time(e_all1)
     kern_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev]))
+    if tx_mode:  # roofline wants the DAS kernel alone: re-time it without the all-reduce (outside the timed region)
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        for e0, e1 in kev:
+            e0.record(); qups_b200.das_spec("DAS", *args); e1.record()
+        torch.cuda.synchronize()
+        kern_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
     tmax = torch.tensor([ms_total, kern_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -237,7 +261,46 @@ def main():
 
     # ---------------- e2e: host buffers through the C ABI (H2D + kernel + D2H timed) ----------------
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and world > 1:
+        # N > 1: transmit partition (SURVEY.md §8e mode 2).  Each rank uploads ONLY its 1/N of the channel cube from
+        # pinned host memory, beamforms a full-size partial image and the images are summed with one NCCL all-reduce;
+        # rank 0 reads the image back.  (Pixel sharding would make every rank upload the whole 1 GB cube.)
+        m0, mc = shard.tx_shard(P.M, rank, world)
+        hX = torch.from_numpy(np.ascontiguousarray(x_np[:, :, m0:m0 + mc].transpose(2, 1, 0))).pin_memory()
+        Pvb = np.broadcast_to(np.asarray(P.Pv, f32), (3, P.M))[:, m0:m0 + mc]
+        Nvb = np.broadcast_to(np.asarray(P.Nv, f32), (3, P.M))[:, m0:m0 + mc]
+        hg = [torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for v in (np.asarray(P.Pi, f32), np.asarray(P.Pr, f32), Pvb, Nvb)]
+        hY = torch.empty((P.I,), dtype=torch.complex64).pin_memory()
+
+        def e2e_step():
+            xd = hX.to(dev, non_blocking=True).permute(2, 1, 0)
+            gd = [h.to(dev, non_blocking=True) for h in hg]
+            b = qups_b200.das_spec("DAS", gd[0], gd[1], gd[2], gd[3], xd, float(P.t0), float(P.fs), float(P.c0), *P.opts,
+                                   "interp", P.interp)
+            b = shard.allreduce_image(b.permute(*reversed(range(b.ndim))).contiguous().reshape(-1))
+            if rank == 0:
+                hY.copy_(b, non_blocking=True)
+            torch.cuda.synchronize()
+            return b
+        ne = max(2, min(a.steps, 5))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ne):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / ne], device=dev, dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = hX.numel() * 8 + sum(h.numel() for h in hg) * 4
+        full = float(torch.view_as_real(hY).abs().sum()) if rank == 0 else 0.0
+        ysum_all = torch.tensor([ysum], device=dev, dtype=torch.float64)
+        dist.all_reduce(ysum_all)
+        e2e = {"value": I_tot / float(dt[0]) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(P.I * 8), "ms_per_step": 1e3 * float(dt[0]),
+               "api": "qups_b200.das_spec on this rank's transmit shard (pinned host -> device) + NCCL all-reduce of the "
+                      "partial images + image read-back on rank 0",
+               "sharding": "transmits (each rank uploads 1/N of the cube)", "image_abs_sum": full}
+    elif not a.no_e2e:
         L = _lib.lib()
         pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
         hPi = pin(np.asarray(Pi_slab, f32).reshape(3, -1, order="F").T)
@@ -285,7 +348,7 @@ def main():
 
     peak, peak_src = measured_peaks()
     from qups_b200.synth import DasProblem
-    loc = DasProblem(P.name, Pi_slab, P.Pr, P.Pv, P.Nv, P.T, P.fs, P.t0, P.c0, P.opts, P.interp)
+    loc = DasProblem(P.name, Pi_slab, P.Pr, np.zeros((3, M_loc)), np.zeros((3, M_loc)), P.T, P.fs, P.t0, P.c0, P.opts, P.interp)
     bytes_launch = loc.bytes_alg()
     achieved = bytes_launch / (float(tmax[1]) * 1e-3) / 1e9
     traffic = None

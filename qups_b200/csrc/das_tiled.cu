@@ -74,6 +74,10 @@ struct TiledArgs {
     uint32_t tilesA, tilesB;
     uint32_t wmax;          // samples per smem slot (even)
     uint32_t numNT;
+    uint32_t nsplit;        // receive-axis split: CTA (tile, split) handles a contiguous range of receive tiles
+    float2 *part;           // nsplit > 1: partial images [nsplit][I], summed in order by das_reduce_kernel
+    uint64_t I;
+    int rev;                // launch the tiles in reverse order (largest I1 first)
     float fs;
     int VS, DV, tpose, accumulate;
     uint64_t total_elems;   // T*N*M
@@ -272,7 +276,10 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- tile coordinates -------------------------------------------------------
-    const uint32_t tile = blockIdx.x;
+    const uint32_t bid = a.rev ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+    const uint32_t tile = bid / a.nsplit, split = bid % a.nsplit;
+    // receive tiles [nt0, nt1) of this CTA (balanced contiguous ranges)
+    const uint32_t nt0 = (uint32_t)(((uint64_t)a.numNT * split) / a.nsplit), nt1 = (uint32_t)(((uint64_t)a.numNT * (split + 1)) / a.nsplit);
     const uint32_t ta = tile % a.tilesA, tb = (tile / a.tilesA) % a.tilesB, tc = tile / (a.tilesA * a.tilesB);
     // lane patch: a warp covers kLPA pixels along the lane axis x (32/kLPA) pixel-row pairs; a compact 2-D
     // patch keeps the tap addresses of a half-warp inside one 128-byte row of shared memory
@@ -328,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             hi = __reduce_max_sync(0xffffffffu, hi);
             if (lane == 0) { atomicMin(&s_dvmin[m], lo); atomicMax(&s_dvmax[m], hi); }
         }
-        for (uint32_t n = 0; n < a.N; ++n) {
+        for (uint32_t n = nt0 * kNT; n < min(nt1 * kNT, a.N); ++n) {
             const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
             int lo = INT_MAX, hi = INT_MIN;
 #pragma unroll
@@ -407,18 +414,23 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         }
-        if (a.accumulate) {
-            if (valid[0]) { const float2 o = a.y[pix[0]]; acc0.x += o.x; acc0.y += o.y; }
-            if (valid[1]) { const float2 o = a.y[pix[1]]; acc1.x += o.x; acc1.y += o.y; }
+        if (a.nsplit > 1) { // partial image of this receive range; das_reduce_kernel sums the splits in order
+            if (valid[0]) a.part[(uint64_t)split * a.I + pix[0]] = acc0;
+            if (valid[1]) a.part[(uint64_t)split * a.I + pix[1]] = acc1;
+        } else {
+            if (a.accumulate) {
+                if (valid[0]) { const float2 o = a.y[pix[0]]; acc0.x += o.x; acc0.y += o.y; }
+                if (valid[1]) { const float2 o = a.y[pix[1]]; acc1.x += o.x; acc1.y += o.y; }
+            }
+            if (valid[0]) a.y[pix[0]] = acc0;
+            if (valid[1]) a.y[pix[1]] = acc1;
         }
-        if (valid[0]) a.y[pix[0]] = acc0;
-        if (valid[1]) a.y[pix[1]] = acc1;
     } else {
         // =========================== producer warp =================================
         __syncthreads(); // matches the consumers' post-phase-0 barrier
         const bool cinv_ok = (cinv > 0.f) && (fs > 0.f);
         uint32_t it = 0;
-        for (uint32_t nt = 0; nt < a.numNT; ++nt) {
+        for (uint32_t nt = nt0; nt < nt1; ++nt) {
             const uint32_t n = nt * kNT + lane;
             const bool has = (lane < kNT) && (n < a.N);
             int olo = INT_MAX, ohi = INT_MIN;
@@ -514,6 +526,19 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
     }
 }
 
+// sums the receive-split partial images in split order (deterministic) into y
+__global__ void __launch_bounds__(256) das_reduce_kernel(float2 *y, const float2 *part, uint64_t I, uint32_t nsplit, int accumulate) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < I; i += (uint64_t)gridDim.x * blockDim.x) {
+        float2 acc = accumulate ? y[i] : make_float2(0.f, 0.f);
+        for (uint32_t s = 0; s < nsplit; ++s) {
+            const float2 v = part[(uint64_t)s * I + i];
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+        y[i] = acc;
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------
 static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax) {
     size_t head = kBarBytes + sizeof(int4) * kStages + sizeof(int2) * kStages * kNT + sizeof(int) * (2 * (size_t)M + 2 * (size_t)N);
@@ -574,9 +599,40 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<(unsigned)tiles, kThreads, smem, st>>>(t);
+    // Work decomposition: when the pixel tiles alone cannot fill ~4 waves of the 148 SMs (small images, pixel-sharded
+    // multi-GPU slabs), split the receive axis across CTAs so the grid stays balanced; partials are summed in order.
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t want = 4ull * QUPS_MINBLOCKS * (uint64_t)sms;
+    uint32_t nsplit = 1;
+    if (tiles < want) nsplit = (uint32_t)((want + tiles - 1) / tiles);
+    if (nsplit > t.numNT / 2) nsplit = t.numNT / 2;   // at least two receive tiles per CTA
+    if (nsplit < 1) nsplit = 1;
+    if (const char *e2 = getenv("QUPS_B200_NSPLIT")) { int v = atoi(e2); if (v >= 1 && (uint32_t)v <= t.numNT) nsplit = (uint32_t)v; }
+    if (tiles * nsplit > 0x7fffffffull) nsplit = 1;
+    t.nsplit = nsplit;
+    t.rev = 1;
+    if (const char *e3 = getenv("QUPS_B200_TILE_REV")) t.rev = atoi(e3) != 0;
+    t.I = a.I;
+    t.part = nullptr;
+    if (nsplit > 1) {
+        e = cudaMallocAsync((void **)&t.part, sizeof(float2) * a.I * nsplit, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<(unsigned)(tiles * nsplit), kThreads, smem, st>>>(t);
     count_launch();
-    return (int)cudaGetLastError();
+    e = cudaGetLastError();
+    if (nsplit > 1) {
+        if (e == cudaSuccess) {
+            const uint64_t g = (a.I + 255) / 256;
+            das_reduce_kernel<<<(unsigned)(g < 4096 ? g : 4096), 256, 0, st>>>(t.y, t.part, a.I, nsplit, t.accumulate);
+            count_launch();
+            e = cudaGetLastError();
+        }
+        cudaFreeAsync(t.part, st);
+    }
+    return (int)e;
 }
 
 } // namespace qups

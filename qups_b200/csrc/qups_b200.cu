@@ -359,7 +359,7 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
         if (nch > 1) {
             if ((e = cudaEventRecord(g_ws.ev[HostWs::NEV - 1], sc)) != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord");
             if (rc == 0 && (e = cudaStreamWaitEvent(sx, g_ws.ev[HostWs::NEV - 1], 0)) != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent");
-            // chunk sizes grow geometrically (x1.6): the first copy that cannot overlap anything is short, and each
+            // chunk sizes grow geometrically (x1.3): the first copy that cannot overlap anything is short, and each
             // later copy still finishes before the previous chunk's beamforming does (copy is faster than compute)
             uint64_t bounds[HostWs::NEV];
             uint64_t nb = 0, pos = 0;
@@ -367,15 +367,15 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
                 for (uint64_t c = 0; c <= nch; ++c) bounds[c] = p->M * c / nch;
                 nb = nch;
             } else {
-                double sz = (double)p->M / 16.0;
-                if (sz < 8) sz = 8;
+                double sz = (double)p->M / 8.0; // launches below ~32 transmits lose >8 % to per-launch setup (measured)
+                if (sz < 32) sz = 32;
                 bounds[0] = 0;
                 while (pos < p->M && nb < HostWs::NEV - 3) {
                     uint64_t step = (uint64_t)sz;
                     if (p->M - pos < step + step / 2) step = p->M - pos;
                     pos += step;
                     bounds[++nb] = pos;
-                    sz *= 1.6;
+                    sz *= 1.3;
                 }
                 bounds[nb] = p->M;
             }

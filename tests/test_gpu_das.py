@@ -213,3 +213,23 @@ def test_host_entry_point_matches_device_entry_point(oracle_c):
         assert rc == 0, _lib.lib().qups_last_error()
         assert rel_linf(y.reshape(ref.shape, order="F"), ref) < TOL
     _lib.lib().qups_host_release()
+
+
+def test_tiled_volume_matrix_array(oracle_c):
+    """3-D ScanCartesian voxels + TransducerMatrix (BASELINE config 4, reduced): tiles over (I1, I2) per I3 slice."""
+    import qups_b200
+    from qups_b200 import synth
+    Pr = synth.matrix_array(6, 5, 0.3e-3)
+    g = np.linspace(-1e-3, 1e-3, 3)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    Pv = np.stack([X.reshape(-1), Y.reshape(-1), np.full(9, -4e-3)], 0)
+    Nv = np.tile(np.array([[0.0], [0.0], [1.0]]), (1, 9))
+    ax = np.linspace(-1.5e-3, 1.5e-3, 19)
+    Pi = synth.scan_cartesian(ax, np.linspace(3e-3, 9e-3, 37), ax[:7])
+    rng = np.random.default_rng(9)
+    x = np.asfortranarray((rng.standard_normal((400, 30, 9)) + 1j * rng.standard_normal((400, 30, 9))).astype(np.complex64))
+    P = dict(Pi=Pi, Pr=Pr, Pv=Pv, Nv=Nv, x=x, t0=0.0, fs=25e6, c=1540.0, opts=("diverging-waves",))
+    ref = _ora(oracle_c, "DAS", P, "cubic")
+    got = _gpu("DAS", P, "cubic", "tiled")
+    assert got.shape == ref.shape == (37, 19, 7, 1, 1)
+    assert np.abs(ref).max() > 0 and rel_linf(got, ref) < TOL
