@@ -143,8 +143,9 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--shard", default="tx", choices=["tx", "pixels"],
-                    help="N>1 decomposition: transmit partition + all-reduce (default) or pixel slabs without collective")
+    ap.add_argument("--shard", default="pixels", choices=["tx", "pixels"],
+                    help="N>1 decomposition of the device-resident leg: pixel slabs without collective (default) or transmit "
+                         "partition + all-reduce; the e2e leg always uses the transmit partition (1/N of the cube per GPU)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,12 +199,12 @@ def main():
     x_np = synth.noise_cube(P.T, P.N, P.M, seed=0)
     t = lambda v: torch.from_numpy(np.ascontiguousarray(np.asarray(v, f32))).to(dev)
     if tx_mode:
-        m0, mc = shard.tx_shard(P.M, rank, world)
+        msel = np.arange(rank, P.M, world)  # interleaved transmits: every rank sees the same mix of geometries
         Pi_slab, Isz = P.Pi, P.Pi.shape[1:]
-        Pv_l = np.broadcast_to(np.asarray(P.Pv, f32), (3, P.M))[:, m0:m0 + mc]
-        Nv_l = np.broadcast_to(np.asarray(P.Nv, f32), (3, P.M))[:, m0:m0 + mc]
-        x_d = torch.from_numpy(np.asfortranarray(x_np[:, :, m0:m0 + mc])).to(dev)
-        M_loc = mc
+        Pv_l = np.broadcast_to(np.asarray(P.Pv, f32), (3, P.M))[:, msel]
+        Nv_l = np.broadcast_to(np.asarray(P.Nv, f32), (3, P.M))[:, msel]
+        x_d = torch.from_numpy(np.asfortranarray(x_np[:, :, msel])).to(dev)
+        M_loc = len(msel)
         cfg["sharding"] = "transmits: each rank holds 1/N of the cube, full-size partial image, one NCCL all-reduce per step"
     else:
         Pi_slab, axis, s0, cnt = shard.pixel_shard(P.Pi, rank, world)
@@ -265,10 +266,10 @@ def main():
         # N > 1: transmit partition (SURVEY.md §8e mode 2).  Each rank uploads ONLY its 1/N of the channel cube from
         # pinned host memory, beamforms a full-size partial image and the images are summed with one NCCL all-reduce;
         # rank 0 reads the image back.  (Pixel sharding would make every rank upload the whole 1 GB cube.)
-        m0, mc = shard.tx_shard(P.M, rank, world)
-        hX = torch.from_numpy(np.ascontiguousarray(x_np[:, :, m0:m0 + mc].transpose(2, 1, 0))).pin_memory()
-        Pvb = np.broadcast_to(np.asarray(P.Pv, f32), (3, P.M))[:, m0:m0 + mc]
-        Nvb = np.broadcast_to(np.asarray(P.Nv, f32), (3, P.M))[:, m0:m0 + mc]
+        msel = np.arange(rank, P.M, world)  # interleaved transmit shard (balanced across ranks)
+        hX = torch.from_numpy(np.ascontiguousarray(x_np[:, :, msel].transpose(2, 1, 0))).pin_memory()
+        Pvb = np.broadcast_to(np.asarray(P.Pv, f32), (3, P.M))[:, msel]
+        Nvb = np.broadcast_to(np.asarray(P.Nv, f32), (3, P.M))[:, msel]
         hg = [torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for v in (np.asarray(P.Pi, f32), np.asarray(P.Pr, f32), Pvb, Nvb)]
         hY = torch.empty((P.I,), dtype=torch.complex64).pin_memory()
 
