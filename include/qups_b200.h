@@ -15,6 +15,7 @@
  *   qups_wsinterpd    <-  kern/wsinterpd.m:205-213  (src/interpd.cu:422-447)
  *   qups_greens       <-  src/UltrasoundSystem.m:718 k.feval(x,ps,as,pn,pv,kn,sb,iblock,[t0k,t0x,fs,fsr,cinv,R0],[E,E],flag)
  *                         src/greens.cu:88-122      greens / greensf / greensh
+ *   qups_convd        <-  kern/convd.m:194-201      k.feval(z, x, y, sizes)   (src/convd.cu:133-156 conv / convf / convc / convcf)
  *   qups_modulate     <-  kern/das_spec.m:413-417   x .* exp(2i*pi*fmod.*t)  (CPU-branch convention, fused pre-pass)
  *   qups_*_host       <-  the same calls for callers holding HOST arrays (plain MEX, no gpuArray)
  *
@@ -176,6 +177,19 @@ typedef struct {
  * Pr : 3 x N x E ; Pv : 3 x M x E ; kern : complex T */
 QUPS_API int qups_greens(const qups_greens_params *p, void *y, const void *Pi, const void *a, const void *Pr, const void *Pv,
                 const void *kern, qups_stream_t stream);
+
+/* ---- convd ---------------------------------------------------------------- */
+/* Batched direct 1-D convolution along one dimension: replaces conv/convf/convc/convcf (src/convd.cu:133-156,
+ * launcher kern/convd.m:135-201).  x is C x Lx x S, y is yC x Ly x yS (yC in {1,C}, yS in {1,S}), z is C x Lz x S;
+ * shape 0 'full' (Lz = Lx+Ly-1), 1 'same' (Lz = Lx, centred as MATLAB conv), 2 'valid' (Lz = max(Lx-Ly+1, 0)). */
+typedef struct {
+    uint32_t struct_size;
+    int32_t dtype;      /* QUPS_F32 | QUPS_F64 */
+    int32_t is_complex; /* interleaved complex data */
+    int32_t shape;
+    uint64_t C, S, Lx, Ly, yC, yS;
+} qups_convd_params;
+QUPS_API int qups_convd(const qups_convd_params *p, void *z, const void *x, const void *y, qups_stream_t stream);
 
 /* ---- misc --------------------------------------------------------------- */
 QUPS_API const char *qups_last_error(void);

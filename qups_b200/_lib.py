@@ -19,7 +19,7 @@ INTERP = {"nearest": NEAREST, "linear": LINEAR, "cubic": CUBIC, "lanczos3": LANC
 
 EXPORTS = (
     "qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
-    "qups_greens", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
+    "qups_greens", "qups_convd", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
 )
 
 
@@ -68,6 +68,13 @@ class GreensParams(C.Structure):
     ]
 
 
+class ConvdParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("dtype", C.c_int32), ("is_complex", C.c_int32), ("shape", C.c_int32),
+        ("C", C.c_uint64), ("S", C.c_uint64), ("Lx", C.c_uint64), ("Ly", C.c_uint64), ("yC", C.c_uint64), ("yS", C.c_uint64),
+    ]
+
+
 _lib = None
 
 
@@ -91,6 +98,8 @@ def lib() -> C.CDLL:
     L.qups_wsinterpd2.argtypes = [C.POINTER(Ws2Params), vp, vp, vp, vp, vp, vp]
     L.qups_wsinterpd.argtypes = [C.POINTER(Ws2Params), vp, vp, vp, vp, vp]
     L.qups_greens.argtypes = [C.POINTER(GreensParams), vp, vp, vp, vp, vp, vp, vp]
+    L.qups_convd.argtypes = [C.POINTER(ConvdParams), vp, vp, vp, vp]
+    L.qups_convd.restype = C.c_int
     for f in ("qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
               "qups_greens", "qups_version"):
         getattr(L, f).restype = C.c_int

@@ -27,6 +27,7 @@ UNITS = {
     "das_generic.cu": ["-fmad=false"],
     "greens.cu": ["-fmad=false"],
     "wsinterpd2.cu": ["-fmad=false"],
+    "convd.cu": ["-fmad=false"],
     "das_tiled.cu": [],
     "qups_b200.cu": [],
 }

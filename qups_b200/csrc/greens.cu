@@ -13,6 +13,8 @@
 // thread owns output samples and walks the scatterers IN ORDER with a cheap
 // window test — deterministic, no atomics, and the per-sample sum order equals
 // the oracle's.  Compiled with -fmad=false.
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "other_kernels.cuh"
 
@@ -97,23 +99,180 @@ __global__ void __launch_bounds__(kGThreads) greens_kernel(const GreensDev<R> p,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Binned variant (the default): per (trace, 2048-sample block, scatterer chunk) the staged entries are bucketed
+// by arrival sample with a STABLE counting sort (warp-ordered ranks via match_any), so an output sample visits only
+// the ~(kspan + bin)/S fraction of scatterers that can reach it instead of testing all of them.  Deterministic (no
+// atomics, fixed order: by bucket, then by scatterer index); the per-sample sum order differs from the oracle's
+// plain scatterer order, hence tolerance-level (not bit-level) parity.  greens_kernel above stays as the exact-order
+// variant (QUPS_B200_GREENS=simple) and as the fallback for very long waveforms.
+constexpr int kGBW = 32;      // bucket width in output samples
+constexpr int kGNB = 128;     // max buckets per block: (2048 + kspan + 4)/32 + 1 must fit
+
+template <typename DK, typename DOUT, typename R>
+__global__ void __launch_bounds__(kGThreads) greens_binned_kernel(const GreensDev<R> p, DOUT *y, const R *Pi, const R *amp,
+                                                                  const R *Pr, const R *Pv, const DK *kern) {
+    constexpr int kGChunk = (sizeof(R) == 4) ? 2048 : 1024;
+    constexpr int kW = kGThreads / 32;
+    __shared__ R s_ttx[kGChunk], s_trx[kGChunk], s_w[kGChunk];
+    __shared__ float s_c[kGChunk];
+    __shared__ unsigned short s_perm[kGChunk];
+    __shared__ int s_cnt[kW][kGNB];
+    __shared__ int s_start[kGNB + 1];
+    const uint64_t n = blockIdx.x, m = blockIdx.y;
+    const uint64_t EE = p.E * p.E, total = p.I * EE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DOUT *yt = y + p.S * (n + p.N * m);
+    const float kspan = (float)p.kspan;
+    const int nbk = min(kGNB, (int)((kGThreads * 8 + kspan + 4.f) / kGBW) + 2);
+    for (uint64_t sb = 0; sb < p.S; sb += (uint64_t)kGThreads * 8) {
+        cplx<R> acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = {R(0), R(0)};
+        // bucket origin: arrivals c in [org, org + nbk*BW) can reach this block
+        const float org = (float)(p.n0 + (long long)sb) - kspan - 2.f;
+        for (uint64_t e0 = 0; e0 < total; e0 += kGChunk) {
+            const int cnt = (int)((total - e0 < (uint64_t)kGChunk) ? (total - e0) : kGChunk);
+            __syncthreads();
+            for (int q = threadIdx.x; q < kW * kGNB; q += kGThreads) (&s_cnt[0][0])[q] = 0;
+            for (int q = threadIdx.x; q < cnt; q += kGThreads) {
+                const uint64_t e = e0 + q, i = e / EE, em = (e % EE) / p.E, en = e % p.E;
+                const R sx = Pi[3 * i], sy = Pi[3 * i + 1], sz = Pi[3 * i + 2];
+                const R *pr = Pr + 3 * (n + p.N * en), *pv = Pv + 3 * (m + p.M * em);
+                const R r_rx = rx_dist(sx, sy, sz, pr[0], pr[1], pr[2]);
+                const R r_tx = rx_dist(sx, sy, sz, pv[0], pv[1], pv[2]);
+                R att;
+                if (p.R0 != R(0)) {
+                    const R a = (r_rx > p.R0) ? r_rx : p.R0, b = (r_tx > p.R0) ? r_tx : p.R0;
+                    att = div_rn(amp[i], mul_rn(a, b));
+                } else att = amp[i];
+                const R trx = mul_rn(div_rn(r_rx, p.c0), p.fs), ttx = mul_rn(div_rn(r_tx, p.c0), p.fs);
+                s_ttx[q] = ttx;
+                s_trx[q] = mul_rn(-p.fsr, trx);
+                s_w[q] = div_rn(att, p.fsr);
+                s_c[q] = (float)add_rn(add_rn(ttx, trx), p.t0s);
+            }
+            __syncthreads();
+            // ---- stable counting sort of the chunk by bucket: warp w owns a contiguous, ascending range ----
+            const int per = ((cnt + kW * 32 - 1) / (kW * 32)) * 32;
+            const int q0 = warp * per, q1 = min(cnt, q0 + per);
+            for (int qb = q0; qb < q1; qb += 32) {
+                const int q = qb + lane;
+                int b = -1;
+                if (q < q1) {
+                    const float rel = (s_c[q] - org) * (1.f / kGBW);
+                    if (rel >= 0.f && rel < (float)nbk) b = (int)rel;
+                }
+                const unsigned mk = __match_any_sync(0xffffffffu, b);
+                if (b >= 0 && lane == (__ffs((int)mk) - 1)) s_cnt[warp][b] += __popc(mk);
+                __syncwarp();
+            }
+            __syncthreads();
+            // bucket totals (one thread per bucket) -> exclusive scan (one warp) -> per-warp write cursors
+            if ((int)threadIdx.x < nbk) {
+                int tot = 0;
+                for (int w = 0; w < kW; ++w) tot += s_cnt[w][threadIdx.x];
+                s_start[threadIdx.x + 1] = tot;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int carry = 0;
+                for (int b0 = 0; b0 < nbk; b0 += 32) {
+                    const int b = b0 + lane;
+                    int v = (b < nbk) ? s_start[b + 1] : 0, incl = v;
+                    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+                    if (b < nbk) s_start[b + 1] = carry + incl;
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) s_start[0] = 0;
+            }
+            __syncthreads();
+            if ((int)threadIdx.x < nbk) {
+                int run = s_start[threadIdx.x];
+                for (int w = 0; w < kW; ++w) { const int c = s_cnt[w][threadIdx.x]; s_cnt[w][threadIdx.x] = run; run += c; }
+            }
+            __syncthreads();
+            for (int qb = q0; qb < q1; qb += 32) {
+                const int q = qb + lane;
+                int b = -1;
+                if (q < q1) {
+                    const float rel = (s_c[q] - org) * (1.f / kGBW);
+                    if (rel >= 0.f && rel < (float)nbk) b = (int)rel;
+                }
+                const unsigned mk = __match_any_sync(0xffffffffu, b);
+                if (b >= 0) {
+                    const int pos = s_cnt[warp][b] + __popc(mk & ((1u << lane) - 1u));
+                    s_perm[pos] = (unsigned short)q;
+                }
+                __syncwarp();
+                if (b >= 0 && lane == (__ffs((int)mk) - 1)) s_cnt[warp][b] += __popc(mk);
+                __syncwarp();
+            }
+            __syncthreads();
+            // ---- evaluation: each owned sample walks only the buckets that can reach it ----
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int sr = threadIdx.x + k * kGThreads;                 // sample inside the block
+                const uint64_t s = sb + (uint64_t)sr;
+                if (s >= p.S) continue;
+                const R tv = (R)(p.n0 + (long long)s);
+                // arrivals c with tv - c in [-2, kspan + 2]  <=>  c - org in [sr, sr + kspan + 4]
+                const int b0 = sr / kGBW, b1 = min(nbk - 1, (int)(((float)sr + kspan + 4.f) / kGBW));
+                const int e_lo = s_start[b0], e_hi = s_start[b1 + 1];
+                for (int e = e_lo; e < e_hi; ++e) {
+                    const int q = s_perm[e];
+                    const R d = tv - (R)s_c[q];
+                    if (d >= R(-2) && d <= p.kspan + R(2)) {
+                        R t1 = sub_rn(tv, s_ttx[q]);
+                        t1 = sub_rn(t1, p.t0s);
+                        t1 = mul_rn(p.fsr, t1);
+                        const R xq = add_rn(R(1), add_rn(t1, s_trx[q]));
+                        const cplx<R> v = interp1<DK>(kern, (long)p.T, xq, p.interp);
+                        acc[k].re = add_rn(acc[k].re, mul_rn(s_w[q], v.re));
+                        acc[k].im = add_rn(acc[k].im, mul_rn(s_w[q], v.im));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t s = sb + threadIdx.x + (uint64_t)k * kGThreads;
+            if (s < p.S)
+                data_traits<DOUT>::store(yt, s, {(typename data_traits<DOUT>::real)acc[k].re,
+                                                 (typename data_traits<DOUT>::real)acc[k].im});
+        }
+    }
+}
+
 int launch_greens(const qups_greens_params &p, void *y, const void *Pi, const void *a, const void *Pr, const void *Pv,
                   const void *kern, cudaStream_t st) {
     if (p.S == 0 || p.N == 0 || p.M == 0) return 0;
     if (p.N > 0x7fffffffull || p.M > 65535) return -3;
     const uint64_t E = p.E ? p.E : 1;
     dim3 grid((unsigned)p.N, (unsigned)p.M), block(kGThreads);
+    // bucketed kernel unless the waveform is so long that its reach exceeds the bucket table, or the exact
+    // scatterer-order variant is requested (tests pin bit-exactness on it)
+    bool binned = ((double)p.T / p.fsr + 4.0 + kGThreads * 8) / kGBW + 2 <= kGNB;
+    if (const char *ev = getenv("QUPS_B200_GREENS")) { if (!strcmp(ev, "simple")) binned = false; }
     if (p.dtype == QUPS_F32) {
         GreensDev<float> d{p.I, p.S, p.T, p.N, p.M, E, (long long)p.n0, p.interp,
                            (float)p.t0x * (float)p.fs, (float)p.fs, (float)p.fsr, (float)p.c0, (float)p.R0,
                            (float)((double)p.T / p.fsr)};
-        greens_kernel<float2, float2, float><<<grid, block, 0, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a,
-                                                                     (const float *)Pr, (const float *)Pv, (const float2 *)kern);
+        if (binned)
+            greens_binned_kernel<float2, float2, float><<<grid, block, 0, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a,
+                                                                                (const float *)Pr, (const float *)Pv, (const float2 *)kern);
+        else
+            greens_kernel<float2, float2, float><<<grid, block, 0, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a,
+                                                                         (const float *)Pr, (const float *)Pv, (const float2 *)kern);
     } else if (p.dtype == QUPS_F64) {
         GreensDev<double> d{p.I, p.S, p.T, p.N, p.M, E, (long long)p.n0, p.interp,
                             p.t0x * p.fs, p.fs, p.fsr, p.c0, p.R0, (double)p.T / p.fsr};
-        greens_kernel<double2, double2, double><<<grid, block, 0, st>>>(d, (double2 *)y, (const double *)Pi, (const double *)a,
-                                                                        (const double *)Pr, (const double *)Pv, (const double2 *)kern);
+        if (binned)
+            greens_binned_kernel<double2, double2, double><<<grid, block, 0, st>>>(d, (double2 *)y, (const double *)Pi, (const double *)a,
+                                                                                   (const double *)Pr, (const double *)Pv, (const double2 *)kern);
+        else
+            greens_kernel<double2, double2, double><<<grid, block, 0, st>>>(d, (double2 *)y, (const double *)Pi, (const double *)a,
+                                                                            (const double *)Pr, (const double *)Pv, (const double2 *)kern);
     } else
         return -3;
     count_launch(1);

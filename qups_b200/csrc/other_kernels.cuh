@@ -9,4 +9,5 @@ int launch_wsinterpd2(const qups_ws2_params &p, void *y, const void *w, const vo
                       cudaStream_t st);
 int launch_greens(const qups_greens_params &p, void *y, const void *Pi, const void *a, const void *Pr, const void *Pv,
                   const void *kern, cudaStream_t st);
+int launch_convd(const qups_convd_params &p, void *z, const void *x, const void *y, cudaStream_t st);
 } // namespace qups

@@ -439,4 +439,16 @@ int qups_greens(const qups_greens_params *p, void *y, const void *Pi, const void
     return 0;
 }
 
+int qups_convd(const qups_convd_params *p, void *z, const void *x, const void *y, qups_stream_t stream) {
+    g_err[0] = 0;
+    if (!p || p->struct_size != sizeof(qups_convd_params)) return fail(QUPS_ERR_INVALID, "bad qups_convd_params");
+    if (p->shape < 0 || p->shape > 2) return fail(QUPS_ERR_INVALID, "shape must be full(0), same(1) or valid(2)");
+    if (!((p->yC == 1 || p->yC == p->C) && (p->yS == 1 || p->yS == p->S))) return fail(QUPS_ERR_INVALID, "A and B must have compatible dimensions");
+    if (int e = launch_convd(*p, z, x, y, (cudaStream_t)stream)) {
+        if (e == -3) return fail(QUPS_ERR_UNSUPPORTED, "unsupported dtype for convd");
+        return cuda_fail(e, "convd kernel");
+    }
+    return 0;
+}
+
 } // extern "C"

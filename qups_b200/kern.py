@@ -345,3 +345,54 @@ def wsinterpd2(x, t1, t2, dim=1, w=1, sdim=(), interp="linear", extrapval=0, ome
 def wsinterpd(x, t, dim=1, w=1, sdim=(), interp="linear", extrapval=0, omega=0):
     """Mirror of ``kern/wsinterpd.m:1`` (single delay table)."""
     return wsinterpd2(x, t, None, dim, w, sdim, interp, extrapval, omega)
+
+
+def convd(x, y=None, dim=None, shape="full"):
+    """Batched 1-D convolution along one dimension — mirror of ``kern/convd.m:1`` (GPU branch :135-201).
+
+    C = convd(A, B, dim, shape); B defaults to conj(flip(A)) (auto-correlation); dim (1-based) defaults to the
+    first non-singleton dimension; shape in {'full','same','valid'}.  Returns (C, lags) with lags as :102-110.
+    B must match A outside `dim`, or be singleton in all dims before and/or all dims after `dim`.
+    """
+    if shape not in ("full", "same", "valid"):
+        raise ValueError("shape must be one of {'full', 'same', 'valid'}")
+    xt = _as_tensor(x)
+    numpy_out = not (isinstance(x, torch.Tensor) and x.is_cuda)
+    if dim is None:
+        dim = next((d + 1 for d, s in enumerate(xt.shape) if s != 1), 1)
+    d0 = dim - 1
+    nd = max(xt.ndim, dim)
+    xs = _sz(xt, nd)
+    yt = torch.conj(torch.flip(xt.reshape(xs), [d0])).resolve_conj() if y is None else _as_tensor(y)
+    ys = _sz(yt, nd)
+    cplx = xt.is_complex() or yt.is_complex()
+    dbl = xt.dtype in (torch.float64, torch.complex128) or yt.dtype in (torch.float64, torch.complex128)
+    dt = (torch.complex128 if dbl else torch.complex64) if cplx else (torch.float64 if dbl else torch.float32)
+    C_, S_ = int(np.prod(xs[:d0])) if d0 else 1, int(np.prod(xs[d0 + 1:])) if d0 + 1 < nd else 1
+    yC, yS = int(np.prod(ys[:d0])) if d0 else 1, int(np.prod(ys[d0 + 1:])) if d0 + 1 < nd else 1
+    if not ((yC in (1, C_)) and (yS in (1, S_)) and (yC == 1 or tuple(ys[:d0]) == tuple(xs[:d0]))
+            and (yS == 1 or tuple(ys[d0 + 1:]) == tuple(xs[d0 + 1:]))):
+        raise AssertionError("A and B must have compatible dimensions")
+    Lx, Ly = xs[d0], ys[d0]
+    if shape == "full":
+        Lz, lags = Lx + Ly - 1, np.arange(-(Ly - 1), Lx)
+    elif shape == "same":
+        Lz, lags = Lx, np.arange(0, Lx) - (Ly - 1) // 2
+    else:
+        Lz, lags = max(Lx - Ly + 1, 0), np.arange(0, max(Lx - Ly + 1, 0))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dX, dY = _colmajor(xt.reshape(xs), dt, dev), _colmajor(yt.reshape(ys), dt, dev)
+    osz = tuple(xs[:d0]) + (Lz,) + tuple(xs[d0 + 1:])
+    z = torch.zeros(int(np.prod(osz)), dtype=dt, device=dev)
+    p = _lib.ConvdParams()
+    p.struct_size = C.sizeof(_lib.ConvdParams)
+    p.dtype, p.is_complex = (_lib.F64 if dbl else _lib.F32), int(cplx)
+    p.shape = {"full": 0, "same": 1, "valid": 2}[shape]
+    p.C, p.S, p.Lx, p.Ly, p.yC, p.yS = C_, S_, Lx, Ly, yC, yS
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().qups_convd(C.byref(p), _ptr(z), _ptr(dX), _ptr(dY), _stream(dev)))
+    out = _from_colmajor(z, osz)
+    lag_shape = [1] * nd
+    lag_shape[d0] = -1
+    lags = lags.reshape(lag_shape)
+    return (np.asfortranarray(out.cpu().numpy()) if numpy_out else out), lags

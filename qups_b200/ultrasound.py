@@ -172,10 +172,71 @@ class UltrasoundSystem:
             a, b = int(idx[0]), int(idx[-1])
             x, n0 = x[a:b + 1], n0 + a
         chd = ChannelData(x, n0 / fs, fs)
-        # focusTx is the identity for a pure FSA sequence (:3453-3455); other sequences are a "next" row
-        if self.seq.type != "FSA":
-            raise _lib.QupsError(-3, "greens + focusTx for non-FSA sequences is not implemented in this round")
-        return chd
+        # synthesize the requested sequence from the FSA data (:877); identity for a pure FSA sequence
+        return focusTx(chd, self.seq, pv, interp=interp)
+
+
+def seq_delays(seq: "Sequence", tx: np.ndarray) -> np.ndarray:
+    """Sequence.delays(tx): M x S transmit delays (src/Sequence.m:888-925)."""
+    p = np.asarray(tx, np.float64)                       # 3 x M elements
+    M = p.shape[1]
+    if seq.type == "FSA":
+        return np.zeros((M, M))
+    f = np.asarray(seq.focus, np.float64)                # 3 x S
+    if seq.type == "PW":
+        return -(f[:, None, :] * p[:, :, None]).sum(0) / seq.c0
+    v = f[:, None, :] - p[:, :, None]                    # element -> focus
+    tau = np.sqrt((v ** 2).sum(0)) / seq.c0
+    if seq.type == "FC":
+        sgn = 1.0
+    elif seq.type == "DV":
+        sgn = -1.0
+    else:  # VS: negative when the focus is behind the transducer
+        sgn = np.where((f[2][None, :] > p[2][:, None]).all(0), 1.0, -1.0)[None, :]
+    return tau * sgn
+
+
+def seq_apodization(seq: "Sequence", tx: np.ndarray) -> np.ndarray:
+    """Sequence.apodization(tx) default (src/Sequence.m:951-960)."""
+    M = np.asarray(tx).shape[1]
+    if seq.type == "FSA":
+        return np.eye(M)
+    return np.ones((M, np.asarray(seq.focus).shape[1]))
+
+
+def focusTx(chd: "ChannelData", seq: "Sequence", tx: np.ndarray, interp="cubic", buffer=0, ws2=None) -> "ChannelData":
+    """chd' = focusTx(us, chd, seq): synthesise the transmits of `seq` from full-synthetic-aperture data,
+    chd'(t,n,m') = sum_m apd(m,m') * chd(t - tau(m,m'), n, m)    (src/UltrasoundSystem.m:3374-3503) via
+    sample2sep over the transmit dimension (:3498 -> src/ChannelData.m:1338 -> wsinterpd2)."""
+    ws2 = kern.wsinterpd2 if ws2 is None else ws2
+    tau = -seq_delays(seq, tx)                            # M x M'   (:3448)
+    apd = seq_apodization(seq, tx)
+    if seq.type == "FSA" and not np.any(tau) and np.array_equal(apd, np.eye(apd.shape[0])):
+        return chd                                        # identity (:3453-3455)
+    fs = float(chd.fs)
+    nz = (apd != 0) | np.zeros(tau.shape, bool)
+    nmin = int(np.floor(tau[nz].min() * fs))
+    nmax = int(np.ceil(tau[nz].max() * fs))
+    t0 = np.asarray(chd.t0, np.float64) + nmin / fs       # (:3460)
+    tau = tau - nmin / fs
+    x = chd.data
+    pad = (nmax - nmin) + int(buffer)                     # zeropad(chd, 0, ...)  (:3462)
+    is_t = isinstance(x, torch.Tensor)
+    if is_t:
+        x = torch.cat([x, torch.zeros((pad,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)], 0) if pad else x
+        rt = np.float32 if x.dtype == torch.complex64 else np.float64
+    else:
+        x = np.concatenate([x, np.zeros((pad,) + x.shape[1:], x.dtype)], 0) if pad else x
+        rt = np.float32 if x.dtype == np.complex64 else np.float64
+    Tn, N, M = x.shape[:3]
+    # sample2sep(chd.time, -tau, interp, apd, mdim): ntau1 = (time - t0) fs = 0..T'-1 ; ntau2 = -tau fs
+    t1 = np.arange(Tn, dtype=rt).reshape(Tn, 1, 1, 1)
+    t2 = (-(tau * fs)).astype(rt).reshape(1, 1, M, -1)
+    w = apd.astype(rt).reshape(1, 1, apd.shape[0], -1)
+    x4 = x.reshape(tuple(x.shape[:3]) + (1,)) if is_t else x.reshape(x.shape[:3] + (1,), order="F")
+    y = ws2(x4, t1, t2, 1, w, (3,), interp, 0, 0)         # T' x N x 1 x M'
+    y = y[:, :, 0, :]
+    return ChannelData(y, t0 if np.ndim(t0) else float(t0), fs)
 
 
 def greens_raw(ps, amp, pn, pv, kern_s, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, interp="cubic", device=None,

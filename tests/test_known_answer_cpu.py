@@ -43,3 +43,28 @@ def test_bftest_psf_location_fsa(oracle_c):
     assert np.abs(b).max() > 0
     iz, ix = np.unravel_index(np.argmax(np.abs(b)), b.shape)
     assert abs(zs[iz] - 15e-3) <= 1.1e-3 and abs(xs[ix] - 2e-3) <= 1.1e-3
+
+
+def test_focustx_host_logic_with_oracle_sampler(oracle_np):
+    """focusTx mirror (src/UltrasoundSystem.m:3374-3503) == brute-force delayed sum, with the ORACLE as the sampler
+    (the product path samples with the CUDA wsinterpd2 kernel; this pins the host logic on CPU)."""
+    from qups_b200.ultrasound import focusTx, Sequence, ChannelData, seq_delays
+    pn = synth.linear_array(8, 0.3e-3)
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((64, 8, 8)) + 1j * rng.standard_normal((64, 8, 8))).astype(np.complex128)
+    th = np.deg2rad([-5, 0, 5])
+    seq = Sequence("PW", np.stack([np.sin(th), 0 * th, np.cos(th)], 0), 1540.0)
+    fs = 20e6
+    out = focusTx(ChannelData(x, 1e-6, fs), seq, pn, "linear", ws2=oracle_np.wsinterpd2)
+    tau = -seq_delays(seq, pn)
+    nmin = np.floor(tau.min() * fs)
+    Tn = out.data.shape[0]
+    ref = np.zeros_like(out.data)
+    for mp in range(3):
+        for m in range(8):
+            tq = np.arange(Tn) - (tau[m, mp] * fs - nmin)
+            xp = np.concatenate([x[:, :, m], np.zeros((Tn - 64, 8))], 0)
+            for n in range(8):
+                ref[:, n, mp] += oracle_np.interp1(xp[:, n], 1 + tq, "linear", 0)
+    assert np.abs(ref - out.data).max() < 1e-12
+    assert abs(out.t0 - (1e-6 + nmin / fs)) < 1e-15
