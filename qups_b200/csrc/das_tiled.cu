@@ -78,6 +78,10 @@ struct TiledArgs {
     float2 *part;           // nsplit > 1: partial images [nsplit][I], summed in order by das_reduce_kernel
     uint64_t I;
     int rev;                // launch the tiles in reverse order (largest I1 first)
+    // real apodization arrays (NAP = 1 or 2): a_s[base + i1*st0 + i2*st1 + i3*st2 + n*st3 + m*st4], 32-bit indices
+    const float *ap[2];
+    uint32_t ast[2][5];
+    uint32_t I1, I2;
     float fs;
     int VS, DV, tpose, accumulate;
     uint64_t total_elems;   // T*N*M
@@ -256,7 +260,7 @@ __device__ __forceinline__ void edge_pair(float xq, uint32_t soff, float Tf, int
     }
 }
 
-template <int INTERP>
+template <int INTERP, int NAP>
 __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(const TiledArgs a) {
     static_assert(kR == 2, "the packed fp32x2 inner loop assumes two pixel rows per thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -319,6 +323,16 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             px[r] = __ldg(a.Pi + 3 * pix[r]);
             py[r] = __ldg(a.Pi + 3 * pix[r] + 1);
             pz[r] = __ldg(a.Pi + 3 * pix[r] + 2);
+        }
+        // per-pixel part of the apodization index (NAP arrays, real weights)
+        uint32_t aoff[NAP > 0 ? NAP : 1][kR];
+        if constexpr (NAP > 0) {
+#pragma unroll
+            for (int r = 0; r < kR; ++r) {
+                const uint32_t i1 = (uint32_t)(pix[r] % a.I1), i2 = (uint32_t)((pix[r] / a.I1) % a.I2), i3 = (uint32_t)(pix[r] / ((uint64_t)a.I1 * a.I2));
+#pragma unroll
+                for (int q = 0; q < NAP; ++q) aoff[q][r] = i1 * a.ast[q][0] + i2 * a.ast[q][1] + i3 * a.ast[q][2];
+            }
         }
         // ---- phase 0: per-tile min/max of dv(.,m) and dr(.,n) -------------------------
         for (uint32_t m = 0; m < a.M; ++m) {
@@ -384,10 +398,32 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             const float t0m = pv.w;
             pk.t0 = t0m;
             const int2 *dsc = desc + s * kNT;
+            uint32_t tb[NAP > 0 ? NAP : 1]; // trace part of the apodization index at j = 0
+            if constexpr (NAP > 0) {
+#pragma unroll
+                for (int q = 0; q < NAP; ++q) tb[q] = nt * kNT * a.ast[q][3] + m * a.ast[q][4];
+            }
+            auto apw = [&](int r, int j) -> float { // product of the NAP weights for (pixel row r, trace j)
+                float w = 1.f;
+                if constexpr (NAP > 0) {
+                    w = __ldg(a.ap[0] + (aoff[0][r] + tb[0] + (uint32_t)j * a.ast[0][3]));
+                    if constexpr (NAP > 1) w *= __ldg(a.ap[1] + (aoff[1][r] + tb[1] + (uint32_t)j * a.ast[1][3]));
+                }
+                return w;
+            };
             if (hdr.x == ST_ALL_FAST) {
 #pragma unroll
-                for (int j = 0; j < kNT; ++j)
-                    fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, acc0, acc1);
+                for (int j = 0; j < kNT; ++j) {
+                    if constexpr (NAP == 0) {
+                        fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, acc0, acc1);
+                    } else { // a .* interp1(...): sample into temporaries, then one weighted accumulate per pixel
+                        float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
+                        fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, t0, t1);
+                        const float w0 = apw(0, j), w1 = apw(1, j);
+                        acc0.x = fmaf(w0, t0.x, acc0.x); acc0.y = fmaf(w0, t0.y, acc0.y);
+                        acc1.x = fmaf(w1, t1.x, acc1.x); acc1.y = fmaf(w1, t1.y, acc1.y);
+                    }
+                }
             } else {
                 // mixed stage: per-trace flags; dr is read through a local-memory copy so the loop stays rolled
                 float2 drl[kNT];
@@ -400,14 +436,22 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                     const float2 drj = drl[j];
                     const float xq0 = sample_pos(pk.dv.x, drj.x, cinv, t0m, fs);
                     const float xq1 = sample_pos(pk.dv.y, drj.y, cinv, t0m, fs);
+                    float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
                     if (d.y != TR_SLOW) { // FAST or EDGE: everything comes from the staged window
-                        edge_pair<INTERP>(xq0, (uint32_t)d.x, Tf, (int)a.T, acc0.x, acc0.y);
-                        edge_pair<INTERP>(xq1, (uint32_t)d.x, Tf, (int)a.T, acc1.x, acc1.y);
+                        edge_pair<INTERP>(xq0, (uint32_t)d.x, Tf, (int)a.T, t0.x, t0.y);
+                        edge_pair<INTERP>(xq1, (uint32_t)d.x, Tf, (int)a.T, t1.x, t1.y);
                     } else {              // window does not fit the slot / NaN bound: full interp1 from global memory
                         const uint32_t n = nt * kNT + j;
                         const uint64_t nm = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
-                        slow_pair(a.x + nm * a.T, a.T, xq0, INTERP, acc0.x, acc0.y);
-                        slow_pair(a.x + nm * a.T, a.T, xq1, INTERP, acc1.x, acc1.y);
+                        slow_pair(a.x + nm * a.T, a.T, xq0, INTERP, t0.x, t0.y);
+                        slow_pair(a.x + nm * a.T, a.T, xq1, INTERP, t1.x, t1.y);
+                    }
+                    if constexpr (NAP == 0) {
+                        acc0.x += t0.x; acc0.y += t0.y; acc1.x += t1.x; acc1.y += t1.y;
+                    } else {
+                        const float w0 = apw(0, j), w1 = apw(1, j);
+                        acc0.x = fmaf(w0, t0.x, acc0.x); acc0.y = fmaf(w0, t0.y, acc0.y);
+                        acc1.x = fmaf(w1, t1.x, acc1.x); acc1.y = fmaf(w1, t1.y, acc1.y);
                     }
                 }
             }
@@ -550,7 +594,12 @@ TiledPlan das_tiled_plan(const DasArgs<float> &a, int dtype_in, int dtype_out) {
     TiledPlan p{0, ""};
     if (dtype_in != 0 || dtype_out != 0) { p.why = "tiled path is fp32 only"; return p; }
     if (a.keep_rx || a.keep_tx) { p.why = "tiled path sums both apertures"; return p; }
-    if (a.S != 0) { p.why = "tiled path takes no apodization arrays"; return p; }
+    if (a.S > 2 || (a.S > 0 && !a.apod_real)) { p.why = "tiled path takes at most two REAL apodization arrays"; return p; }
+    for (int q = 0; q < a.S; ++q) { // 32-bit index arithmetic inside the kernel
+        uint64_t last = a.astride[q][5] + (a.I1 - 1) * a.astride[q][0] + (a.I2 - 1) * a.astride[q][1] + (a.I3 - 1) * a.astride[q][2] +
+                        (a.N - 1) * a.astride[q][3] + (a.M - 1) * a.astride[q][4];
+        if (last >= (1ull << 31)) { p.why = "apodization array too large for the tiled path"; return p; }
+    }
     for (int d = 0; d < 5; ++d)
         if (a.cstride[d] != 0) { p.why = "tiled path needs a scalar sound speed"; return p; }
     if (a.interp < 0 || a.interp > 2) { p.why = "tiled path: nearest|linear|cubic"; return p; }
@@ -591,11 +640,23 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     const uint64_t tiles = (uint64_t)t.tilesA * t.tilesB * t.IC;
     if (tiles == 0 || tiles > 0x7fffffffull) return (int)cudaErrorInvalidValue;
 
+    t.I1 = (uint32_t)a.I1; t.I2 = (uint32_t)a.I2;
+    for (int q = 0; q < 2; ++q) {
+        t.ap[q] = (q < a.S) ? reinterpret_cast<const float *>(a.apod) + a.astride[q][5] : nullptr;
+        for (int d = 0; d < 5; ++d) t.ast[q][d] = (q < a.S) ? (uint32_t)a.astride[q][d] : 0u;
+    }
     void (*kern)(const TiledArgs) = nullptr;
-    switch (a.interp) {
-        case 0: kern = das_tiled_kernel<0>; break;
-        case 1: kern = das_tiled_kernel<1>; break;
-        default: kern = das_tiled_kernel<2>; break;
+    const int sel = (a.interp < 0 ? 0 : (a.interp > 2 ? 2 : a.interp)) * 3 + a.S;
+    switch (sel) {
+        case 0: kern = das_tiled_kernel<0, 0>; break;
+        case 1: kern = das_tiled_kernel<0, 1>; break;
+        case 2: kern = das_tiled_kernel<0, 2>; break;
+        case 3: kern = das_tiled_kernel<1, 0>; break;
+        case 4: kern = das_tiled_kernel<1, 1>; break;
+        case 5: kern = das_tiled_kernel<1, 2>; break;
+        case 6: kern = das_tiled_kernel<2, 0>; break;
+        case 7: kern = das_tiled_kernel<2, 1>; break;
+        default: kern = das_tiled_kernel<2, 2>; break;
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -38,3 +38,14 @@ r = np.linalg.norm(ps[:, :, None] - pn[:, None, :], axis=0)
 n0 = int(np.floor((2 * r.min() / P.c0 + wt0 - (wtend - wt0)) * P.fs)); T = int(np.ceil((2 * r.max() / P.c0 + wtend) * P.fs)) - n0 + 1
 t = ev_time(lambda: ultrasound.greens_raw(ps, amp, pn, pn, kern, n0, T, P.fs, P.c0, wt0, 1.0, 2e-4, "cubic"), 2)
 print(f"greens 10k scat 64x64 el T={T} K={len(kern)}: {t:.1f} ms  {S*64*64/t/1e6:.2f} G scat-rx-tx/s")
+
+# headline geometry with a dense I x N real apodization (1 GB): the staged kernel with NAP = 1
+P = synth.config_c2()
+x = torch.from_numpy(synth.noise_cube(P.T, P.N, P.M)).cuda()
+g = (dev(P.Pi), dev(P.Pr), dev(P.Pv), dev(P.Nv))
+apod = torch.rand((1024, 1024, 1, 256, 1), device="cuda")
+t = ev_time(lambda: qups_b200.das_spec("DAS", *g, x, 0.0, P.fs, P.c0, "interp", "cubic", "apod", apod), 2)
+print(f"C2 + dense IxN real apod: {t:.1f} ms {P.I/t/1e3:.2f} Mpix/s ({qups_b200.last_das_kernel()})")
+apod2 = torch.rand((1, 1, 1, 256, 256), device="cuda")
+t = ev_time(lambda: qups_b200.das_spec("DAS", *g, x, 0.0, P.fs, P.c0, "interp", "cubic", "apod", apod2), 2)
+print(f"C2 + N x M real apod: {t:.1f} ms {P.I/t/1e3:.2f} Mpix/s ({qups_b200.last_das_kernel()})")

@@ -180,7 +180,7 @@ def test_auto_dispatch_and_errors():
     with pytest.raises(ValueError):
         _gpu("DAS", P, "spline", "auto")
     with pytest.raises(AssertionError):
-        _gpu("DAS", P, "cubic", "auto", ("apod", np.ones((3, 3))))
+        _gpu("DAS", P, "cubic", "auto", ("apod", np.ones((3, 3), np.float32)))
 
 
 def test_host_entry_point_matches_device_entry_point(oracle_c):
@@ -233,3 +233,32 @@ def test_tiled_volume_matrix_array(oracle_c):
     got = _gpu("DAS", P, "cubic", "tiled")
     assert got.shape == ref.shape == (37, 19, 7, 1, 1)
     assert np.abs(ref).max() > 0 and rel_linf(got, ref) < TOL
+
+
+@pytest.mark.parametrize("kind", ["FC", "PW"])
+def test_tiled_real_apodization(oracle_c, kind):
+    """Real apodization arrays (1 or 2, any broadcast shape) ride the staged kernel: bit-exact for nearest with
+    integer-valued data and weights (masks), tolerance for cubic; complex weights fall back to the generic kernel."""
+    import qups_b200
+    rng = np.random.default_rng(12)
+    P = small_problem(kind, nz=37, nx=45, N=21, M=6, T=300, int_data=True, zlim=(2e-3, 14e-3))
+    Isz = P["Pi"].shape[1:]
+    shapes = [Isz + (21, 1), (1, 1, 1, 21, 6), (Isz[0], Isz[1], 1, 1, 6), (1, 1, 1, 1, 6), Isz + (21, 6)]
+    for shp in shapes:
+        a1 = rng.integers(0, 3, shp).astype(np.float32)        # 0 / 1 / 2 : masks and integer weights
+        ref = _ora(oracle_c, "DAS", P, "nearest", apod=[a1])
+        got = _gpu("DAS", P, "nearest", "tiled", ("apod", a1))
+        assert qups_b200.last_das_kernel() == "das_tiled"
+        assert np.array_equal(got, ref), shp
+    a1 = rng.uniform(0, 1, Isz + (21, 1)).astype(np.float32)
+    a2 = (rng.uniform(0, 1, (1, 1, 1, 21, 6)) > 0.3).astype(np.float32)
+    P2 = small_problem(kind, nz=37, nx=45, N=21, M=6, T=300, zlim=(2e-3, 14e-3))
+    for interp in ("linear", "cubic"):
+        ref = _ora(oracle_c, "DAS", P2, interp, apod=[a1, a2])
+        got = _gpu("DAS", P2, interp, "tiled", ("apod", a1, "apod", a2))
+        assert rel_linf(got, ref) < TOL, interp
+    ac = (a1 * np.exp(0.2j)).astype(np.complex64)
+    _gpu("DAS", P2, "cubic", "auto", ("apod", ac))
+    assert qups_b200.last_das_kernel() == "das_generic"
+    _gpu("DAS", P2, "cubic", "auto", ("apod", a1, "apod", a2, "apod", a2))
+    assert qups_b200.last_das_kernel() == "das_generic"
