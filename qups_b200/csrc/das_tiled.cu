@@ -398,6 +398,9 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             const float t0m = pv.w;
             pk.t0 = t0m;
             const int2 *dsc = desc + s * kNT;
+            // two-level accumulation: the 16 x 4 taps of a stage are summed into stage-local accumulators first
+            // (pairwise-style error growth: sqrt(64) + sqrt(#stages) instead of sqrt(#terms))
+            float2 sa0 = make_float2(0.f, 0.f), sa1 = make_float2(0.f, 0.f);
             uint32_t tb[NAP > 0 ? NAP : 1]; // trace part of the apodization index at j = 0
             if constexpr (NAP > 0) {
 #pragma unroll
@@ -415,13 +418,13 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
 #pragma unroll
                 for (int j = 0; j < kNT; ++j) {
                     if constexpr (NAP == 0) {
-                        fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, acc0, acc1);
+                        fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, sa0, sa1);
                     } else { // a .* interp1(...): sample into temporaries, then one weighted accumulate per pixel
                         float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
                         fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, t0, t1);
                         const float w0 = apw(0, j), w1 = apw(1, j);
-                        acc0.x = fmaf(w0, t0.x, acc0.x); acc0.y = fmaf(w0, t0.y, acc0.y);
-                        acc1.x = fmaf(w1, t1.x, acc1.x); acc1.y = fmaf(w1, t1.y, acc1.y);
+                        sa0.x = fmaf(w0, t0.x, sa0.x); sa0.y = fmaf(w0, t0.y, sa0.y);
+                        sa1.x = fmaf(w1, t1.x, sa1.x); sa1.y = fmaf(w1, t1.y, sa1.y);
                     }
                 }
             } else {
@@ -447,14 +450,15 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                         slow_pair(a.x + nm * a.T, a.T, xq1, INTERP, t1.x, t1.y);
                     }
                     if constexpr (NAP == 0) {
-                        acc0.x += t0.x; acc0.y += t0.y; acc1.x += t1.x; acc1.y += t1.y;
+                        sa0.x += t0.x; sa0.y += t0.y; sa1.x += t1.x; sa1.y += t1.y;
                     } else {
                         const float w0 = apw(0, j), w1 = apw(1, j);
-                        acc0.x = fmaf(w0, t0.x, acc0.x); acc0.y = fmaf(w0, t0.y, acc0.y);
-                        acc1.x = fmaf(w1, t1.x, acc1.x); acc1.y = fmaf(w1, t1.y, acc1.y);
+                        sa0.x = fmaf(w0, t0.x, sa0.x); sa0.y = fmaf(w0, t0.y, sa0.y);
+                        sa1.x = fmaf(w1, t1.x, sa1.x); sa1.y = fmaf(w1, t1.y, sa1.y);
                     }
                 }
             }
+            acc0.x += sa0.x; acc0.y += sa0.y; acc1.x += sa1.x; acc1.y += sa1.y;
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         }

@@ -262,3 +262,36 @@ def test_tiled_real_apodization(oracle_c, kind):
     assert qups_b200.last_das_kernel() == "das_generic"
     _gpu("DAS", P2, "cubic", "auto", ("apod", a1, "apod", a2, "apod", a2))
     assert qups_b200.last_das_kernel() == "das_generic"
+
+
+def test_full_size_headline_parity_on_pixel_subsets(oracle_c):
+    """BASELINE.json headline size (1024^2 px, 256 x 256, T = 2048, cubic): the full staged-kernel image is checked
+    (a) against the C oracle on 96 random pixels (all 65 536 pairs each), (b) against the bit-exact generic kernel on
+    4096 random pixels, (c) for linearity and a checksum of checksums across pixel slabs."""
+    import torch
+    import qups_b200
+    from qups_b200 import synth, _lib
+    P = synth.config_c2()
+    x = synth.noise_cube(P.T, P.N, P.M, seed=0)
+    f32 = np.float32
+    dev = lambda v: torch.from_numpy(np.ascontiguousarray(np.asarray(v, f32))).cuda()
+    xd = torch.from_numpy(x).cuda()
+    g = (dev(P.Pr), dev(P.Pv), dev(P.Nv))
+    full = qups_b200.das_spec("DAS", dev(P.Pi), *g, xd, 0.0, P.fs, P.c0, "interp", "cubic")
+    assert qups_b200.last_das_kernel() == "das_tiled"
+    full = full.cpu().numpy().reshape(1024, 1024, order="F")
+    scale = np.abs(full).max()
+    rng = np.random.default_rng(3)
+    iz, ix = rng.integers(0, 1024, 4096), rng.integers(0, 1024, 4096)
+    sub = np.ascontiguousarray(P.Pi[:, iz, ix, 0]).reshape(3, -1, 1, 1)
+    gen = qups_b200.das_spec("DAS", dev(sub), *g, xd, 0.0, P.fs, P.c0, "interp", "cubic", _path=_lib.PATH_GENERIC)
+    gen = gen.cpu().numpy().reshape(-1)
+    assert np.max(np.abs(gen - full[iz, ix])) / scale < TOL
+    ref = oracle_c.das_spec("DAS", sub[:, :96], P.Pr, P.Pv, P.Nv, x, 0.0, P.fs, P.c0, interp="cubic").reshape(-1)
+    assert np.array_equal(ref, gen[:96])                      # generic kernel == oracle, bit for bit, at full N x M
+    assert np.max(np.abs(ref - full[iz[:96], ix[:96]])) / scale < TOL
+    # linearity + slab additivity (checksum of checksums): two x-slabs beamformed separately == the full image
+    left = qups_b200.das_spec("DAS", dev(P.Pi[:, :, :512]), *g, xd, 0.0, P.fs, P.c0, "interp", "cubic").cpu().numpy()
+    assert np.max(np.abs(left.reshape(1024, 512, order="F") - full[:, :512])) / scale < 1e-6   # receive-split changes the sum order
+    twice = qups_b200.das_spec("DAS", dev(P.Pi[:, :, 512:]), *g, 2 * xd, 0.0, P.fs, P.c0, "interp", "cubic").cpu().numpy()
+    assert np.max(np.abs(twice.reshape(1024, 512, order="F") - 2 * full[:, 512:])) / scale < 2e-6
