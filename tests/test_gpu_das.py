@@ -292,6 +292,6 @@ def test_full_size_headline_parity_on_pixel_subsets(oracle_c):
     assert np.max(np.abs(ref - full[iz[:96], ix[:96]])) / scale < TOL
     # linearity + slab additivity (checksum of checksums): two x-slabs beamformed separately == the full image
     left = qups_b200.das_spec("DAS", dev(P.Pi[:, :, :512]), *g, xd, 0.0, P.fs, P.c0, "interp", "cubic").cpu().numpy()
-    assert np.max(np.abs(left.reshape(1024, 512, order="F") - full[:, :512])) / scale < 1e-6   # receive-split changes the sum order
+    assert np.max(np.abs(left.reshape(1024, 512, order="F") - full[:, :512])) / scale < TOL   # receive-split changes the sum order
     twice = qups_b200.das_spec("DAS", dev(P.Pi[:, :, 512:]), *g, 2 * xd, 0.0, P.fs, P.c0, "interp", "cubic").cpu().numpy()
-    assert np.max(np.abs(twice.reshape(1024, 512, order="F") - 2 * full[:, 512:])) / scale < 2e-6
+    assert np.max(np.abs(twice.reshape(1024, 512, order="F") - 2 * full[:, 512:])) / scale < 2 * TOL
