@@ -29,6 +29,7 @@
 // sequence (common.cuh), so tap indices are bit-identical to the oracle; the
 // interpolation weights / accumulation use FMAs (tolerance-level difference).
 #include <limits.h>
+#include <stdio.h>
 #include "das_args.cuh"
 
 namespace qups {
@@ -53,6 +54,21 @@ constexpr int kR = 2;                 // pixel rows per thread
 constexpr int kCW = QUPS_CW;          // consumer warps
 constexpr int kStages = QUPS_STAGES;  // smem ring depth
 constexpr int kThreads = (kCW + 1) * 32;
+#ifndef QUPS_STATS
+#define QUPS_STATS 0
+#endif
+#ifndef QUPS_EXP
+#define QUPS_EXP 0
+#endif
+#ifndef QUPS_MAGIC
+#define QUPS_MAGIC 1
+#endif
+#ifndef QUPS_W9
+#define QUPS_W9 1
+#endif
+#ifndef QUPS_ACC2
+#define QUPS_ACC2 1
+#endif
 #ifndef QUPS_LPA
 #define QUPS_LPA 8
 #endif
@@ -61,6 +77,13 @@ constexpr int kBarBytes = ((2 * kStages * 8 + 63) / 64) * 64;  // full[] + empty
 constexpr int kTA = 32;        // tile extent along the lane axis
 constexpr int kTB = kCW * kR;  // tile extent along the row axis
 
+// QUPS_MAGIC: the cubic fast path derives the tap address from the bits of 2^23 + floor(xq); the constant
+// (0x4B000000 << 3) mod 2^32 is folded into the published slot offset
+template <int INTERP> struct magic_off { static constexpr uint32_t value = (QUPS_MAGIC && INTERP == 2) ? (0x4B000000u << 3) : 0u; };
+
+#if QUPS_STATS
+__device__ unsigned long long g_stats[8]; // [0..3] traces by flag, [4] split traces, [5] all-fast stages, [6] general stages
+#endif
 enum { TR_FAST = 0, TR_SKIP = 1, TR_SLOW = 2, TR_EDGE = 3 };   // per (n,m) trace
 enum { ST_MIXED = 0, ST_ALL_FAST = 1, ST_END = 2 };             // per published stage of kNT traces
 
@@ -179,17 +202,40 @@ struct Pack2 {
     float cinv, t0, fs;
 };
 template <int INTERP>
-__device__ __forceinline__ void fast_pair2(const Pack2 &c, float2 dr, uint32_t soff, float2 &acc0, float2 &acc1) {
+__device__ __forceinline__ void fast_pair2(const Pack2 &c, float2 dr, uint32_t soff, uint32_t soff1, float2 &acc0, float2 &acc1) {
     float2 xq;
     xq.x = sample_pos(c.dv.x, dr.x, c.cinv, c.t0, c.fs);
     xq.y = sample_pos(c.dv.y, dr.y, c.cinv, c.t0, c.fs);
     if (INTERP == 2) {
+#if QUPS_MAGIC
+        // floor + float->int + address in one go: for 0 <= xq < 2^23, add.rm(xq, 2^23) = 2^23 + floor(xq) exactly
+        // (ulp = 1 in [2^23, 2^24), round toward -inf), so its low mantissa bits ARE the index: no FRND / F2I (both on
+        // the quarter-rate XU pipe).  (bits << 3) wraps mod 2^32; the constant part is folded into the base address.
+        const float2 tm = make_float2(__fadd_rd(xq.x, 8388608.f), __fadd_rd(xq.y, 8388608.f));
+        const float2 kf = __fadd2_rn(tm, make_float2(-8388608.f, -8388608.f)); // exact
+        const float2 u = __ffma2_rn(kf, make_float2(-1.f, -1.f), xq);          // exact
+        // (the producer pre-subtracts kMagicOff from the slot offset it publishes for all-fast stages)
+        const uint32_t a0 = soff + (__float_as_uint(tm.x) << 3);
+        const uint32_t a1 = soff1 + (__float_as_uint(tm.y) << 3);
+#else
         const float2 kf = make_float2(floorf(xq.x), floorf(xq.y));
         const float2 u = __ffma2_rn(kf, make_float2(-1.f, -1.f), xq); // exact
         const uint32_t a0 = soff + ((uint32_t)__float2int_rz(kf.x) << 3);
-        const uint32_t a1 = soff + ((uint32_t)__float2int_rz(kf.y) << 3);
+        const uint32_t a1 = soff1 + ((uint32_t)__float2int_rz(kf.y) << 3);
+#endif
         const float2 p0 = lds64(a0), p1 = lds64(a0 + 8), p2 = lds64(a0 + 16), p3 = lds64(a0 + 24);
         const float2 q0 = lds64(a1), q1 = lds64(a1 + 8), q2 = lds64(a1 + 16), q3 = lds64(a1 + 24);
+#if QUPS_W9
+        // Keys weights through the partition-of-unity / linear-reproduction identities (9 packed ops instead of 11):
+        // w0 = -u(1-u)^2/2, w3 = -u^2(1-u)/2, w1 = (1-u) - 2 w0 + w3, w2 = u + w0 - 2 w3
+        const float2 one2 = make_float2(1.f, 1.f), m2 = make_float2(-2.f, -2.f);
+        const float2 v = __ffma2_rn(u, make_float2(-1.f, -1.f), one2);
+        const float2 h = __fmul2_rn(__fmul2_rn(u, v), make_float2(-0.5f, -0.5f));
+        const float2 w0 = __fmul2_rn(h, v);
+        const float2 w3 = __fmul2_rn(h, u);
+        const float2 w1 = __ffma2_rn(m2, w0, __fadd2_rn(v, w3));
+        const float2 w2 = __ffma2_rn(m2, w3, __fadd2_rn(u, w0));
+#else
         const float2 u2 = __fmul2_rn(u, u);
         const float2 w0 = __fmul2_rn(__ffma2_rn(__ffma2_rn(make_float2(-0.5f, -0.5f), u, make_float2(1.f, 1.f)), u,
                                                 make_float2(-0.5f, -0.5f)), u);
@@ -198,6 +244,18 @@ __device__ __forceinline__ void fast_pair2(const Pack2 &c, float2 dr, uint32_t s
         const float2 w2 = __fmul2_rn(__ffma2_rn(__ffma2_rn(make_float2(-1.5f, -1.5f), u, make_float2(2.f, 2.f)), u,
                                                 make_float2(0.5f, 0.5f)), u);
         const float2 w3 = __fmul2_rn(__ffma2_rn(make_float2(0.5f, 0.5f), u, make_float2(-0.5f, -0.5f)), u2);
+#endif
+#if QUPS_ACC2
+        // complex accumulate as ONE packed FFMA2 per tap: (re,im) += w * (v.re, v.im), the weight broadcast
+        acc0 = __ffma2_rn(p0, make_float2(w0.x, w0.x), acc0);
+        acc1 = __ffma2_rn(q0, make_float2(w0.y, w0.y), acc1);
+        acc0 = __ffma2_rn(p1, make_float2(w1.x, w1.x), acc0);
+        acc1 = __ffma2_rn(q1, make_float2(w1.y, w1.y), acc1);
+        acc0 = __ffma2_rn(p2, make_float2(w2.x, w2.x), acc0);
+        acc1 = __ffma2_rn(q2, make_float2(w2.y, w2.y), acc1);
+        acc0 = __ffma2_rn(p3, make_float2(w3.x, w3.x), acc0);
+        acc1 = __ffma2_rn(q3, make_float2(w3.y, w3.y), acc1);
+#else
         acc0.x = fmaf(w0.x, p0.x, acc0.x); acc0.y = fmaf(w0.x, p0.y, acc0.y);
         acc1.x = fmaf(w0.y, q0.x, acc1.x); acc1.y = fmaf(w0.y, q0.y, acc1.y);
         acc0.x = fmaf(w1.x, p1.x, acc0.x); acc0.y = fmaf(w1.x, p1.y, acc0.y);
@@ -206,9 +264,10 @@ __device__ __forceinline__ void fast_pair2(const Pack2 &c, float2 dr, uint32_t s
         acc1.x = fmaf(w2.y, q2.x, acc1.x); acc1.y = fmaf(w2.y, q2.y, acc1.y);
         acc0.x = fmaf(w3.x, p3.x, acc0.x); acc0.y = fmaf(w3.x, p3.y, acc0.y);
         acc1.x = fmaf(w3.y, q3.x, acc1.x); acc1.y = fmaf(w3.y, q3.y, acc1.y);
+#endif
     } else {
         fast_pair<INTERP>(xq.x, soff, acc0.x, acc0.y);
-        fast_pair<INTERP>(xq.y, soff, acc1.x, acc1.y);
+        fast_pair<INTERP>(xq.y, soff1, acc1.x, acc1.y);
     }
 }
 
@@ -260,20 +319,64 @@ __device__ __forceinline__ void edge_pair(float xq, uint32_t soff, float Tf, int
     }
 }
 
+// EDGE / SLOW traces of a general stage, both pixel rows of a thread (rare: kept out of line so the unrolled
+// stage body stays small).  so0/so1 are the published (magic-adjusted) slot offsets of the two pixels' clusters.
+template <int INTERP>
+__device__ __noinline__ void rare_pair2(const float2 *trace, uint32_t T, int flag, float xq0, float xq1, uint32_t so0,
+                                        uint32_t so1, float2 &t0, float2 &t1) {
+    if (flag != TR_SLOW) { // EDGE (or FAST next to one): everything comes from the staged window(s)
+        edge_pair<INTERP>(xq0, so0 + magic_off<INTERP>::value, (float)T, (int)T, t0.x, t0.y);
+        edge_pair<INTERP>(xq1, so1 + magic_off<INTERP>::value, (float)T, (int)T, t1.x, t1.y);
+    } else {               // window does not fit the slot / NaN bound: full interp1 from global memory
+        slow_pair(trace, T, xq0, INTERP, t0.x, t0.y);
+        slow_pair(trace, T, xq1, INTERP, t1.x, t1.y);
+    }
+}
+
+// sample-index window [t_lo, t_hi] (0-based taps) that covers every pixel whose position lies in [xlo, xhi];
+// returns 0 if the whole range is outside the trace (contributes exactly 0), 1 otherwise; inr = window interior
+// to the trace (unchecked gather allowed), else clipped to the trace incl. the end samples interp1's padding needs
+template <int INTERP>
+__device__ __forceinline__ int tap_window(float xlo, float xhi, float Tf, int T, int &t_lo, int &t_hi, bool &inr, int &tap0) {
+    if (xhi < 1.0f || xlo > Tf) return 0;
+    // every delay operation is monotone and individually rounded, so all tap indices lie in [k(xlo), k(xhi)]
+    inr = interior<INTERP>(xlo, Tf) && interior<INTERP>(xhi, Tf);
+    const float xl = fmaxf(xlo, 1.0f), xh = fminf(xhi, Tf);
+    int klo, khi, tap1;
+    if (INTERP == 2)      { klo = (int)floorf(xl); khi = (int)floorf(xh); tap0 = 2; tap1 = 1; }
+    else if (INTERP == 1) { klo = (int)floorf(xl); khi = (int)floorf(xh); tap0 = 1; tap1 = 0; }
+    else { klo = (int)floorf(__fadd_rn(xl, 0.5f)); khi = (int)floorf(__fadd_rn(xh, 0.5f)); tap0 = 1; tap1 = -1; }
+    t_lo = klo - tap0; t_hi = khi + tap1;
+    if (!inr) {
+        // EDGE: keep the three end samples the interp1 padding needs (edge_pair), then clip
+        if (INTERP == 2) {
+            if (klo <= 1) t_hi = max(t_hi, 2);
+            if (khi >= T - 1) t_lo = min(t_lo, T - 3);
+        } else if (INTERP == 1) {
+            if (khi >= T) t_lo = min(t_lo, T - 2);
+        }
+        t_lo = max(t_lo, 0);
+        t_hi = min(t_hi, T - 1);
+    }
+    return 1;
+}
+
 template <int INTERP, int NAP>
 __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(const TiledArgs a) {
     static_assert(kR == 2, "the packed fp32x2 inner loop assumes two pixel rows per thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [0,64) full/empty mbarriers | stage_hdr[kStages] int4 | desc[kStages][kNT] int2 |
-    //         dvmin[M] dvmax[M] drmin[N] drmax[N] (ordered ints) | 128B-aligned stage ring
+    // layout: [0,64) full/empty mbarriers | stage_hdr[kStages] int4 | desc[kStages][kNT] int4 |
+    //         dv cluster bounds: nmin[M] nmax[M] pmin[M] pmax[M] | drmin[N] drmax[N] (ordered ints) | 128B-aligned ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     int4 *stage_hdr = reinterpret_cast<int4 *>(smem_raw + kBarBytes);
-    int2 *desc = reinterpret_cast<int2 *>(smem_raw + kBarBytes + sizeof(int4) * kStages);
-    int *s_dvmin = reinterpret_cast<int *>(smem_raw + kBarBytes + sizeof(int4) * kStages + sizeof(int2) * kStages * kNT);
-    int *s_dvmax = s_dvmin + a.M;
-    int *s_drmin = s_dvmax + a.M;
+    int4 *desc = reinterpret_cast<int4 *>(smem_raw + kBarBytes + sizeof(int4) * kStages);
+    int *s_dvnmin = reinterpret_cast<int *>(smem_raw + kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT);
+    int *s_dvnmax = s_dvnmin + a.M;
+    int *s_dvpmin = s_dvnmax + a.M;
+    int *s_dvpmax = s_dvpmin + a.M;
+    int *s_drmin = s_dvpmax + a.M;
     int *s_drmax = s_drmin + a.N;
-    const uint32_t ring_off = (uint32_t)((kBarBytes + sizeof(int4) * kStages + sizeof(int2) * kStages * kNT + sizeof(int) * (2 * a.M + 2 * a.N) + 127) & ~127u);
+    const uint32_t ring_off = (uint32_t)((kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * (4 * a.M + 2 * a.N) + 127) & ~127u);
     const uint32_t ring = smem_u32(smem_raw) + ring_off;
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
 
@@ -299,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
     }
-    for (uint32_t i = tid; i < a.M; i += kThreads) { s_dvmin[i] = INT_MAX; s_dvmax[i] = INT_MIN; }
+    for (uint32_t i = tid; i < a.M; i += kThreads) { s_dvnmin[i] = INT_MAX; s_dvnmax[i] = INT_MIN; s_dvpmin[i] = INT_MAX; s_dvpmax[i] = INT_MIN; }
     for (uint32_t i = tid; i < a.N; i += kThreads) { s_drmin[i] = INT_MAX; s_drmax[i] = INT_MIN; }
     __syncthreads();
 
@@ -335,19 +438,27 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             }
         }
         // ---- phase 0: per-tile min/max of dv(.,m) and dr(.,n) -------------------------
+        // dv is tracked in two clusters, dv < 0 and dv >= 0: a focused transmit flips the sign of dv at the focal
+        // plane (kern/das_spec.m:429), so a tile crossing it touches two disjoint windows of each trace
         for (uint32_t m = 0; m < a.M; ++m) {
             const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
             const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
-            int lo = INT_MAX, hi = INT_MIN;
+            int nlo = INT_MAX, nhi = INT_MIN, plo = INT_MAX, phi = INT_MIN;
 #pragma unroll
             for (int r = 0; r < kR; ++r) {
-                const int o = f2o(tx_dist(px[r], py[r], pz[r], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV));
-                lo = min(lo, o);
-                hi = max(hi, o);
+                const float d = tx_dist(px[r], py[r], pz[r], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+                const int o = f2o(d);
+                if (d < 0.f) { nlo = min(nlo, o); nhi = max(nhi, o); }
+                else         { plo = min(plo, o); phi = max(phi, o); }
             }
-            lo = __reduce_min_sync(0xffffffffu, lo);
-            hi = __reduce_max_sync(0xffffffffu, hi);
-            if (lane == 0) { atomicMin(&s_dvmin[m], lo); atomicMax(&s_dvmax[m], hi); }
+            nlo = __reduce_min_sync(0xffffffffu, nlo);
+            nhi = __reduce_max_sync(0xffffffffu, nhi);
+            plo = __reduce_min_sync(0xffffffffu, plo);
+            phi = __reduce_max_sync(0xffffffffu, phi);
+            if (lane == 0) {
+                if (nlo <= nhi) { atomicMin(&s_dvnmin[m], nlo); atomicMax(&s_dvnmax[m], nhi); }
+                if (plo <= phi) { atomicMin(&s_dvpmin[m], plo); atomicMax(&s_dvpmax[m], phi); }
+            }
         }
         for (uint32_t n = nt0 * kNT; n < min(nt1 * kNT, a.N); ++n) {
             const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
@@ -397,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             pk.dv.y = tx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
             const float t0m = pv.w;
             pk.t0 = t0m;
-            const int2 *dsc = desc + s * kNT;
+            const int4 *dsc = desc + s * kNT; // .x = slot offset of the dv < 0 cluster, .y = flag, .z = offset of the dv >= 0 cluster
             // two-level accumulation: the 16 x 4 taps of a stage are summed into stage-local accumulators first
             // (pairwise-style error growth: sqrt(64) + sqrt(#stages) instead of sqrt(#terms))
             float2 sa0 = make_float2(0.f, 0.f), sa1 = make_float2(0.f, 0.f);
@@ -415,39 +526,43 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                 return w;
             };
             if (hdr.x == ST_ALL_FAST) {
+                // every trace FAST with a single window: fully unrolled, branch-free
 #pragma unroll
                 for (int j = 0; j < kNT; ++j) {
+                    const uint32_t so = (uint32_t)dsc[j].x;
                     if constexpr (NAP == 0) {
-                        fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, sa0, sa1);
+                        fast_pair2<INTERP>(pk, dr[j], so, so, sa0, sa1);
                     } else { // a .* interp1(...): sample into temporaries, then one weighted accumulate per pixel
                         float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
-                        fast_pair2<INTERP>(pk, dr[j], (uint32_t)dsc[j].x, t0, t1);
+                        fast_pair2<INTERP>(pk, dr[j], so, so, t0, t1);
                         const float w0 = apw(0, j), w1 = apw(1, j);
                         sa0.x = fmaf(w0, t0.x, sa0.x); sa0.y = fmaf(w0, t0.y, sa0.y);
                         sa1.x = fmaf(w1, t1.x, sa1.x); sa1.y = fmaf(w1, t1.y, sa1.y);
                     }
                 }
             } else {
-                // mixed stage: per-trace flags; dr is read through a local-memory copy so the loop stays rolled
+                // general stage: one CTA-uniform branch per trace (SKIP / FAST / rare); each pixel picks the window of
+                // its own dv cluster.  Kept ROLLED (dr read through a local-memory copy): unrolling it a second time
+                // next to the all-fast body overflows the instruction cache (measured: no_instruction stalls 0.15 -> 1.05)
+                const bool neg0 = pk.dv.x < 0.f, neg1 = pk.dv.y < 0.f;
                 float2 drl[kNT];
 #pragma unroll
                 for (int j = 0; j < kNT; ++j) drl[j] = dr[j];
 #pragma unroll 1
                 for (int j = 0; j < kNT; ++j) {
-                    const int2 d = dsc[j];
+                    const int4 d = dsc[j];
                     if (d.y == TR_SKIP) continue;
                     const float2 drj = drl[j];
-                    const float xq0 = sample_pos(pk.dv.x, drj.x, cinv, t0m, fs);
-                    const float xq1 = sample_pos(pk.dv.y, drj.y, cinv, t0m, fs);
+                    const uint32_t so0 = (uint32_t)(neg0 ? d.x : d.z), so1 = (uint32_t)(neg1 ? d.x : d.z);
                     float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
-                    if (d.y != TR_SLOW) { // FAST or EDGE: everything comes from the staged window
-                        edge_pair<INTERP>(xq0, (uint32_t)d.x, Tf, (int)a.T, t0.x, t0.y);
-                        edge_pair<INTERP>(xq1, (uint32_t)d.x, Tf, (int)a.T, t1.x, t1.y);
-                    } else {              // window does not fit the slot / NaN bound: full interp1 from global memory
+                    if (d.y == TR_FAST) {
+                        fast_pair2<INTERP>(pk, drj, so0, so1, t0, t1);
+                    } else {
                         const uint32_t n = nt * kNT + j;
                         const uint64_t nm = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
-                        slow_pair(a.x + nm * a.T, a.T, xq0, INTERP, t0.x, t0.y);
-                        slow_pair(a.x + nm * a.T, a.T, xq1, INTERP, t1.x, t1.y);
+                        const float xq0 = sample_pos(pk.dv.x, drj.x, cinv, t0m, fs);
+                        const float xq1 = sample_pos(pk.dv.y, drj.y, cinv, t0m, fs);
+                        rare_pair2<INTERP>(a.x + nm * a.T, a.T, d.y, xq0, xq1, so0, so1, t0, t1);
                     }
                     if constexpr (NAP == 0) {
                         sa0.x += t0.x; sa0.y += t0.y; sa1.x += t1.x; sa1.y += t1.y;
@@ -477,6 +592,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
         // =========================== producer warp =================================
         __syncthreads(); // matches the consumers' post-phase-0 barrier
         const bool cinv_ok = (cinv > 0.f) && (fs > 0.f);
+        const int Ti = (int)a.T;
         uint32_t it = 0;
         for (uint32_t nt = nt0; nt < nt1; ++nt) {
             const uint32_t n = nt * kNT + lane;
@@ -491,8 +607,8 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                 bool skip = true;
                 if (ml < a.M) {
                     const float t0l = __ldg(a.Pv4 + 4 * ml + 3);
-                    const float xl = sample_pos(o2f(s_dvmin[ml]), rlo_t, cinv, t0l, fs);
-                    const float xh = sample_pos(o2f(s_dvmax[ml]), rhi_t, cinv, t0l, fs);
+                    const float xl = sample_pos(o2f(min(s_dvnmin[ml], s_dvpmin[ml])), rlo_t, cinv, t0l, fs);
+                    const float xh = sample_pos(o2f(max(s_dvnmax[ml], s_dvpmax[ml])), rhi_t, cinv, t0l, fs);
                     skip = cinv_ok && (xl <= xh) && (xh < 1.0f || xl > Tf);
                 }
                 uint32_t todo = ~__ballot_sync(0xffffffffu, skip);
@@ -501,63 +617,83 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                     todo &= todo - 1;
                     const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                     int flag = TR_SKIP;
-                    uint32_t bytes = 0, soff = 0, dst = 0;
-                    const float2 *src = nullptr;
+                    // up to two windows per trace: [0] single window / dv < 0 cluster, [1] dv >= 0 cluster
+                    uint32_t bytes[2] = {0u, 0u}, soff[2] = {0u, 0u}, dst[2] = {0u, 0u};
+                    const float2 *src[2] = {nullptr, nullptr};
                     if (has) {
                         const float t0m = __ldg(a.Pv4 + 4 * m + 3);
-                        const float xlo = sample_pos(o2f(s_dvmin[m]), rlo, cinv, t0m, fs);
-                        const float xhi = sample_pos(o2f(s_dvmax[m]), rhi, cinv, t0m, fs);
+                        const int nmin = s_dvnmin[m], nmax = s_dvnmax[m], pmin = s_dvpmin[m], pmax = s_dvpmax[m];
+                        const float xlo = sample_pos(o2f(min(nmin, pmin)), rlo, cinv, t0m, fs);
+                        const float xhi = sample_pos(o2f(max(nmax, pmax)), rhi, cinv, t0m, fs);
                         flag = TR_SLOW;
+                        const uint64_t tr = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
+                        const uint32_t slot = ring + (s * kNT + lane) * a.wmax * 8u;
+                        // place window [t_lo, t_hi] of this trace at slot element `at`; returns its length (0 = does not fit)
+                        auto place = [&](int q, int t_lo, int t_hi, int tap0, uint32_t at) -> uint32_t {
+                            const int64_t abs_lo = (int64_t)(tr * a.T) + t_lo;
+                            const int64_t abs_al = abs_lo & ~(int64_t)1; // 16-byte aligned element
+                            const int w0 = t_lo - (int)(abs_lo - abs_al);
+                            int wlen = t_hi - w0 + 1;
+                            wlen = (wlen + 1) & ~1;
+                            if (!(wlen > 0 && at + (uint32_t)wlen <= a.wmax && abs_al >= 0 && (uint64_t)(abs_al + wlen) <= a.total_elems)) return 0u;
+                            bytes[q] = (uint32_t)wlen * 8u;
+                            dst[q] = slot + at * 8u;
+                            soff[q] = dst[q] - (uint32_t)(w0 + tap0) * 8u - magic_off<INTERP>::value;
+#if QUPS_EXP == 2
+                            src[q] = a.x + (abs_al & 0xfffe); // experiment: every window from an L2-resident 512 KB
+#else
+                            src[q] = a.x + abs_al;
+#endif
+                            return (uint32_t)wlen;
+                        };
                         if (cinv_ok && xlo <= xhi) {
-                            if (xhi < 1.0f || xlo > Tf) {
+                            int t_lo = 0, t_hi = 0, tap0 = 0;
+                            bool inr = false;
+                            if (!tap_window<INTERP>(xlo, xhi, Tf, Ti, t_lo, t_hi, inr, tap0)) {
                                 flag = TR_SKIP; // every pixel of the tile is outside the trace: contributes 0
-                            } else {
-                                // every delay operation is monotone and individually rounded, so all tap
-                                // indices of the tile lie in [k(xlo), k(xhi)]; clip to the trace for EDGE
-                                const bool inr = interior<INTERP>(xlo, Tf) && interior<INTERP>(xhi, Tf);
-                                const float xl = fmaxf(xlo, 1.0f), xh = fminf(xhi, Tf);
-                                int klo, khi, tap0, tap1;
-                                if (INTERP == 2)      { klo = (int)floorf(xl); khi = (int)floorf(xh); tap0 = 2; tap1 = 1; }
-                                else if (INTERP == 1) { klo = (int)floorf(xl); khi = (int)floorf(xh); tap0 = 1; tap1 = 0; }
-                                else { klo = (int)floorf(__fadd_rn(xl, 0.5f)); khi = (int)floorf(__fadd_rn(xh, 0.5f)); tap0 = 1; tap1 = -1; }
-                                int t_lo = klo - tap0, t_hi = khi + tap1; // 0-based first / last tap
-                                if (!inr) {
-                                    // EDGE: keep the three end samples the interp1 padding needs (edge_pair), then clip
-                                    if (INTERP == 2) {
-                                        if (klo <= 1) t_hi = max(t_hi, 2);
-                                        if (khi >= (int)a.T - 1) t_lo = min(t_lo, (int)a.T - 3);
-                                    } else if (INTERP == 1) {
-                                        if (khi >= (int)a.T) t_lo = min(t_lo, (int)a.T - 2);
+                            } else if (place(0, t_lo, t_hi, tap0, 0u)) {
+                                flag = inr ? TR_FAST : TR_EDGE;
+                                soff[1] = soff[0];
+                            } else if (nmin <= nmax && pmin <= pmax) {
+                                // the tile straddles the sign flip of dv: stage the windows of the two clusters
+                                const float xnl = sample_pos(o2f(nmin), rlo, cinv, t0m, fs), xnh = sample_pos(o2f(nmax), rhi, cinv, t0m, fs);
+                                const float xpl = sample_pos(o2f(pmin), rlo, cinv, t0m, fs), xph = sample_pos(o2f(pmax), rhi, cinv, t0m, fs);
+                                if (xnl <= xnh && xpl <= xph) {
+                                    int nl = 0, nh = 0, pl = 0, ph2 = 0, tp = 0;
+                                    bool inn = true, inp = true;
+                                    const int hn = tap_window<INTERP>(xnl, xnh, Tf, Ti, nl, nh, inn, tp);
+                                    const int hp = tap_window<INTERP>(xpl, xph, Tf, Ti, pl, ph2, inp, tp);
+                                    uint32_t used = 0;
+                                    bool ok = true;
+                                    if (hn) { used = place(0, nl, nh, tp, 0u); ok = used != 0; }
+                                    if (ok && hp) ok = place(1, pl, ph2, tp, used) != 0;
+                                    if (ok) {
+                                        // a cluster entirely outside the trace has no window: its pixels fail the range test
+                                        // of the EDGE path and contribute 0 (the offset is never dereferenced)
+                                        flag = (hn && hp && inn && inp) ? TR_FAST : TR_EDGE;
+                                        if (!hn && !hp) flag = TR_SKIP;
+                                    } else {
+                                        bytes[0] = bytes[1] = 0u;
                                     }
-                                    t_lo = max(t_lo, 0);
-                                    t_hi = min(t_hi, (int)a.T - 1);
-                                }
-                                const uint64_t tr = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
-                                const int64_t abs_lo = (int64_t)(tr * a.T) + t_lo;
-                                const int64_t abs_al = abs_lo & ~(int64_t)1; // 16-byte aligned element
-                                const int w0 = t_lo - (int)(abs_lo - abs_al);
-                                int wlen = t_hi - w0 + 1;
-                                wlen = (wlen + 1) & ~1;
-                                if (wlen > 0 && wlen <= (int)a.wmax && abs_al >= 0 && (uint64_t)(abs_al + wlen) <= a.total_elems) {
-                                    flag = inr ? TR_FAST : TR_EDGE;
-                                    bytes = (uint32_t)wlen * 8u;
-                                    dst = ring + (s * kNT + lane) * a.wmax * 8u;
-                                    soff = dst - (uint32_t)(w0 + tap0) * 8u;
-                                    src = a.x + abs_al;
                                 }
                             }
                         }
                     }
                     if (__all_sync(0xffffffffu, flag == TR_SKIP)) continue; // exact per-trace test: nothing to do
-                    const bool all_fast = __all_sync(0xffffffffu, flag == TR_FAST || lane >= kNT);
-                    const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+                    const bool all_fast = __all_sync(0xffffffffu, (flag == TR_FAST && bytes[1] == 0u) || lane >= kNT);
+                    const uint32_t total = __reduce_add_sync(0xffffffffu, bytes[0] + bytes[1]);
+#if QUPS_STATS
+                    if (lane < kNT) { atomicAdd(&g_stats[flag], 1ull); if (bytes[1]) atomicAdd(&g_stats[4], 1ull); }
+                    if (lane == 0) atomicAdd(&g_stats[all_fast ? 5 : 6], 1ull);
+#endif
                     mbar_wait(bar_empty + 8 * s, ph ^ 1); // slot free (first lap passes immediately)
-                    if (lane < kNT) desc[s * kNT + lane] = make_int2((int)soff, flag);
+                    if (lane < kNT) desc[s * kNT + lane] = make_int4((int)soff[0], flag, (int)soff[1], 0);
                     if (lane == 0) stage_hdr[s] = make_int4(all_fast ? ST_ALL_FAST : ST_MIXED, (int)m, (int)nt, 0);
                     __syncwarp();
                     if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * s, total);
                     __syncwarp();
-                    if (bytes) bulk_g2s(dst, src, bytes, bar_full + 8 * s);
+                    if (bytes[0]) bulk_g2s(dst[0], src[0], bytes[0], bar_full + 8 * s);
+                    if (bytes[1]) bulk_g2s(dst[1], src[1], bytes[1], bar_full + 8 * s);
                     ++it;
                 }
             }
@@ -589,7 +725,7 @@ __global__ void __launch_bounds__(256) das_reduce_kernel(float2 *y, const float2
 
 // ---- host side ------------------------------------------------------------------------
 static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax) {
-    size_t head = kBarBytes + sizeof(int4) * kStages + sizeof(int2) * kStages * kNT + sizeof(int) * (2 * (size_t)M + 2 * (size_t)N);
+    size_t head = kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * (4 * (size_t)M + 2 * (size_t)N);
     head = (head + 127) & ~(size_t)127;
     return head + (size_t)kStages * kNT * wmax * 8;
 }
@@ -688,6 +824,17 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     kern<<<(unsigned)(tiles * nsplit), kThreads, smem, st>>>(t);
     count_launch();
     e = cudaGetLastError();
+#if QUPS_STATS
+    {
+        unsigned long long h[8] = {0};
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_stats, sizeof(h));
+        fprintf(stderr, "[das_tiled stats] traces FAST %llu SKIP %llu SLOW %llu EDGE %llu split %llu | stages all-fast %llu general %llu\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_stats, z, sizeof(z));
+    }
+#endif
     if (nsplit > 1) {
         if (e == cudaSuccess) {
             const uint64_t g = (a.I + 255) / 256;
