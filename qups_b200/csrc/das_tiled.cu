@@ -562,7 +562,17 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                         const uint64_t nm = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
                         const float xq0 = sample_pos(pk.dv.x, drj.x, cinv, t0m, fs);
                         const float xq1 = sample_pos(pk.dv.y, drj.y, cinv, t0m, fs);
-                        rare_pair2<INTERP>(a.x + nm * a.T, a.T, d.y, xq0, xq1, so0, so1, t0, t1);
+                        // an EDGE trace crosses the end of the data somewhere in the TILE; most warps of the tile are
+                        // still entirely interior (-> packed fast path) or entirely outside (-> contribute 0)
+                        const bool in2 = interior<INTERP>(xq0, Tf) && interior<INTERP>(xq1, Tf);
+                        const bool out2 = !(xq0 >= 1.0f && xq0 <= Tf) && !(xq1 >= 1.0f && xq1 <= Tf);
+                        if (d.y == TR_EDGE && __all_sync(0xffffffffu, in2)) {
+                            fast_pair2<INTERP>(pk, drj, so0, so1, t0, t1);
+                        } else if (d.y == TR_EDGE && __all_sync(0xffffffffu, out2)) {
+                            continue;
+                        } else {
+                            rare_pair2<INTERP>(a.x + nm * a.T, a.T, d.y, xq0, xq1, so0, so1, t0, t1);
+                        }
                     }
                     if constexpr (NAP == 0) {
                         sa0.x += t0.x; sa0.y += t0.y; sa1.x += t1.x; sa1.y += t1.y;
