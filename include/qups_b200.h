@@ -108,6 +108,46 @@ typedef struct {
 QUPS_API int qups_das(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
              const void *apod, const void *cinv, const uint64_t *acstride, const void *x, qups_stream_t stream);
 
+/* ---- closed-form apodization -------------------------------- */
+/* The reference's apodization generators return dense ND masks that DAS receives as 'apod' arrays
+ * (src/UltrasoundSystem.m:4892-5429: apScanline, apMultiline, apTranslatingAperture, apApertureGrowth,
+ * apTxParallelogram, apAcceptanceAngle, apCosineAngle).  Each is a closed-form function of (pixel, element)
+ * geometry; this block lets DAS evaluate it in-kernel instead of reading 4-8 bytes per (pixel, receive) pair.
+ * The weight of a (pixel i, receive n, transmit m) term is  rx(i,n) * tx(i,m) * prod_s apod_s(i,n,m).
+ *   rx_kind                       rx_p                         rx_aux (device, fp32)
+ *   ACCEPTANCE_ANGLE  (:5303)     [cosd(theta)]                3 x N element normals
+ *   COSINE_ANGLE      (:5377)     [90/theta]                   3 x N element normals
+ *   APERTURE_GROWTH   (:5165)     [f, Dmax, nonplanar(0|1)]    nonplanar: 2 x N [cosd(ae); sind(ae)] of the element angles
+ *   TRANSLATING       (:5074)     [tol_rx]                     N lateral coordinates of the receivers (x, or angle)
+ *   tx_kind                       tx_p                         tx_aux (device, fp32)
+ *   SCANLINE          (:4892)     [tol]   |xi - xv| <  tol     M lateral coordinates of the transmits (focus x, or angle)
+ *   TRANSLATING       (:5074)     [tol]   |xi - xv| <= tol     M lateral coordinates
+ *   PARALLELOGRAM     (:5269)     [xlo, xhi] (xdc bounds)      4 x M [sind(th+phi1); cosd(th+phi1); sind(th+phi2); cosd(th+phi2)], 16-byte aligned
+ * lat / lat_dim: lateral coordinate of the pixels per index along grid dimension lat_dim (ScanPolar: scan.a along adim);
+ * NULL -> the pixel's x coordinate (ScanCartesian).  apMultiline (:4970) is a small I_lat x M matrix: pass it as an array. */
+typedef enum {
+    QUPS_AP_RX_NONE = 0, QUPS_AP_RX_ACCEPTANCE_ANGLE = 1, QUPS_AP_RX_COSINE_ANGLE = 2, QUPS_AP_RX_APERTURE_GROWTH = 3,
+    QUPS_AP_RX_TRANSLATING = 4
+} qups_ap_rx_kind;
+typedef enum { QUPS_AP_TX_NONE = 0, QUPS_AP_TX_SCANLINE = 1, QUPS_AP_TX_TRANSLATING = 2, QUPS_AP_TX_PARALLELOGRAM = 3 } qups_ap_tx_kind;
+typedef struct {
+    uint32_t struct_size; /* = sizeof(qups_apod_fused) */
+    int32_t rx_kind, tx_kind;
+    int32_t lat_dim;
+    float rx_p[4], tx_p[4];
+    const void *rx_aux, *tx_aux, *lat;
+} qups_apod_fused;
+
+/* qups_das with closed-form apodization; `apod` arrays (p->S) still multiply in.  fp32 geometry (dtype F32, or F16 data on
+ * the plain-DAS configuration).  Calls outside the staged kernel's envelope materialise the dense weights internally. */
+QUPS_API int qups_das_fused(const qups_das_params *p, const qups_apod_fused *apf, void *y, const void *Pi, const void *Pr,
+                   const void *Pv4, const void *Nv, const void *apod, const void *cinv, const uint64_t *acstride, const void *x,
+                   qups_stream_t stream);
+/* The dense array the reference's generator would return: which = 0 -> receive weights I1 x I2 x I3 x NM(=N),
+ * which = 1 -> transmit weights I1 x I2 x I3 x 1 x NM(=M); real fp32, or complex (imag 0) when as_complex. */
+QUPS_API int qups_apod_generate(const qups_apod_fused *apf, int32_t which, void *out, int32_t as_complex, const void *Pi, const void *Pr,
+                       uint64_t I1, uint64_t I2, uint64_t I3, uint64_t NM, qups_stream_t stream);
+
 /* tau(i,n,m) = cinv .* (dv + dr)   (no -t0)   kern/das_spec.m:448-449; tau : real I x N x M */
 QUPS_API int qups_delays(const qups_das_params *p, void *tau, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
                 const void *cinv, const uint64_t *cstride, qups_stream_t stream);

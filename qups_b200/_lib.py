@@ -19,7 +19,7 @@ INTERP = {"nearest": NEAREST, "linear": LINEAR, "cubic": CUBIC, "lanczos3": LANC
 
 EXPORTS = (
     "qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
-    "qups_greens", "qups_convd", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
+    "qups_das_fused", "qups_apod_generate", "qups_greens", "qups_convd", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
 )
 
 
@@ -75,6 +75,18 @@ class ConvdParams(C.Structure):
     ]
 
 
+class ApodFused(C.Structure):
+    """qups_apod_fused (include/qups_b200.h): closed-form apodization evaluated inside the DAS kernel."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("rx_kind", C.c_int32), ("tx_kind", C.c_int32), ("lat_dim", C.c_int32),
+        ("rx_p", C.c_float * 4), ("tx_p", C.c_float * 4),
+        ("rx_aux", C.c_void_p), ("tx_aux", C.c_void_p), ("lat", C.c_void_p),
+    ]
+
+
+AP_RX_NONE, AP_RX_ACCEPTANCE_ANGLE, AP_RX_COSINE_ANGLE, AP_RX_APERTURE_GROWTH, AP_RX_TRANSLATING = range(5)
+AP_TX_NONE, AP_TX_SCANLINE, AP_TX_TRANSLATING, AP_TX_PARALLELOGRAM = range(4)
+
 _lib = None
 
 
@@ -90,6 +102,9 @@ def lib() -> C.CDLL:
     L = C.CDLL(LIB_PATH)
     vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
     L.qups_das.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, vp, u64p, vp, vp]
+    L.qups_das_fused.argtypes = [C.POINTER(DasParams), C.POINTER(ApodFused), vp, vp, vp, vp, vp, vp, vp, u64p, vp, vp]
+    L.qups_apod_generate.argtypes = [C.POINTER(ApodFused), C.c_int32, vp, C.c_int32, vp, vp, C.c_uint64, C.c_uint64,
+                                     C.c_uint64, C.c_uint64, vp]
     L.qups_delays.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, u64p, vp]
     L.qups_das_host.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, u64p, vp,
                                 C.c_int]
@@ -100,7 +115,7 @@ def lib() -> C.CDLL:
     L.qups_greens.argtypes = [C.POINTER(GreensParams), vp, vp, vp, vp, vp, vp, vp]
     L.qups_convd.argtypes = [C.POINTER(ConvdParams), vp, vp, vp, vp]
     L.qups_convd.restype = C.c_int
-    for f in ("qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
+    for f in ("qups_das", "qups_das_fused", "qups_apod_generate", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
               "qups_greens", "qups_version"):
         getattr(L, f).restype = C.c_int
     L.qups_last_error.restype = C.c_char_p

@@ -28,6 +28,7 @@ UNITS = {
     "greens.cu": ["-fmad=false"],
     "wsinterpd2.cu": ["-fmad=false"],
     "convd.cu": ["-fmad=false"],
+    "apod_gen.cu": ["-fmad=false"],
     "das_tiled.cu": [],
     "qups_b200.cu": [],
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <stdint.h>
 #include "common.cuh"
+#include "apod_fused.cuh"
 
 namespace qups {
 
@@ -24,6 +25,8 @@ template <typename R> struct DasArgs {
     void *y;
     uint64_t cstride[6];
     uint64_t astride[MAX_APOD][6];
+    int fused;      // 0 = no closed-form apodization; otherwise `fa` is valid (fp32 paths only)
+    FusedApod fa;
 };
 
 // launch entry points implemented in das_generic.cu / das_tiled.cu
@@ -46,6 +49,11 @@ struct TiledPlan {
 };
 TiledPlan das_tiled_plan(const DasArgs<float> &a, int dtype_in, int dtype_out);
 int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st);
+
+// dense image of a closed-form apodization (apod_gen.cu): which = 0 -> receive weights I x N, 1 -> transmit weights I x M;
+// out is real fp32, or interleaved complex fp32 (imag = 0) when as_complex
+int launch_apod_generate(const FusedApod &fa, int which, float *out, int as_complex, const float *Pi, const float *Pr,
+                         uint64_t I1, uint64_t I2, uint64_t I3, uint64_t NM, cudaStream_t st);
 
 void count_launch(uint64_t n = 1);
 

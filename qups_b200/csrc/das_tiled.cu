@@ -108,6 +108,8 @@ struct TiledArgs {
     float fs;
     int VS, DV, tpose, accumulate;
     uint64_t total_elems;   // T*N*M
+    FusedApod fa;           // closed-form apodization evaluated in-kernel (FUSED > 0)
+    uint32_t I3;
 };
 
 // ---- small PTX wrappers -----------------------------------------------------
@@ -361,7 +363,9 @@ __device__ __forceinline__ int tap_window(float xlo, float xhi, float Tf, int T,
     return 1;
 }
 
-template <int INTERP, int NAP>
+// FUSED: 0 = none; 1 = closed-form TRANSMIT weights only (one weight per pixel and stage, folded into the stage sum);
+//        2 = closed-form RECEIVE weights (per-thread table in shared memory, refreshed per receive tile) + optional transmit weights
+template <int INTERP, int NAP, int FUSED>
 __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(const TiledArgs a) {
     static_assert(kR == 2, "the packed fp32x2 inner loop assumes two pixel rows per thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -376,8 +380,12 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
     int *s_dvpmax = s_dvpmin + a.M;
     int *s_drmin = s_dvpmax + a.M;
     int *s_drmax = s_drmin + a.N;
-    const uint32_t ring_off = (uint32_t)((kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * (4 * a.M + 2 * a.N) + 127) & ~127u);
+    int *s_txany = s_drmax + a.N;   // FUSED: does any pixel of the tile have a non-zero transmit / receive weight?
+    int *s_rxany = s_txany + (FUSED ? a.M : 0);
+    const uint32_t ring_off = (uint32_t)((kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * ((FUSED ? 5 : 4) * a.M + (FUSED ? 3 : 2) * a.N) + 127) & ~127u);
     const uint32_t ring = smem_u32(smem_raw) + ring_off;
+    // FUSED == 2: receive-weight table [kNT][kCW*32] float2 (.x/.y = the thread's two pixel rows) behind the ring
+    const uint32_t wtab = ring + kStages * kNT * a.wmax * 8u;
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -404,6 +412,10 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
     }
     for (uint32_t i = tid; i < a.M; i += kThreads) { s_dvnmin[i] = INT_MAX; s_dvnmax[i] = INT_MIN; s_dvpmin[i] = INT_MAX; s_dvpmax[i] = INT_MIN; }
     for (uint32_t i = tid; i < a.N; i += kThreads) { s_drmin[i] = INT_MAX; s_drmax[i] = INT_MIN; }
+    if constexpr (FUSED != 0) {
+        for (uint32_t i = tid; i < a.M; i += kThreads) s_txany[i] = (a.fa.tx_kind == AP_TX_NONE);
+        for (uint32_t i = tid; i < a.N; i += kThreads) s_rxany[i] = (FUSED != 2);
+    }
     __syncthreads();
 
     const float cinv = __ldg(a.cinv);
@@ -437,6 +449,14 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                 for (int q = 0; q < NAP; ++q) aoff[q][r] = i1 * a.ast[q][0] + i2 * a.ast[q][1] + i3 * a.ast[q][2];
             }
         }
+        float plat[kR] = {0.f, 0.f}; // lateral coordinate of the pixel (scan.x, or scan.a for polar scans)
+        if constexpr (FUSED != 0) {
+#pragma unroll
+            for (int r = 0; r < kR; ++r) {
+                const uint32_t i1 = (uint32_t)(pix[r] % a.I1), i2 = (uint32_t)((pix[r] / a.I1) % a.I2), i3 = (uint32_t)(pix[r] / ((uint64_t)a.I1 * a.I2));
+                plat[r] = ap_lateral(a.fa, px[r], i1, i2, i3);
+            }
+        }
         // ---- phase 0: per-tile min/max of dv(.,m) and dr(.,n) -------------------------
         // dv is tracked in two clusters, dv < 0 and dv >= 0: a focused transmit flips the sign of dv at the focal
         // plane (kern/das_spec.m:429), so a tile crossing it touches two disjoint windows of each trace
@@ -459,6 +479,12 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                 if (nlo <= nhi) { atomicMin(&s_dvnmin[m], nlo); atomicMax(&s_dvnmax[m], nhi); }
                 if (plo <= phi) { atomicMin(&s_dvpmin[m], plo); atomicMax(&s_dvpmax[m], phi); }
             }
+            if constexpr (FUSED != 0) {
+                if (a.fa.tx_kind != AP_TX_NONE) {
+                    const bool nz = ap_tx_weight(a.fa, px[0], py[0], pz[0], plat[0], m) != 0.f || ap_tx_weight(a.fa, px[1], py[1], pz[1], plat[1], m) != 0.f;
+                    if (__any_sync(0xffffffffu, nz) && lane == 0) s_txany[m] = 1;
+                }
+            }
         }
         for (uint32_t n = nt0 * kNT; n < min(nt1 * kNT, a.N); ++n) {
             const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
@@ -472,6 +498,10 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             lo = __reduce_min_sync(0xffffffffu, lo);
             hi = __reduce_max_sync(0xffffffffu, hi);
             if (lane == 0) { atomicMin(&s_drmin[n], lo); atomicMax(&s_drmax[n], hi); }
+            if constexpr (FUSED == 2) {
+                const bool nz = ap_rx_weight(a.fa, px[0], py[0], pz[0], plat[0], a.Pr, n) != 0.f || ap_rx_weight(a.fa, px[1], py[1], pz[1], plat[1], a.Pr, n) != 0.f;
+                if (__any_sync(0xffffffffu, nz) && lane == 0) s_rxany[n] = 1;
+            }
         }
         __syncthreads();
 
@@ -502,6 +532,11 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                     const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
                     dr[j].x = rx_dist(px[0], py[0], pz[0], rx, ry, rz);
                     dr[j].y = rx_dist(px[1], py[1], pz[1], rx, ry, rz);
+                    if constexpr (FUSED == 2) { // this thread's receive weights for the tile: its own table column
+                        const float w0 = ap_rx_weight(a.fa, px[0], py[0], pz[0], plat[0], a.Pr, n);
+                        const float w1 = ap_rx_weight(a.fa, px[1], py[1], pz[1], plat[1], a.Pr, n);
+                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wtab + (uint32_t)(j * kCW * 32 + tid) * 8u), "f"(w0), "f"(w1) : "memory");
+                    }
                 }
             }
             pk.dv.x = tx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
@@ -517,27 +552,43 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
 #pragma unroll
                 for (int q = 0; q < NAP; ++q) tb[q] = nt * kNT * a.ast[q][3] + m * a.ast[q][4];
             }
-            auto apw = [&](int r, int j) -> float { // product of the NAP weights for (pixel row r, trace j)
-                float w = 1.f;
+            auto apw2 = [&](int j) -> float2 { // product of the array (NAP) and fused receive weights for trace j, both pixel rows
+                float2 w = make_float2(1.f, 1.f);
+                if constexpr (FUSED == 2) w = lds64(wtab + (uint32_t)(j * kCW * 32 + tid) * 8u);
                 if constexpr (NAP > 0) {
-                    w = __ldg(a.ap[0] + (aoff[0][r] + tb[0] + (uint32_t)j * a.ast[0][3]));
-                    if constexpr (NAP > 1) w *= __ldg(a.ap[1] + (aoff[1][r] + tb[1] + (uint32_t)j * a.ast[1][3]));
+                    w.x *= __ldg(a.ap[0] + (aoff[0][0] + tb[0] + (uint32_t)j * a.ast[0][3]));
+                    w.y *= __ldg(a.ap[0] + (aoff[0][1] + tb[0] + (uint32_t)j * a.ast[0][3]));
+                    if constexpr (NAP > 1) {
+                        w.x *= __ldg(a.ap[1] + (aoff[1][0] + tb[1] + (uint32_t)j * a.ast[1][3]));
+                        w.y *= __ldg(a.ap[1] + (aoff[1][1] + tb[1] + (uint32_t)j * a.ast[1][3]));
+                    }
                 }
                 return w;
             };
+            constexpr bool kWeighted = (NAP > 0) || (FUSED == 2);
+            float wt0 = 1.f, wt1 = 1.f; // fused transmit weights of the two pixels for this stage
+            bool live = true;
+            if constexpr (FUSED != 0) {
+                if (a.fa.tx_kind != AP_TX_NONE) {
+                    wt0 = ap_tx_weight(a.fa, px[0], py[0], pz[0], plat[0], m);
+                    wt1 = ap_tx_weight(a.fa, px[1], py[1], pz[1], plat[1], m);
+                    live = __any_sync(0xffffffffu, wt0 != 0.f || wt1 != 0.f); // scanline-type masks: most warps idle
+                }
+            }
+            if (live) {
             if (hdr.x == ST_ALL_FAST) {
                 // every trace FAST with a single window: fully unrolled, branch-free
 #pragma unroll
                 for (int j = 0; j < kNT; ++j) {
                     const uint32_t so = (uint32_t)dsc[j].x;
-                    if constexpr (NAP == 0) {
+                    if constexpr (!kWeighted) {
                         fast_pair2<INTERP>(pk, dr[j], so, so, sa0, sa1);
                     } else { // a .* interp1(...): sample into temporaries, then one weighted accumulate per pixel
                         float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
                         fast_pair2<INTERP>(pk, dr[j], so, so, t0, t1);
-                        const float w0 = apw(0, j), w1 = apw(1, j);
-                        sa0.x = fmaf(w0, t0.x, sa0.x); sa0.y = fmaf(w0, t0.y, sa0.y);
-                        sa1.x = fmaf(w1, t1.x, sa1.x); sa1.y = fmaf(w1, t1.y, sa1.y);
+                        const float2 w = apw2(j);
+                        sa0.x = fmaf(w.x, t0.x, sa0.x); sa0.y = fmaf(w.x, t0.y, sa0.y);
+                        sa1.x = fmaf(w.y, t1.x, sa1.x); sa1.y = fmaf(w.y, t1.y, sa1.y);
                     }
                 }
             } else {
@@ -574,16 +625,22 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                             rare_pair2<INTERP>(a.x + nm * a.T, a.T, d.y, xq0, xq1, so0, so1, t0, t1);
                         }
                     }
-                    if constexpr (NAP == 0) {
+                    if constexpr (!kWeighted) {
                         sa0.x += t0.x; sa0.y += t0.y; sa1.x += t1.x; sa1.y += t1.y;
                     } else {
-                        const float w0 = apw(0, j), w1 = apw(1, j);
-                        sa0.x = fmaf(w0, t0.x, sa0.x); sa0.y = fmaf(w0, t0.y, sa0.y);
-                        sa1.x = fmaf(w1, t1.x, sa1.x); sa1.y = fmaf(w1, t1.y, sa1.y);
+                        const float2 w = apw2(j);
+                        sa0.x = fmaf(w.x, t0.x, sa0.x); sa0.y = fmaf(w.x, t0.y, sa0.y);
+                        sa1.x = fmaf(w.y, t1.x, sa1.x); sa1.y = fmaf(w.y, t1.y, sa1.y);
                     }
                 }
             }
-            acc0.x += sa0.x; acc0.y += sa0.y; acc1.x += sa1.x; acc1.y += sa1.y;
+            } // live
+            if constexpr (FUSED != 0) { // the transmit weight is constant over the stage: one multiply per pixel
+                acc0.x = fmaf(wt0, sa0.x, acc0.x); acc0.y = fmaf(wt0, sa0.y, acc0.y);
+                acc1.x = fmaf(wt1, sa1.x, acc1.x); acc1.y = fmaf(wt1, sa1.y, acc1.y);
+            } else {
+                acc0.x += sa0.x; acc0.y += sa0.y; acc1.x += sa1.x; acc1.y += sa1.y;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         }
@@ -620,6 +677,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                     const float xl = sample_pos(o2f(min(s_dvnmin[ml], s_dvpmin[ml])), rlo_t, cinv, t0l, fs);
                     const float xh = sample_pos(o2f(max(s_dvnmax[ml], s_dvpmax[ml])), rhi_t, cinv, t0l, fs);
                     skip = cinv_ok && (xl <= xh) && (xh < 1.0f || xl > Tf);
+                    if constexpr (FUSED != 0) skip = skip || (s_txany[ml] == 0); // no pixel of the tile uses this transmit
                 }
                 uint32_t todo = ~__ballot_sync(0xffffffffu, skip);
                 while (todo) {
@@ -689,6 +747,9 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                             }
                         }
                     }
+                    if constexpr (FUSED == 2) { // receive n is masked for every pixel of the tile: nothing to stage
+                        if (has && s_rxany[n] == 0) { flag = TR_SKIP; bytes[0] = bytes[1] = 0u; }
+                    }
                     if (__all_sync(0xffffffffu, flag == TR_SKIP)) continue; // exact per-trace test: nothing to do
                     const bool all_fast = __all_sync(0xffffffffu, (flag == TR_FAST && bytes[1] == 0u) || lane >= kNT);
                     const uint32_t total = __reduce_add_sync(0xffffffffu, bytes[0] + bytes[1]);
@@ -734,10 +795,10 @@ __global__ void __launch_bounds__(256) das_reduce_kernel(float2 *y, const float2
 }
 
 // ---- host side ------------------------------------------------------------------------
-static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax) {
-    size_t head = kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * (4 * (size_t)M + 2 * (size_t)N);
+static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax, int fused = 0) {
+    size_t head = kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * ((fused ? 5 : 4) * (size_t)M + (fused ? 3 : 2) * (size_t)N);
     head = (head + 127) & ~(size_t)127;
-    return head + (size_t)kStages * kNT * wmax * 8;
+    return head + (size_t)kStages * kNT * wmax * 8 + (fused == 2 ? (size_t)kNT * kCW * 32 * 8 : 0);
 }
 
 TiledPlan das_tiled_plan(const DasArgs<float> &a, int dtype_in, int dtype_out) {
@@ -745,6 +806,7 @@ TiledPlan das_tiled_plan(const DasArgs<float> &a, int dtype_in, int dtype_out) {
     if (dtype_in != 0 || dtype_out != 0) { p.why = "tiled path is fp32 only"; return p; }
     if (a.keep_rx || a.keep_tx) { p.why = "tiled path sums both apertures"; return p; }
     if (a.S > 2 || (a.S > 0 && !a.apod_real)) { p.why = "tiled path takes at most two REAL apodization arrays"; return p; }
+    if (a.fused && a.S > 1) { p.why = "tiled path: closed-form apodization combines with at most one apodization array"; return p; }
     for (int q = 0; q < a.S; ++q) { // 32-bit index arithmetic inside the kernel
         uint64_t last = a.astride[q][5] + (a.I1 - 1) * a.astride[q][0] + (a.I2 - 1) * a.astride[q][1] + (a.I3 - 1) * a.astride[q][2] +
                         (a.N - 1) * a.astride[q][3] + (a.M - 1) * a.astride[q][4];
@@ -759,7 +821,7 @@ TiledPlan das_tiled_plan(const DasArgs<float> &a, int dtype_in, int dtype_out) {
     if (a.N >= (1u << 24) || a.M >= (1u << 24) || a.I >= (1ull << 40)) { p.why = "too large"; return p; }
     if ((reinterpret_cast<uintptr_t>(a.x) & 15) != 0) { p.why = "x not 16-byte aligned"; return p; }
     if ((reinterpret_cast<uintptr_t>(a.Pv4) & 15) != 0) { p.why = "Pv not 16-byte aligned"; return p; }
-    if (tiled_smem_bytes((uint32_t)a.N, (uint32_t)a.M, 64) > 200 * 1024) { p.why = "N+M too large for smem"; return p; }
+    if (tiled_smem_bytes((uint32_t)a.N, (uint32_t)a.M, 64, 2) > 200 * 1024) { p.why = "N+M too large for smem"; return p; }
     p.eligible = 1;
     return p;
 }
@@ -782,11 +844,15 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     t.IC = (uint32_t)a.I3; t.sC = a.I1 * a.I2;
     t.tilesA = (t.IA + kTA - 1) / kTA;
     t.tilesB = (t.IB + kTB - 1) / kTB;
+    // closed-form apodization: 1 = transmit weights only, 2 = receive weights (shared-memory table) [+ transmit weights]
+    const int fused = !a.fused ? 0 : (a.fa.rx_kind != AP_RX_NONE ? 2 : (a.fa.tx_kind != AP_TX_NONE ? 1 : 0));
+    t.fa = a.fa;
+    t.I3 = (uint32_t)a.I3;
     uint32_t wmax = QUPS_WMAX;
     if (const char *e = getenv("QUPS_B200_WMAX")) { int v = atoi(e); if (v >= 8 && v <= 1024) wmax = (uint32_t)(v & ~1); }
-    while (wmax > 16 && tiled_smem_bytes(t.N, t.M, wmax) > 200 * 1024 / QUPS_MINBLOCKS) wmax -= 16;
+    while (wmax > 16 && tiled_smem_bytes(t.N, t.M, wmax, fused) > 200 * 1024 / QUPS_MINBLOCKS) wmax -= 16;
     t.wmax = wmax;
-    const size_t smem = tiled_smem_bytes(t.N, t.M, wmax);
+    const size_t smem = tiled_smem_bytes(t.N, t.M, wmax, fused);
     const uint64_t tiles = (uint64_t)t.tilesA * t.tilesB * t.IC;
     if (tiles == 0 || tiles > 0x7fffffffull) return (int)cudaErrorInvalidValue;
 
@@ -796,18 +862,13 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
         for (int d = 0; d < 5; ++d) t.ast[q][d] = (q < a.S) ? (uint32_t)a.astride[q][d] : 0u;
     }
     void (*kern)(const TiledArgs) = nullptr;
-    const int sel = (a.interp < 0 ? 0 : (a.interp > 2 ? 2 : a.interp)) * 3 + a.S;
-    switch (sel) {
-        case 0: kern = das_tiled_kernel<0, 0>; break;
-        case 1: kern = das_tiled_kernel<0, 1>; break;
-        case 2: kern = das_tiled_kernel<0, 2>; break;
-        case 3: kern = das_tiled_kernel<1, 0>; break;
-        case 4: kern = das_tiled_kernel<1, 1>; break;
-        case 5: kern = das_tiled_kernel<1, 2>; break;
-        case 6: kern = das_tiled_kernel<2, 0>; break;
-        case 7: kern = das_tiled_kernel<2, 1>; break;
-        default: kern = das_tiled_kernel<2, 2>; break;
-    }
+    const int ip = a.interp < 0 ? 0 : (a.interp > 2 ? 2 : a.interp);
+#define QUPS_PICK(I_, N_, F_) if (ip == I_ && a.S == N_ && fused == F_) kern = das_tiled_kernel<I_, N_, F_>;
+#define QUPS_PICK_I(I_) QUPS_PICK(I_, 0, 0) QUPS_PICK(I_, 1, 0) QUPS_PICK(I_, 2, 0) QUPS_PICK(I_, 0, 1) QUPS_PICK(I_, 1, 1) QUPS_PICK(I_, 0, 2) QUPS_PICK(I_, 1, 2)
+    QUPS_PICK_I(0) QUPS_PICK_I(1) QUPS_PICK_I(2)
+#undef QUPS_PICK_I
+#undef QUPS_PICK
+    if (!kern) return (int)cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     // Work decomposition: when the pixel tiles alone cannot fill ~4 waves of the 148 SMs (small images, pixel-sharded

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <type_traits>
 
 #include "../../include/qups_b200.h"
 #include "das_args.cuh"
@@ -15,6 +16,7 @@ namespace qups {
 static thread_local char g_err[512] = "";
 static thread_local uint64_t g_launches = 0;
 static thread_local const char *g_last_das = "none";
+static thread_local const qups_apod_fused *g_fused = nullptr; // set by qups_das_fused around das_impl
 void count_launch(uint64_t n) { g_launches += n; }
 
 static int fail(int code, const char *fmt, ...) {
@@ -50,6 +52,31 @@ static int fill_args(DasArgs<R> &a, const qups_das_params *p, const void *Pi, co
     a.cstride[5] = 0; // entry 6 of cstride is unused padding in the reference (kern/das_spec.m:259)
     for (int s = 0; s < MAX_APOD; ++s)
         for (int d = 0; d < 6; ++d) a.astride[s][d] = (need_astride && s < a.S) ? acstride[6 + 6 * s + d] : 0;
+    a.fused = 0;
+    a.fa = FusedApod{};
+    if (g_fused && need_astride) {
+        a.fused = 1;
+        a.fa.rx_kind = g_fused->rx_kind; a.fa.tx_kind = g_fused->tx_kind;
+        for (int k = 0; k < 4; ++k) { a.fa.rx_p[k] = g_fused->rx_p[k]; a.fa.tx_p[k] = g_fused->tx_p[k]; }
+        a.fa.rx_aux = (const float *)g_fused->rx_aux; a.fa.tx_aux = (const float *)g_fused->tx_aux;
+        a.fa.lat = (const float *)g_fused->lat; a.fa.lat_dim = g_fused->lat_dim;
+    }
+    return 0;
+}
+
+static int validate_fused(const qups_apod_fused *f, const qups_das_params *p) {
+    if (!f) return fail(QUPS_ERR_INVALID, "fused apodization spec is NULL");
+    if (f->struct_size != sizeof(qups_apod_fused))
+        return fail(QUPS_ERR_INVALID, "apod.struct_size %u != %zu (header/library mismatch)", f->struct_size, sizeof(qups_apod_fused));
+    if (f->rx_kind < QUPS_AP_RX_NONE || f->rx_kind > QUPS_AP_RX_TRANSLATING) return fail(QUPS_ERR_INVALID, "unknown receive apodization kind %d", f->rx_kind);
+    if (f->tx_kind < QUPS_AP_TX_NONE || f->tx_kind > QUPS_AP_TX_PARALLELOGRAM) return fail(QUPS_ERR_INVALID, "unknown transmit apodization kind %d", f->tx_kind);
+    const bool rx_needs_aux = f->rx_kind == QUPS_AP_RX_ACCEPTANCE_ANGLE || f->rx_kind == QUPS_AP_RX_COSINE_ANGLE ||
+                              f->rx_kind == QUPS_AP_RX_TRANSLATING || (f->rx_kind == QUPS_AP_RX_APERTURE_GROWTH && f->rx_p[2] != 0.f);
+    if (rx_needs_aux && !f->rx_aux) return fail(QUPS_ERR_INVALID, "receive apodization kind %d needs rx_aux", f->rx_kind);
+    if (f->tx_kind != QUPS_AP_TX_NONE && !f->tx_aux) return fail(QUPS_ERR_INVALID, "transmit apodization kind %d needs tx_aux", f->tx_kind);
+    if (f->tx_kind == QUPS_AP_TX_PARALLELOGRAM && (reinterpret_cast<uintptr_t>(f->tx_aux) & 15)) return fail(QUPS_ERR_INVALID, "tx_aux must be 16-byte aligned");
+    if (f->lat && (f->lat_dim < 1 || f->lat_dim > 3)) return fail(QUPS_ERR_INVALID, "lat_dim must be 1, 2 or 3");
+    if (p && p->dtype == QUPS_F64) return fail(QUPS_ERR_UNSUPPORTED, "closed-form apodization is implemented for fp32 geometry (dtype F32 / F16)");
     return 0;
 }
 
@@ -104,6 +131,53 @@ static int run_das_typed(const qups_das_params *p, void *y, const void *Pi, cons
             if (tiled) {
                 rc = launch_das_tiled(a, st);
                 g_last_das = "das_tiled";
+            } else if (a.fused) {
+                // closed-form apodization outside the staged kernel's envelope (kept apertures, sound-speed maps, complex
+                // or > 1 arrays, ...): materialise the dense weights next to the caller's arrays and run the generic kernel
+                rc = 0;
+                const int extra = (a.fa.rx_kind != AP_RX_NONE) + (a.fa.tx_kind != AP_TX_NONE);
+                if (a.S + extra > MAX_APOD) return fail(QUPS_ERR_UNSUPPORTED, "at most %d apodization arrays incl. the closed-form ones", MAX_APOD);
+                const uint64_t dims[5] = {a.I1, a.I2, a.I3, a.N, a.M};
+                uint64_t have = 0; // elements of the caller's concatenated apod buffer
+                for (int q = 0; q < a.S; ++q) {
+                    uint64_t ne = 1;
+                    for (int d = 0; d < 5; ++d) if (a.astride[q][d]) ne *= dims[d];
+                    have = have > a.astride[q][5] + ne ? have : a.astride[q][5] + ne;
+                }
+                const uint64_t nrx = a.fa.rx_kind != AP_RX_NONE ? a.I * a.N : 0, ntx = a.fa.tx_kind != AP_TX_NONE ? a.I * a.M : 0;
+                DA *buf = nullptr;
+                cudaError_t ce = cudaMallocAsync((void **)&buf, sizeof(DA) * (have + nrx + ntx), st); // complex-sized: enough for either element type
+                if (ce != cudaSuccess) return fail(QUPS_ERR_ALLOC, "cudaMallocAsync(dense apodization, %llu elements): %s", (unsigned long long)(have + nrx + ntx), cudaGetErrorString(ce));
+                if (have) ce = cudaMemcpyAsync(buf, a.apod, (a.apod_real ? sizeof(DA) / 2 : sizeof(DA)) * have, cudaMemcpyDeviceToDevice, st);
+                DasArgs<R> g = a;
+                g.fused = 0;
+                g.apod = buf;
+                if constexpr (std::is_same<DA, float2>::value) {
+                    if (a.S == 0) g.apod_real = 1;                 // no caller arrays: real weights (half the bytes)
+                    const int cplx = g.apod_real ? 0 : 1;          // otherwise match the caller's element type
+                    float *base = reinterpret_cast<float *>(buf);
+                    const uint64_t ew = cplx ? 2 : 1;              // floats per element
+                    uint64_t off = have;
+                    if (nrx && ce == cudaSuccess) {
+                        rc = launch_apod_generate(a.fa, 0, base + off * ew, cplx, (const float *)a.Pi, (const float *)a.Pr, a.I1, a.I2, a.I3, a.N, st);
+                        const uint64_t st6[6] = {a.I1 > 1 ? 1 : 0, a.I2 > 1 ? a.I1 : 0, a.I3 > 1 ? a.I1 * a.I2 : 0, a.N > 1 ? a.I : 0, 0, off};
+                        for (int d = 0; d < 6; ++d) g.astride[g.S][d] = st6[d];
+                        ++g.S; off += nrx;
+                    }
+                    if (ntx && ce == cudaSuccess && rc == 0) {
+                        rc = launch_apod_generate(a.fa, 1, base + off * ew, cplx, (const float *)a.Pi, (const float *)a.Pr, a.I1, a.I2, a.I3, a.M, st);
+                        const uint64_t st6[6] = {a.I1 > 1 ? 1 : 0, a.I2 > 1 ? a.I1 : 0, a.I3 > 1 ? a.I1 * a.I2 : 0, 0, a.M > 1 ? a.I : 0, off};
+                        for (int d = 0; d < 6; ++d) g.astride[g.S][d] = st6[d];
+                        ++g.S;
+                    }
+                } else {
+                    cudaFreeAsync(buf, st);
+                    return fail(QUPS_ERR_UNSUPPORTED, "closed-form apodization outside the staged kernel needs fp32 apodization arrays");
+                }
+                if (ce == cudaSuccess && rc == 0) rc = launch_das_generic<DIN, DA, DOUT, R>(g, st);
+                cudaFreeAsync(buf, st);
+                if (ce != cudaSuccess) return cuda_fail(ce, "dense apodization copy");
+                g_last_das = "das_generic+apod_generate";
             } else {
                 rc = launch_das_generic<DIN, DA, DOUT, R>(a, st);
                 g_last_das = "das_generic";
@@ -233,6 +307,37 @@ int qups_das(const qups_das_params *p, void *y, const void *Pi, const void *Pr, 
              const void *apod, const void *cinv, const uint64_t *acstride, const void *x, qups_stream_t stream) {
     g_err[0] = 0;
     return das_impl(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, (cudaStream_t)stream);
+}
+
+int qups_das_fused(const qups_das_params *p, const qups_apod_fused *fz, void *y, const void *Pi, const void *Pr, const void *Pv4,
+                   const void *Nv, const void *apod, const void *cinv, const uint64_t *acstride, const void *x, qups_stream_t stream) {
+    g_err[0] = 0;
+    if (int rc = validate(p, false)) return rc;
+    if (int rc = validate_fused(fz, p)) return rc;
+    if (fz->rx_kind == QUPS_AP_RX_NONE && fz->tx_kind == QUPS_AP_TX_NONE)
+        return das_impl(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, (cudaStream_t)stream);
+    if (p->dtype == QUPS_F16 && (p->S != 0 || (p->flag & (QUPS_FLAG_KEEP_RX | QUPS_FLAG_KEEP_TX)) || p->accumulate || p->fmod != 0.0))
+        return fail(QUPS_ERR_UNSUPPORTED, "closed-form apodization with fp16 data: plain DAS only (no arrays / kept apertures / modulation)");
+    g_fused = fz;
+    const int rc = das_impl(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, (cudaStream_t)stream);
+    g_fused = nullptr;
+    return rc;
+}
+
+int qups_apod_generate(const qups_apod_fused *fz, int32_t which, void *out, int32_t as_complex, const void *Pi, const void *Pr,
+                       uint64_t I1, uint64_t I2, uint64_t I3, uint64_t NM, qups_stream_t stream) {
+    g_err[0] = 0;
+    if (int rc = validate_fused(fz, nullptr)) return rc;
+    if (which != 0 && which != 1) return fail(QUPS_ERR_INVALID, "which must be 0 (receive weights) or 1 (transmit weights)");
+    if (I1 * I2 * I3 * NM == 0) return 0;
+    if (!out || !Pi || (which == 0 && !Pr)) return fail(QUPS_ERR_INVALID, "NULL array argument");
+    FusedApod fa{};
+    fa.rx_kind = fz->rx_kind; fa.tx_kind = fz->tx_kind;
+    for (int k = 0; k < 4; ++k) { fa.rx_p[k] = fz->rx_p[k]; fa.tx_p[k] = fz->tx_p[k]; }
+    fa.rx_aux = (const float *)fz->rx_aux; fa.tx_aux = (const float *)fz->tx_aux; fa.lat = (const float *)fz->lat; fa.lat_dim = fz->lat_dim;
+    if (int e = launch_apod_generate(fa, which, (float *)out, as_complex, (const float *)Pi, (const float *)Pr, I1, I2, I3, NM, (cudaStream_t)stream))
+        return cuda_fail(e, "apod_generate kernel");
+    return 0;
 }
 
 int qups_delays(const qups_das_params *p, void *tau, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,

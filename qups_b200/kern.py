@@ -103,6 +103,66 @@ def _stride5(sz):
     return st
 
 
+class FusedApod:
+    """Closed-form apodization: what the reference's ap* generators
+    (src/UltrasoundSystem.m:4892-5429) return as dense ND masks, kept as a parameter block and evaluated inside the
+    DAS kernel.  Pass it wherever an 'apod' array goes; `dense()` materialises the array the reference would return
+    (on the GPU, by the same device functions).  rx_* weights depend on (pixel, receive), tx_* on (pixel, transmit)."""
+
+    def __init__(self, rx_kind=0, rx_p=(), rx_aux=None, tx_kind=0, tx_p=(), tx_aux=None, lat=None, lat_dim=2, name=""):
+        self.rx_kind, self.rx_p, self.rx_aux = int(rx_kind), tuple(float(v) for v in rx_p), rx_aux
+        self.tx_kind, self.tx_p, self.tx_aux = int(tx_kind), tuple(float(v) for v in tx_p), tx_aux
+        self.lat, self.lat_dim, self.name = lat, int(lat_dim), name
+
+    def merged(self, o: "FusedApod") -> "FusedApod":
+        """Product of two closed-form apodizations; each side (receive / transmit) can be closed-form only once."""
+        if (self.rx_kind and o.rx_kind) or (self.tx_kind and o.tx_kind):
+            raise QupsError(-3, "two closed-form apodizations on the same aperture: pass one of them as dense()")
+        if self.lat is not None and o.lat is not None and (self.lat_dim != o.lat_dim or not np.array_equal(self.lat, o.lat)):
+            raise QupsError(-1, "inconsistent lateral pixel coordinates")
+        a, b = (self, o) if self.rx_kind else (o, self)
+        t = self if self.tx_kind else o
+        l = self if self.lat is not None else o
+        return FusedApod(a.rx_kind, a.rx_p, a.rx_aux, t.tx_kind, t.tx_p, t.tx_aux, l.lat, l.lat_dim, self.name + "*" + o.name)
+
+    def _struct(self, dev, keep: list):
+        f = _lib.ApodFused()
+        f.struct_size = C.sizeof(_lib.ApodFused)
+        f.rx_kind, f.tx_kind, f.lat_dim = self.rx_kind, self.tx_kind, self.lat_dim
+        for k, v in enumerate(self.rx_p[:4]): f.rx_p[k] = v
+        for k, v in enumerate(self.tx_p[:4]): f.tx_p[k] = v
+        for nm in ("rx_aux", "tx_aux", "lat"):
+            v = getattr(self, nm)
+            if v is not None:  # MATLAB-shaped (rows x count) -> column-major fp32 on the device
+                t = _colmajor(_as_tensor(np.asarray(v, np.float64) if not isinstance(v, torch.Tensor) else v), torch.float32, dev)
+                keep.append(t)
+                setattr(f, nm, t.data_ptr())
+        return f
+
+    def dense(self, Pi, Pr=None, M=None, which="rx", complex_=False):
+        """The dense array the reference generator returns: I1 x I2 x I3 x N (which='rx') or I1 x I2 x I3 x 1 x M ('tx')."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        Pi_t = _as_tensor(Pi)
+        Pi_t = Pi_t.reshape(tuple(Pi_t.shape) + (1,) * (4 - Pi_t.ndim))
+        Isz = tuple(int(v) for v in Pi_t.shape[1:4])
+        keep = []
+        f = self._struct(dev, keep)
+        dPi = _colmajor(_mod_dim(Pi_t), torch.float32, dev)
+        if which == "rx":
+            Pr_t = _mod_dim(_mod_size(_as_tensor(Pr)))
+            NM = int(Pr_t.shape[1])
+            dPr = _colmajor(Pr_t, torch.float32, dev)
+        else:
+            NM, dPr = int(M), None
+        out = torch.empty(int(np.prod(Isz)) * NM, dtype=torch.complex64 if complex_ else torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().qups_apod_generate(C.byref(f), 0 if which == "rx" else 1, _ptr(out), int(complex_), _ptr(dPi),
+                                                     _ptr(dPr), Isz[0], Isz[1], Isz[2], NM, _stream(dev)))
+        y = _from_colmajor(out, Isz + ((NM,) if which == "rx" else (1, NM)))
+        numpy_out = not (isinstance(Pi, torch.Tensor) and Pi.is_cuda)
+        return np.asfortranarray(y.cpu().numpy()) if numpy_out else y
+
+
 def das_spec(fun, Pi, Pr, Pv, Nv, x, t0, fs=None, c=1540.0, *varargin, _path=_lib.PATH_AUTO, _y_f32=False):
     """Specialised delay-and-sum beamformer — mirror of ``kern/das_spec.m:1``.
 
@@ -115,6 +175,7 @@ def das_spec(fun, Pi, Pr, Pv, Nv, x, t0, fs=None, c=1540.0, *varargin, _path=_li
     if fun not in ("DAS", "SYN", "BF", "MUL", "delays"):
         raise ValueError("Invalid beamformer.")
     VS, DV, interp_type, apod, fmod, tpose, device = True, False, "linear", [], 0.0, False, -1
+    fused = None  # closed-form apodization (FusedApod) passed through 'apod' 
     xt = _as_tensor(x) if x is not None else torch.zeros((0,))
     if xt.dtype in (torch.float64, torch.complex128):
         prec = "double"
@@ -132,7 +193,10 @@ def das_spec(fun, Pi, Pr, Pv, Nv, x, t0, fs=None, c=1540.0, *varargin, _path=_li
         elif o == "input-precision": n += 1; prec = str(args[n])
         elif o == "device": n += 1; device = int(args[n])
         elif o == "interp": n += 1; interp_type = str(args[n])
-        elif o == "apod": n += 1; apod.append(args[n])
+        elif o == "apod":
+            n += 1
+            if isinstance(args[n], FusedApod): fused = args[n] if fused is None else fused.merged(args[n])
+            else: apod.append(args[n])
         elif o == "modulation": n += 1; fmod = float(args[n])
         elif o == "transpose": n += 1; tpose = bool(args[n])
         else:
@@ -256,8 +320,14 @@ def das_spec(fun, Pi, Pr, Pv, Nv, x, t0, fs=None, c=1540.0, *varargin, _path=_li
                 yb = torch.empty((F * Om * On * I, 2), dtype=torch.float16, device=dev)
             else:
                 yb = torch.empty(F * Om * On * I, dtype=torch.complex64 if prec != "double" else torch.complex128, device=dev)
-            _lib.check(L.qups_das(C.byref(p), _ptr(yb), _ptr(dPi), _ptr(dPr), _ptr(dPv), _ptr(dNv), _ptr(dA), _ptr(dC),
-                                  acs_c, _ptr(dX), st))
+            if fused is not None:
+                keep = []
+                fz = fused._struct(dev, keep)
+                _lib.check(L.qups_das_fused(C.byref(p), C.byref(fz), _ptr(yb), _ptr(dPi), _ptr(dPr), _ptr(dPv), _ptr(dNv),
+                                            _ptr(dA), _ptr(dC), acs_c, _ptr(dX), st))
+            else:
+                _lib.check(L.qups_das(C.byref(p), _ptr(yb), _ptr(dPi), _ptr(dPr), _ptr(dPv), _ptr(dNv), _ptr(dA), _ptr(dC),
+                                      acs_c, _ptr(dX), st))
             if yb.dtype == torch.float16:
                 yb = torch.view_as_complex(yb.float())
             y = _from_colmajor(yb, Isz + (On, Om) + (fsz if fsz else ()))

@@ -56,6 +56,77 @@ class UltrasoundSystem:
     bw_frac: float = 0.6
     tx_offset: np.ndarray = field(default_factory=lambda: np.zeros((3, 1)))
     tx_normal: np.ndarray = field(default_factory=lambda: np.array([[0.0], [0.0], [1.0]]))
+    rx_normal: Optional[np.ndarray] = None   # 3 x N element normals (3rd output of Transducer.orientations); default +z
+    rx_angle: Optional[np.ndarray] = None    # N element azimuth angles in degrees (1st output of orientations); default 0
+
+    # ---- apodization generators (src/UltrasoundSystem.m:4892-5429) --------------------------------
+    # Each returns a kern.FusedApod: pass it to DAS as an apodization argument (evaluated inside the kernel), or call
+    # .dense(...) for the ND array the reference returns.  ScanCartesian geometry: the lateral pixel coordinate is x.
+    def _rx_normals(self):
+        n = self.rx.shape[1]
+        return np.broadcast_to(np.array([[0.0], [0.0], [1.0]]), (3, n)) if self.rx_normal is None else np.asarray(self.rx_normal, np.float64)
+
+    def apAcceptanceAngle(self, theta=45.0):
+        """apod = (n . (Pi - Pn)/|Pi - Pn|) >= cosd(theta)   (:5303-5375)."""
+        if not theta > 0: raise ValueError("theta must be positive")
+        return kern.FusedApod(rx_kind=_lib.AP_RX_ACCEPTANCE_ANGLE, rx_p=(np.float32(np.cos(np.deg2rad(float(theta)))),),
+                              rx_aux=self._rx_normals(), name="apAcceptanceAngle")
+
+    def apCosineAngle(self, theta=45.0):
+        """apod = cosd(min(90, (90/theta) acosd(n . r)))   (:5377-5429)."""
+        if not theta > 0: raise ValueError("theta must be positive")
+        return kern.FusedApod(rx_kind=_lib.AP_RX_COSINE_ANGLE, rx_p=(np.float32(90.0 / float(theta)),), rx_aux=self._rx_normals(),
+                              name="apCosineAngle")
+
+    def apApertureGrowth(self, f=1.5, Dmax=np.inf):
+        """apod = (z > f |2d|) & (|2d| < Dmax), d/z in the element's frame for non-planar arrays   (:5165-5267)."""
+        if not (f > 0 and Dmax > 0): raise ValueError("f and Dmax must be positive")
+        ae = None if self.rx_angle is None else np.asarray(self.rx_angle, np.float64).reshape(-1)
+        nonplanar = ae is not None and bool(np.any(ae != 0))
+        aux = np.stack([np.cos(np.deg2rad(ae)), np.sin(np.deg2rad(ae))]) if nonplanar else None
+        return kern.FusedApod(rx_kind=_lib.AP_RX_APERTURE_GROWTH, rx_p=(f, Dmax, float(nonplanar)), rx_aux=aux, name="apApertureGrowth")
+
+    def apScanline(self, tol):
+        """apod = |x_i - x_focus(m)| < tol   (:4892-4968)."""
+        if not tol > 0: raise ValueError("tol must be positive")
+        return kern.FusedApod(tx_kind=_lib.AP_TX_SCANLINE, tx_p=(np.float32(tol),), tx_aux=np.asarray(self.seq.focus, np.float64)[0], name="apScanline")
+
+    def apTranslatingAperture(self, tol):
+        """apod = |x_i - x_focus(m)| <= tol(1) & |x_i - x_n| <= tol(end)   (:5074-5163)."""
+        tol = np.atleast_1d(np.asarray(tol, np.float64))
+        if not np.all(tol > 0): raise ValueError("tol must be positive")
+        return kern.FusedApod(rx_kind=_lib.AP_RX_TRANSLATING, rx_p=(np.float32(tol[-1]),), rx_aux=np.asarray(self.rx, np.float64)[0],
+                              tx_kind=_lib.AP_TX_TRANSLATING, tx_p=(np.float32(tol[0]),), tx_aux=np.asarray(self.seq.focus, np.float64)[0],
+                              name="apTranslatingAperture")
+
+    def apTxParallelogram(self, theta=None, phi=0.0, bounds=None):
+        """Pixels whose projection along the (tilted) transmit direction lands on the aperture   (:5269-5301)."""
+        fo = np.asarray(self.seq.focus, np.float64)
+        theta = np.rad2deg(np.arctan2(fo[0], fo[2])) if theta is None else np.asarray(theta, np.float64).reshape(-1)
+        phi = np.atleast_1d(np.asarray(phi, np.float64))
+        if bounds is None:  # us.xdc.bounds(): lateral extent of the element positions
+            bounds = (float(self.rx[0].min()), float(self.rx[0].max()))
+        a1, a2 = np.deg2rad(phi[0] + theta), np.deg2rad(phi[-1] + theta)
+        aux = np.stack([np.sin(a1), np.cos(a1), np.sin(a2), np.cos(a2)])
+        return kern.FusedApod(tx_kind=_lib.AP_TX_PARALLELOGRAM, tx_p=(np.float32(bounds[0]), np.float32(bounds[1])), tx_aux=aux, name="apTxParallelogram")
+
+    def apMultiline(self):
+        """Linear weights between the two transmits straddling each scan line (:4970-5072): a small 1 x I2 x 1 x 1 x M
+        matrix, host logic exactly as the reference (find last-left / first-right transmit); passed to DAS as an array."""
+        x = np.asarray(self.scan, np.float64)[0, 0, :, 0] if self.scan.ndim == 4 else np.asarray(self.scan, np.float64)[0, 0, :]
+        xv = np.asarray(self.seq.focus, np.float64)[0]
+        A = np.zeros((x.size, xv.size))
+        for i, xi in enumerate(x):
+            da = xi - xv
+            l, r = np.nonzero(da >= 0)[0], np.nonzero(da <= 0)[0]
+            if l.size == 0 or r.size == 0:
+                continue
+            li, ri = l[-1], r[0]
+            dlr = abs(xv[li] - xv[ri])
+            al, ar = (1.0, 0.0) if dlr == 0 else (1 - abs(xv[li] - xi) / dlr, 1 - abs(xv[ri] - xi) / dlr)
+            A[i, li] += al
+            A[i, ri] += ar
+        return A.reshape(1, x.size, 1, 1, xv.size)
 
     # ---- DAS ------------------------------------------------------------------------------
     def _pos_args(self):
