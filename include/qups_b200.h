@@ -168,6 +168,28 @@ QUPS_API void qups_host_release(void);
 QUPS_API int qups_modulate(int32_t dtype, void *xout, const void *x, const void *t0, uint64_t T, uint64_t N, uint64_t M,
                   int32_t transpose, double fs, double fmod, qups_stream_t stream);
 
+/* ---- ChannelData pre-processing -------------------------------- */
+/* One pass over the cube doing what the reference scripts do with a chain of ChannelData methods before DAS
+ * (example_.m:261-269):  zeropad (src/ChannelData.m:1153-1183) -> hilbert (:935-966) -> downmix (:757-807) ->
+ * singleT / halfT cast (:452-483).  Any subset: B = A = 0, hilbert = 0, fmix = 0 disable the steps.
+ *   in  : T x K traces (K = N*M*F), element type in_dtype
+ *   out : (B+T+A) x K complex fp32 (QUPS_F32) or half2 (QUPS_F16)
+ *   t0  : device, n_t0 fp32 start times (NULL -> 0); trace k uses t0[(k / traces_per_t0) % n_t0]
+ *         (one t0 per transmit: traces_per_t0 = N, n_t0 = M).  The caller's new t0 is t0 - B/fs.
+ * hilbert: analytic signal over the padded length L = B+T+A (MATLAB hilbert(x): fft, [1 2..2 1 0..0], ifft); real part
+ *          of complex input is used.  L a power of two up to 16384, or any L <= 4096 (Bluestein). */
+typedef enum { QUPS_IN_REAL_F32 = 0, QUPS_IN_CPLX_F32 = 1, QUPS_IN_REAL_I16 = 2, QUPS_IN_REAL_F64 = 3 } qups_prep_in;
+typedef struct {
+    uint32_t struct_size;
+    int32_t in_dtype;   /* qups_prep_in */
+    int32_t out_dtype;  /* QUPS_F32 | QUPS_F16 */
+    int32_t hilbert;
+    uint64_t T, K, B, A;
+    uint64_t traces_per_t0, n_t0;
+    double fs, fmix;    /* downmix by fmix: x .* exp(-2i*pi*fmix*t) */
+} qups_prep_params;
+QUPS_API int qups_chd_prep(const qups_prep_params *p, void *out, const void *in, const void *t0, qups_stream_t stream);
+
 /* ---- wsinterpd / wsinterpd2 ------------------------------------------ */
 /* y(l) = sum over dims with ystride==0 of  exp(1i*omega*t) * w(k) * interp1(x(:,v), 1+t, interp, 0),  t = t1(r)+t2(u)
  * Image of the reference argument list (src/interpd.cu:344-349): D broadcast dims of size sizes[d]; dstride is

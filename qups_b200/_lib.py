@@ -19,7 +19,7 @@ INTERP = {"nearest": NEAREST, "linear": LINEAR, "cubic": CUBIC, "lanczos3": LANC
 
 EXPORTS = (
     "qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
-    "qups_das_fused", "qups_apod_generate", "qups_greens", "qups_convd", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
+    "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_greens", "qups_convd", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
 )
 
 
@@ -84,6 +84,17 @@ class ApodFused(C.Structure):
     ]
 
 
+class PrepParams(C.Structure):
+    """qups_prep_params: fused ChannelData pre-processing (zeropad -> hilbert -> downmix -> cast)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("in_dtype", C.c_int32), ("out_dtype", C.c_int32), ("hilbert", C.c_int32),
+        ("T", C.c_uint64), ("K", C.c_uint64), ("B", C.c_uint64), ("A", C.c_uint64),
+        ("traces_per_t0", C.c_uint64), ("n_t0", C.c_uint64),
+        ("fs", C.c_double), ("fmix", C.c_double),
+    ]
+
+
+IN_REAL_F32, IN_CPLX_F32, IN_REAL_I16, IN_REAL_F64 = range(4)
 AP_RX_NONE, AP_RX_ACCEPTANCE_ANGLE, AP_RX_COSINE_ANGLE, AP_RX_APERTURE_GROWTH, AP_RX_TRANSLATING = range(5)
 AP_TX_NONE, AP_TX_SCANLINE, AP_TX_TRANSLATING, AP_TX_PARALLELOGRAM = range(4)
 
@@ -105,6 +116,7 @@ def lib() -> C.CDLL:
     L.qups_das_fused.argtypes = [C.POINTER(DasParams), C.POINTER(ApodFused), vp, vp, vp, vp, vp, vp, vp, u64p, vp, vp]
     L.qups_apod_generate.argtypes = [C.POINTER(ApodFused), C.c_int32, vp, C.c_int32, vp, vp, C.c_uint64, C.c_uint64,
                                      C.c_uint64, C.c_uint64, vp]
+    L.qups_chd_prep.argtypes = [C.POINTER(PrepParams), vp, vp, vp, vp]
     L.qups_delays.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, u64p, vp]
     L.qups_das_host.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, u64p, vp,
                                 C.c_int]
@@ -115,7 +127,7 @@ def lib() -> C.CDLL:
     L.qups_greens.argtypes = [C.POINTER(GreensParams), vp, vp, vp, vp, vp, vp, vp]
     L.qups_convd.argtypes = [C.POINTER(ConvdParams), vp, vp, vp, vp]
     L.qups_convd.restype = C.c_int
-    for f in ("qups_das", "qups_das_fused", "qups_apod_generate", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
+    for f in ("qups_das", "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
               "qups_greens", "qups_version"):
         getattr(L, f).restype = C.c_int
     L.qups_last_error.restype = C.c_char_p

@@ -29,6 +29,7 @@ UNITS = {
     "wsinterpd2.cu": ["-fmad=false"],
     "convd.cu": ["-fmad=false"],
     "apod_gen.cu": ["-fmad=false"],
+    "chd_prep.cu": [],
     "das_tiled.cu": [],
     "qups_b200.cu": [],
 }

@@ -10,4 +10,22 @@ int launch_wsinterpd2(const qups_ws2_params &p, void *y, const void *w, const vo
 int launch_greens(const qups_greens_params &p, void *y, const void *Pi, const void *a, const void *Pr, const void *Pv,
                   const void *kern, cudaStream_t st);
 int launch_convd(const qups_convd_params &p, void *z, const void *x, const void *y, cudaStream_t st);
+
+// ChannelData pre-processing (chd_prep.cu)
+enum { PREP_REAL_F32 = 0, PREP_CPLX_F32 = 1, PREP_REAL_I16 = 2, PREP_REAL_F64 = 3 };
+
+struct PrepArgs {
+    const void *in;
+    void *out;
+    const float *t0;   // n_t0 start times (device) or nullptr (t0 = 0)
+    uint64_t T, K, B, A, L;   // L = B + T + A
+    uint64_t traces_per_t0, n_t0;
+    int in_dtype, out_half, hilbert, downmix;
+    float fs, cmix;    // cmix = fl32(-2*pi*fmix)
+    uint32_t nfft, log2n; // power-of-two FFT size (L itself, or >= 2L-1 for Bluestein)
+    int bluestein;
+};
+
+// returns 0, a cudaError_t (> 0) or -1000 (hilbert length not supported)
+int launch_chd_prep(PrepArgs a, cudaStream_t st);
 } // namespace qups

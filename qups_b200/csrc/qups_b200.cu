@@ -340,6 +340,29 @@ int qups_apod_generate(const qups_apod_fused *fz, int32_t which, void *out, int3
     return 0;
 }
 
+int qups_chd_prep(const qups_prep_params *p, void *out, const void *in, const void *t0, qups_stream_t stream) {
+    g_err[0] = 0;
+    if (!p) return fail(QUPS_ERR_INVALID, "params is NULL");
+    if (p->struct_size != sizeof(qups_prep_params)) return fail(QUPS_ERR_INVALID, "params.struct_size mismatch");
+    if (p->in_dtype < QUPS_IN_REAL_F32 || p->in_dtype > QUPS_IN_REAL_F64) return fail(QUPS_ERR_INVALID, "unknown in_dtype %d", p->in_dtype);
+    if (p->out_dtype != QUPS_F32 && p->out_dtype != QUPS_F16) return fail(QUPS_ERR_INVALID, "out_dtype must be F32 or F16");
+    if (!(p->fs > 0.0)) return fail(QUPS_ERR_INVALID, "fs must be positive");
+    if (p->K * (p->B + p->T + p->A) == 0) return 0;
+    if (!out || (!in && p->T)) return fail(QUPS_ERR_INVALID, "NULL array argument");
+    PrepArgs a{};
+    a.in = in; a.out = out; a.t0 = (const float *)t0;
+    a.T = p->T; a.K = p->K; a.B = p->B; a.A = p->A;
+    a.traces_per_t0 = p->traces_per_t0 ? p->traces_per_t0 : 1;
+    a.n_t0 = p->n_t0 ? p->n_t0 : 1;
+    a.in_dtype = p->in_dtype; a.out_half = p->out_dtype == QUPS_F16; a.hilbert = p->hilbert != 0; a.downmix = p->fmix != 0.0;
+    a.fs = (float)p->fs;
+    a.cmix = (float)(-2.0 * 3.14159265358979323846 * p->fmix);
+    const int e = launch_chd_prep(a, (cudaStream_t)stream);
+    if (e == -1000) return fail(QUPS_ERR_UNSUPPORTED, "hilbert length %llu: power of two <= 16384 or any length <= 4096", (unsigned long long)(p->B + p->T + p->A));
+    if (e) return cuda_fail(e, "chd_prep kernel");
+    return 0;
+}
+
 int qups_delays(const qups_das_params *p, void *tau, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
                 const void *cinv, const uint64_t *cstride, qups_stream_t stream) {
     g_err[0] = 0;

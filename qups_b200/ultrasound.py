@@ -36,6 +36,62 @@ class ChannelData:
     @property
     def M(self): return self.data.shape[2]
 
+    # ---- pre-processing on the device: mirrors of the ChannelData methods scripts call before DAS ----
+    # Every method is ONE pass of qups_chd_prep over the cube; prep() fuses the whole chain into a single pass.
+    def prep(self, B=0, A=0, hilbert=False, fmix=0.0, out="single"):
+        """zeropad(B, A) -> hilbert -> downmix(fmix) -> singleT/halfT in one kernel (1 read + 1 write of the cube).
+        Returns a ChannelData whose data is a CUDA tensor (complex64, or (.., 2) float16 for out='halfT')."""
+        x = self.data if isinstance(self.data, torch.Tensor) else torch.from_numpy(np.asarray(self.data))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        shp = tuple(x.shape) + (1,) * (3 - x.ndim)
+        T, K = shp[0], int(np.prod(shp[1:]))
+        kinds = {torch.float32: _lib.IN_REAL_F32, torch.complex64: _lib.IN_CPLX_F32, torch.int16: _lib.IN_REAL_I16,
+                 torch.float64: _lib.IN_REAL_F64}
+        if x.dtype == torch.complex128: x = x.to(torch.complex64)
+        if x.dtype not in kinds:
+            raise _lib.QupsError(-3, f"ChannelData.prep: unsupported data type {x.dtype}")
+        xin = kern._colmajor(x.reshape(shp), x.dtype, dev)
+        t0 = torch.as_tensor(np.asarray(self.t0, np.float64).reshape(-1)).to(device=dev, dtype=torch.float32)
+        if t0.numel() not in (1, shp[2]):
+            raise AssertionError("t0 must be a scalar or have one entry per transmit")
+        p = _lib.PrepParams()
+        p.struct_size = C.sizeof(_lib.PrepParams)
+        p.in_dtype, p.out_dtype, p.hilbert = kinds[x.dtype], (_lib.F16 if out == "halfT" else _lib.F32), int(bool(hilbert))
+        p.T, p.K, p.B, p.A = T, K, int(B), int(A)
+        p.traces_per_t0, p.n_t0 = shp[1], t0.numel()
+        p.fs, p.fmix = float(self.fs), float(fmix)
+        L = int(B) + T + int(A)
+        if out == "halfT":
+            yb = torch.empty((K * L, 2), dtype=torch.float16, device=dev)
+        else:
+            yb = torch.empty(K * L, dtype=torch.complex64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().qups_chd_prep(C.byref(p), kern._ptr(yb), kern._ptr(xin), kern._ptr(t0), kern._stream(dev)))
+        osz = (L,) + shp[1:]
+        # the C ABI writes half2; torch has no usable complex-half type, so the mirror widens the (fp16-rounded) values
+        y = kern._from_colmajor(yb, osz) if out != "halfT" else kern._from_colmajor(torch.view_as_complex(yb.float()), osz)
+        t0n = np.asarray(self.t0, np.float64) - int(B) / float(self.fs)
+        return ChannelData(y, t0n if t0n.ndim else float(t0n), self.fs)
+
+    def zeropad(self, B=0, A=0):
+        """src/ChannelData.m:1153-1183."""
+        if B < 0 or A < 0: raise AssertionError("Data append or prepend size must be positive.")
+        return self.prep(B=B, A=A)
+
+    def hilbert(self, N=None):
+        """src/ChannelData.m:935-966 (N > T zero-pads the transform, as MATLAB's hilbert(x, N))."""
+        N = self.T if N is None else int(N)
+        if N < self.T: raise _lib.QupsError(-3, "hilbert with N < T (truncation) is not implemented")
+        out = self.prep(A=N - self.T, hilbert=True)
+        return out
+
+    def downmix(self, fc):
+        """src/ChannelData.m:757-807."""
+        return self.prep(fmix=float(fc))
+
+    def singleT(self): return self.prep(out="single")
+    def halfT(self): return self.prep(out="halfT")
+
 
 @dataclass
 class Sequence:

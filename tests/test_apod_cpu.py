@@ -88,3 +88,17 @@ def test_ultrasound_mirror_multiline_matches_oracle():
     A = us.apMultiline()
     assert A.shape == (1, Pi.shape[2], 1, 1, 5)
     assert np.array_equal(A[0, :, 0, 0, :], ap.apMultiline(Pi[0, 0, :, 0], xv))
+
+
+def test_prep_oracle_hilbert_equals_scipy_and_weights():
+    """oracle/prep_np.py: the reference's hilbert weights (src/ChannelData.m:961-962) == scipy.signal.hilbert (MATLAB's definition)."""
+    import scipy.signal as ss
+    from oracle import prep_np
+    rng = np.random.default_rng(0)
+    for T in (64, 101, 100, 7):
+        x = rng.standard_normal((T, 2, 2))
+        y, _ = prep_np.prep(x, 0.0, 1.0, hilbert=True)
+        assert np.max(np.abs(y - ss.hilbert(x, axis=0))) < 1e-6
+    assert list(prep_np.hilbert_weights(5)) == [1, 2, 2, 0, 0] and list(prep_np.hilbert_weights(6)) == [1, 2, 2, 1, 0, 0]
+    y, t0 = prep_np.prep(np.ones((4, 1, 1)), 1e-6, 1e6, B=2, A=1)
+    assert y.shape == (7, 1, 1) and t0 == pytest.approx(-1e-6) and list(y[:, 0, 0].real) == [0, 0, 1, 1, 1, 1, 0]
