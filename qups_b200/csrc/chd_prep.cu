@@ -30,8 +30,17 @@ namespace qups {
 void count_launch(uint64_t n);
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// in-place radix-2 FFT of s[0..n) in shared memory, all threads of the CTA; inverse = conjugate twiddles (unscaled)
-__device__ void fft_pow2(float2 *s, uint32_t n, uint32_t log2n, bool inverse) {
+// in-place radix-2 FFT of s[0..n) in shared memory, all threads of the CTA; tw[j] = exp(-2*pi*i*j/n), j < n/2
+// (built once per CTA by fft_twiddles); inverse = conjugate twiddles (unscaled)
+__device__ void fft_twiddles(float2 *tw, uint32_t n) {
+    for (uint32_t j = threadIdx.x; j < (n >> 1); j += blockDim.x) {
+        float sn, cs;
+        sincospif(-2.0f * (float)j / (float)n, &sn, &cs); // exact dyadic argument
+        tw[j] = make_float2(cs, sn);
+    }
+    __syncthreads();
+}
+__device__ void fft_pow2(float2 *s, const float2 *tw, uint32_t n, uint32_t log2n, bool inverse) {
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     for (uint32_t i = tid; i < n; i += nt) {
         const uint32_t j = __brev(i) >> (32 - log2n);
@@ -39,14 +48,13 @@ __device__ void fft_pow2(float2 *s, uint32_t n, uint32_t log2n, bool inverse) {
     }
     __syncthreads();
     for (uint32_t st = 1; st <= log2n; ++st) {
-        const uint32_t half = 1u << (st - 1);
+        const uint32_t half = 1u << (st - 1), tshift = log2n - st;
         for (uint32_t b = tid; b < (n >> 1); b += nt) {
             const uint32_t k = b & (half - 1);
             const uint32_t i0 = ((b >> (st - 1)) << st) + k, i1 = i0 + half;
-            float sn, cs;
-            sincospif(-(float)k / (float)half, &sn, &cs); // exp(-i*pi*k/half), exact dyadic argument
-            if (inverse) sn = -sn;
-            const float2 a = s[i0], t = cmulf(s[i1], make_float2(cs, sn));
+            float2 w = tw[k << tshift]; // exp(-i*pi*k/half)
+            if (inverse) w.y = -w.y;
+            const float2 a = s[i0], t = cmulf(s[i1], w);
             s[i0] = make_float2(a.x + t.x, a.y + t.y);
             s[i1] = make_float2(a.x - t.x, a.y - t.y);
         }
@@ -63,7 +71,7 @@ __device__ __forceinline__ float2 chirp(uint64_t n, uint64_t L) {
 }
 
 // DFT of length L (arbitrary) of s[0..L) via Bluestein; work arrays s (nfft) and cb (nfft, precomputed FFT of conj chirp)
-__device__ void dft_bluestein(float2 *s, const float2 *cb, uint64_t L, uint32_t nfft, uint32_t log2n, bool inverse) {
+__device__ void dft_bluestein(float2 *s, const float2 *tw, const float2 *cb, const float2 *ch, uint64_t L, uint32_t nfft, uint32_t log2n, bool inverse) {
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     // inverse DFT = conj(DFT(conj(x)))
     for (uint32_t i = tid; i < nfft; i += nt) {
@@ -71,40 +79,45 @@ __device__ void dft_bluestein(float2 *s, const float2 *cb, uint64_t L, uint32_t 
         if (i < L) {
             v = s[i];
             if (inverse) v.y = -v.y;
-            v = cmulf(v, chirp(i, L));
+            v = cmulf(v, ch[i]);
         }
         s[i] = v;
     }
     __syncthreads();
-    fft_pow2(s, nfft, log2n, false);
+    fft_pow2(s, tw, nfft, log2n, false);
     for (uint32_t i = tid; i < nfft; i += nt) s[i] = cmulf(s[i], cb[i]);
     __syncthreads();
-    fft_pow2(s, nfft, log2n, true);
+    fft_pow2(s, tw, nfft, log2n, true);
     const float sc = 1.0f / (float)nfft;
     for (uint32_t i = tid; i < L; i += nt) {
-        float2 v = cmulf(make_float2(s[i].x * sc, s[i].y * sc), chirp(i, L));
+        float2 v = cmulf(make_float2(s[i].x * sc, s[i].y * sc), ch[i]);
         if (inverse) v.y = -v.y;
         s[i] = v;
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) chd_prep_kernel(const PrepArgs a) {
+__global__ void __launch_bounds__(1024) chd_prep_kernel(const PrepArgs a) {
     extern __shared__ __align__(16) unsigned char prep_smem[];
     float2 *s = reinterpret_cast<float2 *>(prep_smem);
-    float2 *cb = s + (a.hilbert ? a.nfft : 0); // Bluestein: FFT of the wrapped conjugate chirp
+    float2 *tw = s + (a.hilbert ? a.nfft : 0);        // twiddles exp(-2*pi*i*j/nfft), j < nfft/2
+    float2 *cb = tw + (a.nfft >> 1);                  // Bluestein: FFT of the wrapped conjugate chirp (nfft)
+    float2 *ch = cb + a.nfft;                         // Bluestein: chirp c[n], n < L
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint64_t L = a.L;
 
+    if (a.hilbert) fft_twiddles(tw, a.nfft);
     if (a.hilbert && a.bluestein) {
+        for (uint32_t i = tid; i < L; i += nt) ch[i] = chirp(i, L);
+        __syncthreads();
         for (uint32_t i = tid; i < a.nfft; i += nt) {
             float2 v = make_float2(0.f, 0.f);
-            if (i < L) { v = chirp(i, L); v.y = -v.y; }
-            else if (a.nfft - i < L) { v = chirp(a.nfft - i, L); v.y = -v.y; }
+            if (i < L) { v = ch[i]; v.y = -v.y; }
+            else if (a.nfft - i < L) { v = ch[a.nfft - i]; v.y = -v.y; }
             cb[i] = v;
         }
         __syncthreads();
-        fft_pow2(cb, a.nfft, a.log2n, false);
+        fft_pow2(cb, tw, a.nfft, a.log2n, false);
     }
 
     for (uint64_t k = blockIdx.x; k < a.K; k += gridDim.x) {
@@ -123,8 +136,8 @@ __global__ void __launch_bounds__(256) chd_prep_kernel(const PrepArgs a) {
             }
             __syncthreads();
             // ---- analytic signal: fft, weights [1, 2 x (Nd2-1), 1+mod(L,2), 0 ...], ifft (src/ChannelData.m:960-964) ----
-            if (a.bluestein) dft_bluestein(s, cb, L, a.nfft, a.log2n, false);
-            else fft_pow2(s, a.nfft, a.log2n, false);
+            if (a.bluestein) dft_bluestein(s, tw, cb, ch, L, a.nfft, a.log2n, false);
+            else fft_pow2(s, tw, a.nfft, a.log2n, false);
             const uint64_t nd2 = L / 2;
             for (uint64_t j = tid; j < L; j += nt) {
                 float w;
@@ -136,8 +149,8 @@ __global__ void __launch_bounds__(256) chd_prep_kernel(const PrepArgs a) {
                 s[j] = make_float2(s[j].x * w, s[j].y * w);
             }
             __syncthreads();
-            if (a.bluestein) dft_bluestein(s, cb, L, a.nfft, a.log2n, true);
-            else fft_pow2(s, a.nfft, a.log2n, true);
+            if (a.bluestein) dft_bluestein(s, tw, cb, ch, L, a.nfft, a.log2n, true);
+            else fft_pow2(s, tw, a.nfft, a.log2n, true);
         }
         // ---- downmix + cast + store ----------------------------------------------------------------------
         float t0 = 0.f;
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(256) chd_prep_kernel(const PrepArgs a) {
             if (a.out_half) reinterpret_cast<__half2 *>(a.out)[k * L + j] = __floats2half2_rn(v.x, v.y);
             else reinterpret_cast<float2 *>(a.out)[k * L + j] = v;
         }
-        __syncthreads();
+        if (a.hilbert) __syncthreads();
     }
 }
 
@@ -184,7 +197,7 @@ int launch_chd_prep(PrepArgs a, cudaStream_t st) {
         const uint64_t need = pow2 ? a.L : 2 * a.L - 1;
         while (n < need) { n <<= 1; ++lg; if (lg > 20) return -1000; }
         a.nfft = n; a.log2n = lg; a.bluestein = !pow2;
-        smem = sizeof(float2) * (size_t)n * (a.bluestein ? 2 : 1);
+        smem = sizeof(float2) * ((size_t)n + n / 2 + (a.bluestein ? (size_t)n + a.L : 0));
         if (smem > 200 * 1024) return -1000;
     }
     cudaError_t e = cudaFuncSetAttribute(chd_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024));
@@ -192,9 +205,19 @@ int launch_chd_prep(PrepArgs a, cudaStream_t st) {
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = smem ? (int)((200 * 1024) / smem > 8 ? 8 : (200 * 1024) / smem) : 8;
-    const uint64_t cap = (uint64_t)sms * (per_sm < 1 ? 1 : per_sm);
-    chd_prep_kernel<<<(unsigned)(a.K < cap ? a.K : cap), 256, smem, st>>>(a);
+    // FFT traces: persistent CTAs (tables are built once per CTA), as many as shared memory allows, wide CTAs when one
+    // trace fills the SM; plain element-wise passes: one CTA per trace, no barriers
+    unsigned threads = 256;
+    uint64_t grid = a.K;
+    if (a.hilbert) {
+        int per_sm = (int)((200 * 1024) / smem);
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        threads = per_sm >= 4 ? 256 : (per_sm >= 2 ? 512 : 1024);
+        const uint64_t cap = (uint64_t)sms * per_sm;
+        grid = a.K < cap ? a.K : cap;
+    } else if (grid > 0x7fffffffull) grid = 0x7fffffffull;
+    chd_prep_kernel<<<(unsigned)grid, threads, smem, st>>>(a);
     count_launch(1);
     return (int)cudaGetLastError();
 }
