@@ -15,6 +15,12 @@ function y = qups_b200_feval(op, C, varargin)
 %     'c0',c0,'R0',kwargs.R0,'E',E,'interp',flagnum).  The host-side scatterer windowing (sb, iblock,
 %     :678-714) is not needed: the library windows internally.
 %
+% y = QUPS_B200_FEVAL('das', C, ..., [fs, fmod], rx_aux, tx_aux, lat) with C.ap_rx_kind / ap_tx_kind / ap_rx_p / ap_tx_p /
+% ap_lat_dim set from a qups_b200_apod struct evaluates closed-form apodization inside the kernel
+% (replaces the dense arrays of src/UltrasoundSystem.m:4892-5429); a = QUPS_B200_FEVAL('apod', C, a0, Pi, Pr, rx_aux,
+% tx_aux, lat) returns the dense array itself; y = QUPS_B200_FEVAL('prep', C, y0, x, t0) fuses
+% zeropad -> hilbert -> downmix -> cast (src/ChannelData.m:757-807, 935-966, 1153-1183) into one pass.
+%
 % All array arguments are gpuArrays of the class the reference already prepares at these sites; the result
 % is a gpuArray with the size and class of the first array argument, like feval's return value.
 %

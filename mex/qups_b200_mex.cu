@@ -12,6 +12,10 @@
 //   y = qups_b200_mex('das',    C, yg, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, [fs fmod])
 //   y = qups_b200_mex('ws2',    C, y0, w, x, t1, t2, dsizes, strides)
 //   x = qups_b200_mex('greens', C, x0, ps, as, pn, pv, kn)
+//   y = qups_b200_mex('das',    C, yg, ..., [fs fmod], rx_aux, tx_aux, lat)   closed-form apodization (C.ap_rx_kind / C.ap_tx_kind,
+//                                                                               C.ap_rx_p, C.ap_tx_p, C.ap_lat_dim; empty [] for unused arrays)
+//   a = qups_b200_mex('apod',   C, a0, Pi, Pr, rx_aux, tx_aux, lat)           dense image of the same generator (C.which = 0 rx | 1 tx)
+//   y = qups_b200_mex('prep',   C, y0, x, t0)                                 zeropad -> hilbert -> downmix -> cast (C.B, C.A, C.hilbert, C.fmix, C.fs, C.N)
 // where C is a scalar struct holding what the reference puts in __constant__ memory with k.setConstantMemory
 // (kern/das_spec.m:294-298): C.I1,C.I2,C.I3,C.N,C.M,C.T,C.S,C.VS,C.DV,C.flag  (+ ws2: C.T,C.interp,C.omega ;
 // greens: C.n0,C.t0x,C.fs,C.fsr,C.c0,C.R0,C.E,C.interp).  The output is a new gpuArray of the size/type of the
@@ -33,6 +37,18 @@ static int dtype_of(const mxGPUArray *a) {
         default: mexErrMsgIdAndTxt("QUPS:b200:type", "Unsupported data class."); return -1;
     }
 }
+static void fill_apf(qups_apod_fused *f, const mxArray *C, const mxGPUArray *rx, const mxGPUArray *tx, const mxGPUArray *lat) {
+    memset(f, 0, sizeof(*f));
+    f->struct_size = sizeof(*f);
+    f->rx_kind = (int32_t)fld(C, "ap_rx_kind", 0); f->tx_kind = (int32_t)fld(C, "ap_tx_kind", 0);
+    f->lat_dim = (int32_t)fld(C, "ap_lat_dim", 2);
+    const mxArray *rp = mxGetField(C, 0, "ap_rx_p"), *tp = mxGetField(C, 0, "ap_tx_p");
+    for (size_t k = 0; rp && k < mxGetNumberOfElements(rp) && k < 4; ++k) f->rx_p[k] = (float)mxGetPr(rp)[k];
+    for (size_t k = 0; tp && k < mxGetNumberOfElements(tp) && k < 4; ++k) f->tx_p[k] = (float)mxGetPr(tp)[k];
+    f->rx_aux = rx && mxGPUGetNumberOfElements(rx) ? mxGPUGetDataReadOnly(rx) : NULL;   /* single gpuArrays */
+    f->tx_aux = tx && mxGPUGetNumberOfElements(tx) ? mxGPUGetDataReadOnly(tx) : NULL;
+    f->lat = lat && mxGPUGetNumberOfElements(lat) ? mxGPUGetDataReadOnly(lat) : NULL;
+}
 static void check(int rc) {
     if (rc != 0) mexErrMsgIdAndTxt("QUPS:b200:error", "libqups_b200 error %d: %s", rc, qups_last_error());
 }
@@ -53,7 +69,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
 #define RO(a) mxGPUGetDataReadOnly(a)
 
     if (!strcmp(op, "das")) {
-        if (nrhs != 12) mexErrMsgIdAndTxt("QUPS:b200:usage", "'das' takes 12 arguments");
+        if (nrhs != 12 && nrhs != 15) mexErrMsgIdAndTxt("QUPS:b200:usage", "'das' takes 12 arguments (15 with closed-form apodization)");
         const mxGPUArray *Pi = IN(3), *Pr = IN(4), *Pv = IN(5), *Nv = IN(6), *ap = IN(7), *ci = IN(8), *x = IN(10);
         qups_das_params p;
         memset(&p, 0, sizeof(p));
@@ -69,6 +85,13 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         /* [cstride, astride] arrives as a host uint64 array (MATLAB copies small arrays for feval) */
         if (!mxIsUint64(prhs[9])) mexErrMsgIdAndTxt("QUPS:b200:type", "strides must be uint64");
         const uint64_t *acs = (const uint64_t *)mxGetData(prhs[9]);
+        if (nrhs == 15) { /* closed-form apodization evaluated in-kernel (src/UltrasoundSystem.m:4892-5429 generators) */
+            const mxGPUArray *rxa = IN(12), *txa = IN(13), *lat = IN(14);
+            qups_apod_fused f;
+            fill_apf(&f, C, rxa, txa, lat);
+            check(qups_das_fused(&p, &f, y, RO(Pi), RO(Pr), RO(Pv), RO(Nv), p.S ? RO(ap) : NULL, RO(ci), acs, RO(x), NULL));
+            mxGPUDestroyGPUArray(rxa); mxGPUDestroyGPUArray(txa); mxGPUDestroyGPUArray(lat);
+        } else
         check(qups_das(&p, y, RO(Pi), RO(Pr), RO(Pv), RO(Nv), p.S ? RO(ap) : NULL, RO(ci), acs, RO(x), NULL));
         mxGPUDestroyGPUArray(Pi); mxGPUDestroyGPUArray(Pr); mxGPUDestroyGPUArray(Pv); mxGPUDestroyGPUArray(Nv);
         mxGPUDestroyGPUArray(ap); mxGPUDestroyGPUArray(ci); mxGPUDestroyGPUArray(x);
@@ -112,6 +135,36 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         check(qups_greens(&p, y, RO(ps), RO(as), RO(pn), RO(pv), RO(kn), NULL));
         mxGPUDestroyGPUArray(ps); mxGPUDestroyGPUArray(as); mxGPUDestroyGPUArray(pn); mxGPUDestroyGPUArray(pv);
         mxGPUDestroyGPUArray(kn);
+    } else if (!strcmp(op, "apod")) {
+        if (nrhs != 8) mexErrMsgIdAndTxt("QUPS:b200:usage", "'apod' takes 8 arguments");
+        const mxGPUArray *Pi = IN(3), *Pr = IN(4), *rxa = IN(5), *txa = IN(6), *lat = IN(7);
+        qups_apod_fused f;
+        fill_apf(&f, C, rxa, txa, lat);
+        const int which = (int)fld(C, "which", 0);
+        check(qups_apod_generate(&f, which, y, mxGPUGetComplexity(out) == mxCOMPLEX, RO(Pi), RO(Pr), (uint64_t)fld(C, "I1", 1),
+                                 (uint64_t)fld(C, "I2", 1), (uint64_t)fld(C, "I3", 1), (uint64_t)fld(C, which ? "M" : "N", 1), NULL));
+        mxGPUDestroyGPUArray(Pi); mxGPUDestroyGPUArray(Pr); mxGPUDestroyGPUArray(rxa); mxGPUDestroyGPUArray(txa); mxGPUDestroyGPUArray(lat);
+    } else if (!strcmp(op, "prep")) {
+        if (nrhs != 5) mexErrMsgIdAndTxt("QUPS:b200:usage", "'prep' takes 5 arguments");
+        const mxGPUArray *x = IN(3), *t0 = IN(4);            /* y0: complex single (B+T+A) x N x M prototype; t0: single */
+        qups_prep_params p;
+        memset(&p, 0, sizeof(p));
+        p.struct_size = sizeof(p);
+        const bool cplx = mxGPUGetComplexity(x) == mxCOMPLEX;
+        switch (mxGPUGetClassID(x)) {
+            case mxSINGLE_CLASS: p.in_dtype = cplx ? QUPS_IN_CPLX_F32 : QUPS_IN_REAL_F32; break;
+            case mxINT16_CLASS: p.in_dtype = QUPS_IN_REAL_I16; break;
+            case mxDOUBLE_CLASS: p.in_dtype = QUPS_IN_REAL_F64; break;
+            default: mexErrMsgIdAndTxt("QUPS:b200:type", "Unsupported data class.");
+        }
+        p.out_dtype = mxGPUGetClassID(out) == mxUINT16_CLASS ? QUPS_F16 : QUPS_F32;
+        const mwSize *xs = mxGPUGetDimensions(x);
+        p.T = xs[0]; p.K = mxGPUGetNumberOfElements(x) / (xs[0] ? xs[0] : 1);
+        p.B = (uint64_t)fld(C, "B", 0); p.A = (uint64_t)fld(C, "A", 0); p.hilbert = (int32_t)fld(C, "hilbert", 0);
+        p.traces_per_t0 = (uint64_t)fld(C, "N", 1); p.n_t0 = mxGPUGetNumberOfElements(t0);
+        p.fs = fld(C, "fs", 1); p.fmix = fld(C, "fmix", 0);
+        check(qups_chd_prep(&p, y, RO(x), p.n_t0 ? RO(t0) : NULL, NULL));
+        mxGPUDestroyGPUArray(x); mxGPUDestroyGPUArray(t0);
     } else {
         mexErrMsgIdAndTxt("QUPS:b200:usage", "unknown op '%s'", op);
     }

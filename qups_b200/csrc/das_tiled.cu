@@ -763,8 +763,13 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                     __syncwarp();
                     if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * s, total);
                     __syncwarp();
+#if QUPS_EXP == 3
+                    // experiment (timing only, wrong data): the stage's bytes as ONE bulk copy instead of up to 32
+                    if (lane == 0 && total) bulk_g2s(ring + s * kNT * a.wmax * 8u, a.x + (((uint64_t)m * a.N + nt * kNT) * a.T & ~1ull), total, bar_full + 8 * s);
+#else
                     if (bytes[0]) bulk_g2s(dst[0], src[0], bytes[0], bar_full + 8 * s);
                     if (bytes[1]) bulk_g2s(dst[1], src[1], bytes[1], bar_full + 8 * s);
+#endif
                     ++it;
                 }
             }

@@ -32,13 +32,15 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_sizes_match_the_header(lib, tmp_path):
     from qups_b200 import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include "qups_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n", '
-                   'sizeof(qups_das_params), sizeof(qups_ws2_params), sizeof(qups_greens_params));return 0;}\n')
+    src.write_text('#include "qups_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(qups_das_params), sizeof(qups_ws2_params), sizeof(qups_greens_params), sizeof(qups_apod_fused), '
+                   'sizeof(qups_prep_params), sizeof(qups_convd_params));return 0;}\n')
     exe = tmp_path / "sz"
     env = dict(os.environ); env.pop("CC", None)
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True, env=env)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
-    assert [int(v) for v in out] == [C.sizeof(_lib.DasParams), C.sizeof(_lib.Ws2Params), C.sizeof(_lib.GreensParams)]
+    assert [int(v) for v in out] == [C.sizeof(_lib.DasParams), C.sizeof(_lib.Ws2Params), C.sizeof(_lib.GreensParams),
+                                     C.sizeof(_lib.ApodFused), C.sizeof(_lib.PrepParams), C.sizeof(_lib.ConvdParams)]
 
 
 def test_validation_errors_without_a_gpu(lib):
@@ -85,3 +87,69 @@ def test_no_oracle_on_the_product_path():
         if fn.endswith(".py"):
             src = open(os.path.join(pk, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_fused_apod_and_prep_validation_without_a_gpu(lib):
+    from qups_b200 import _lib
+    p = _lib.DasParams()
+    p.struct_size = C.sizeof(_lib.DasParams)
+    p.dtype, p.flag, p.T = _lib.F32, _lib.CUBIC, 100
+    f = _lib.ApodFused()
+    assert lib.qups_das_fused(C.byref(p), C.byref(f), None, None, None, None, None, None, None, None, None, None) == -1
+    assert b"struct_size" in lib.qups_last_error()
+    f.struct_size = C.sizeof(_lib.ApodFused)
+    f.rx_kind = 9
+    assert lib.qups_das_fused(C.byref(p), C.byref(f), None, None, None, None, None, None, None, None, None, None) == -1
+    f.rx_kind = _lib.AP_RX_ACCEPTANCE_ANGLE  # needs the element normals
+    assert lib.qups_das_fused(C.byref(p), C.byref(f), None, None, None, None, None, None, None, None, None, None) == -1
+    assert b"rx_aux" in lib.qups_last_error()
+    f.rx_kind, f.tx_kind = 0, _lib.AP_TX_SCANLINE
+    assert lib.qups_apod_generate(C.byref(f), 1, None, 0, None, None, 4, 4, 1, 3, None) == -1
+    q = _lib.PrepParams()
+    assert lib.qups_chd_prep(C.byref(q), None, None, None, None) == -1
+    q.struct_size = C.sizeof(_lib.PrepParams)
+    q.in_dtype, q.out_dtype, q.fs = 7, _lib.F32, 1.0
+    assert lib.qups_chd_prep(C.byref(q), None, None, None, None) == -1
+    q.in_dtype, q.fs = _lib.IN_REAL_F32, 0.0
+    assert lib.qups_chd_prep(C.byref(q), None, None, None, None) == -1
+    q.fs, q.T, q.K = 1.0, 0, 0   # empty cube: nothing to do
+    assert lib.qups_chd_prep(C.byref(q), None, None, None, None) == 0
+
+
+def test_mex_gateway_compiles_against_a_stub_mex_h(tmp_path):
+    """MATLAB is absent: syntax/type-check mex/qups_b200_mex.cu against minimal stand-ins for mex.h / mxGPUArray.h."""
+    (tmp_path / "gpu").mkdir()
+    (tmp_path / "mex.h").write_text("""
+#include <stddef.h>
+typedef struct mxArray_tag mxArray; typedef size_t mwSize;
+typedef enum { mxDOUBLE_CLASS, mxSINGLE_CLASS, mxUINT16_CLASS, mxINT16_CLASS, mxUINT64_CLASS } mxClassID;
+typedef enum { mxREAL, mxCOMPLEX } mxComplexity;
+#ifdef __cplusplus
+extern "C" {
+#endif
+const mxArray *mxGetField(const mxArray *, size_t, const char *); double mxGetScalar(const mxArray *);
+void mexErrMsgIdAndTxt(const char *, const char *, ...); bool mxIsChar(const mxArray *); bool mxIsStruct(const mxArray *);
+int mxGetString(const mxArray *, char *, size_t); double *mxGetPr(const mxArray *); bool mxIsUint64(const mxArray *);
+void *mxGetData(const mxArray *); size_t mxGetNumberOfElements(const mxArray *);
+#ifdef __cplusplus
+}
+#endif
+""")
+    (tmp_path / "gpu" / "mxGPUArray.h").write_text("""
+typedef struct mxGPUArray_tag mxGPUArray;
+#ifdef __cplusplus
+extern "C" {
+#endif
+int mxInitGPU(void); const mxGPUArray *mxGPUCreateFromMxArray(const mxArray *); mxGPUArray *mxGPUCopyGPUArray(const mxGPUArray *);
+void mxGPUDestroyGPUArray(const mxGPUArray *); void *mxGPUGetData(mxGPUArray *); const void *mxGPUGetDataReadOnly(const mxGPUArray *);
+mxClassID mxGPUGetClassID(const mxGPUArray *); mxComplexity mxGPUGetComplexity(const mxGPUArray *);
+const mwSize *mxGPUGetDimensions(const mxGPUArray *); mwSize mxGPUGetNumberOfDimensions(const mxGPUArray *);
+mwSize mxGPUGetNumberOfElements(const mxGPUArray *); mxArray *mxGPUCreateMxArrayOnGPU(const mxGPUArray *);
+#ifdef __cplusplus
+}
+#endif
+""")
+    env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
+    r = subprocess.run(["g++", "-x", "c++", "-fsyntax-only", "-I", str(tmp_path), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "mex", "qups_b200_mex.cu")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
