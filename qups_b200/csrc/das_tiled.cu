@@ -29,6 +29,7 @@
 // sequence (common.cuh), so tap indices are bit-identical to the oracle; the
 // interpolation weights / accumulation use FMAs (tolerance-level difference).
 #include <limits.h>
+#include <math.h>
 #include <stdio.h>
 #include "das_args.cuh"
 
@@ -74,8 +75,7 @@ constexpr int kThreads = (kCW + 1) * 32;
 #endif
 constexpr int kLPA = QUPS_LPA;        // lanes of a warp along the lane axis (32, 16 or 8)
 constexpr int kBarBytes = ((2 * kStages * 8 + 63) / 64) * 64;  // full[] + empty[] mbarriers
-constexpr int kTA = 32;        // tile extent along the lane axis
-constexpr int kTB = kCW * kR;  // tile extent along the row axis
+constexpr int kTilePix = kCW * 32 * kR; // pixels per tile; its SHAPE (tA x tB, lane patch lpa) is chosen per call from the pixel spacing
 
 // QUPS_MAGIC: the cubic fast path derives the tap address from the bits of 2^23 + floor(xq); the constant
 // (0x4B000000 << 3) mod 2^32 is folded into the published slot offset
@@ -95,7 +95,9 @@ struct TiledArgs {
     uint32_t IA, IB, IC;    // extents: lane axis, row axis, slice axis
     uint64_t sA, sB, sC;    // pixel-index strides of those axes
     uint32_t tilesA, tilesB;
+    uint32_t tA, tB, lpa;   // tile extents along the lane / row axes (tA * tB = kTilePix) and lanes of a warp along the lane axis
     uint32_t wmax;          // samples per smem slot (even)
+    uint32_t stages;        // ring depth in use (2 .. kStages): fewer, longer slots on coarse pixel grids
     uint32_t numNT;
     uint32_t nsplit;        // receive-axis split: CTA (tile, split) handles a contiguous range of receive tiles
     float2 *part;           // nsplit > 1: partial images [nsplit][I], summed in order by das_reduce_kernel
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
     const uint32_t ring_off = (uint32_t)((kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * ((FUSED ? 5 : 4) * a.M + (FUSED ? 3 : 2) * a.N) + 127) & ~127u);
     const uint32_t ring = smem_u32(smem_raw) + ring_off;
     // FUSED == 2: receive-weight table [kNT][kCW*32] float2 (.x/.y = the thread's two pixel rows) behind the ring
-    const uint32_t wtab = ring + kStages * kNT * a.wmax * 8u;
+    const uint32_t wtab = ring + a.stages * kNT * a.wmax * 8u;
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -396,11 +398,11 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
     // receive tiles [nt0, nt1) of this CTA (balanced contiguous ranges)
     const uint32_t nt0 = (uint32_t)(((uint64_t)a.numNT * split) / a.nsplit), nt1 = (uint32_t)(((uint64_t)a.numNT * (split + 1)) / a.nsplit);
     const uint32_t ta = tile % a.tilesA, tb = (tile / a.tilesA) % a.tilesB, tc = tile / (a.tilesA * a.tilesB);
-    // lane patch: a warp covers kLPA pixels along the lane axis x (32/kLPA) pixel-row pairs; a compact 2-D
-    // patch keeps the tap addresses of a half-warp inside one 128-byte row of shared memory
-    constexpr int kWA = kTA / kLPA, kLPB = 32 / kLPA;
-    static_assert(kCW % kWA == 0, "consumer warps must tile the lane axis");
-    const uint32_t ia = ta * kTA + (warp % kWA) * kLPA + (lane % kLPA);
+    // lane patch: a warp covers lpa pixels along the lane axis x (32/lpa) pixel-row pairs; wA = tA/lpa warps sit side by
+    // side along the lane axis.  A compact patch keeps the tap addresses of a half-warp inside one 128-byte row of shared
+    // memory; the tile shape follows the pixel spacing so the staged windows stay short on anisotropic grids.
+    const uint32_t lpa = a.lpa, lpb = 32u / lpa, wA = a.tA / lpa;
+    const uint32_t ia = ta * a.tA + (warp % wA) * lpa + (lane % lpa);
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
         bool valid[kR];
 #pragma unroll
         for (int r = 0; r < kR; ++r) {
-            const uint32_t ib = tb * kTB + ((warp / kWA) * kLPB + (lane / kLPA)) * kR + r;
+            const uint32_t ib = tb * a.tB + ((warp / wA) * lpb + (lane / lpa)) * kR + r;
             valid[r] = (ia < a.IA) && (ib < a.IB);
             // out-of-image lanes shadow a valid pixel so they never widen the windows
             const uint32_t ca = ia < a.IA ? ia : a.IA - 1, cb = ib < a.IB ? ib : a.IB - 1;
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
         for (int j = 0; j < kNT; ++j) dr[j] = make_float2(0.f, 0.f);
         int cur_nt = -1;
         for (uint32_t it = 0;; ++it) {
-            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
             mbar_wait(bar_full + 8 * s, ph);
             const int4 hdr = stage_hdr[s]; // kind, m, nt
             if (hdr.x == ST_END) break;
@@ -683,7 +685,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                 while (todo) {
                     const uint32_t m = m0 + (uint32_t)(__ffs((int)todo) - 1);
                     todo &= todo - 1;
-                    const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                    const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
                     int flag = TR_SKIP;
                     // up to two windows per trace: [0] single window / dv < 0 cluster, [1] dv >= 0 cluster
                     uint32_t bytes[2] = {0u, 0u}, soff[2] = {0u, 0u}, dst[2] = {0u, 0u};
@@ -776,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
         }
         // end-of-work marker
         {
-            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
             if (lane == 0) {
                 stage_hdr[s] = make_int4(ST_END, 0, 0, 0);
@@ -800,10 +802,10 @@ __global__ void __launch_bounds__(256) das_reduce_kernel(float2 *y, const float2
 }
 
 // ---- host side ------------------------------------------------------------------------
-static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax, int fused = 0) {
+static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax, int fused = 0, uint32_t stages = kStages) {
     size_t head = kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * ((fused ? 5 : 4) * (size_t)M + (fused ? 3 : 2) * (size_t)N);
     head = (head + 127) & ~(size_t)127;
-    return head + (size_t)kStages * kNT * wmax * 8 + (fused == 2 ? (size_t)kNT * kCW * 32 * 8 : 0);
+    return head + (size_t)stages * kNT * wmax * 8 + (fused == 2 ? (size_t)kNT * kCW * 32 * 8 : 0);
 }
 
 TiledPlan das_tiled_plan(const DasArgs<float> &a, int dtype_in, int dtype_out) {
@@ -847,17 +849,82 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     if (lane_axis == 2) { t.IA = (uint32_t)a.I2; t.sA = a.I1; t.IB = (uint32_t)a.I1; t.sB = 1; }
     else                { t.IA = (uint32_t)a.I1; t.sA = 1;    t.IB = (uint32_t)a.I2; t.sB = a.I1; }
     t.IC = (uint32_t)a.I3; t.sC = a.I1 * a.I2;
-    t.tilesA = (t.IA + kTA - 1) / kTA;
-    t.tilesB = (t.IB + kTB - 1) / kTB;
+    double span_m = 0.0; // path-length spread across one tile (metres, sum of the two tile extents)
+    // ---- tile shape: 512 pixels as tA x tB with a lpa x (32/lpa) x 2 warp patch, chosen so that the delay spread across the
+    // tile (~ pixel spacing x extent) is smallest: square-ish on isotropic grids (32 x 16, patch 8 x 4 x 2 — measured best on the
+    // headline grid), narrow along a coarsely sampled axis (e.g. one image column per element pitch).  The spacing is read
+    // from three pixel positions; the decision is cached per (Pi, grid) so only the first call with a new grid synchronises.
+    {
+        struct ShapeCache { const void *Pi; uint64_t I1, I2, I3; int lane_axis; uint32_t tA, lpa; double span; };
+        static thread_local ShapeCache sc = {nullptr, 0, 0, 0, 0, 0, 0, 0.0};
+        uint32_t tA = 32, lpa = QUPS_LPA;
+        if (sc.Pi == a.Pi && sc.I1 == a.I1 && sc.I2 == a.I2 && sc.I3 == a.I3 && sc.lane_axis == lane_axis) {
+            tA = sc.tA; lpa = sc.lpa; span_m = sc.span;
+        } else {
+            float P0[3], PA[3], PB[3];
+            double dA = 1.0, dB = 1.0;
+            const bool okA = t.IA > 1, okB = t.IB > 1;
+            cudaError_t ce = cudaMemcpyAsync(P0, a.Pi, sizeof(P0), cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess && okA) ce = cudaMemcpyAsync(PA, a.Pi + 3 * t.sA, sizeof(PA), cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess && okB) ce = cudaMemcpyAsync(PB, a.Pi + 3 * t.sB, sizeof(PB), cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            if (ce != cudaSuccess) return (int)ce;
+            auto dist = [&](const float *q) { double s2 = 0; for (int k = 0; k < 3; ++k) s2 += ((double)q[k] - P0[k]) * ((double)q[k] - P0[k]); return sqrt(s2); };
+            if (okA) dA = dist(PA);
+            if (okB) dB = dist(PB);
+            if (!(dA > 0) || !(dB > 0) || !(dA == dA) || !(dB == dB)) dA = dB = 1.0;
+            if (!okA) dA = dB * 1e3;   // degenerate axis: make the tile as thin as possible along it
+            if (!okB) dB = dA * 1e3;
+            double best = 1e300;
+            for (uint32_t l = 1; l <= 32; l <<= 1)
+                for (uint32_t w = 1; w <= (uint32_t)kCW; w <<= 1) {
+                    const uint32_t ta_ = l * w, tb_ = kTilePix / ta_;
+                    const double tile = dA * ta_ + dB * tb_, warpspan = dA * l + dB * (2.0 * (32 / l));
+                    // prefer the measured-best isotropic shape on ties (32 x 16, patch 8): tiny bias
+                    const double cost = tile + 0.25 * warpspan + ((ta_ == 32 && l == (uint32_t)QUPS_LPA) ? -1e-9 * tile : 0.0);
+                    if (cost < best) { best = cost; tA = ta_; lpa = l; span_m = tile; }
+                }
+            if (!okA || !okB || dA == 1.0) span_m = 0.0; // unknown spacing: keep the default ring
+            sc = {a.Pi, a.I1, a.I2, a.I3, lane_axis, tA, lpa, span_m};
+        }
+        if (const char *e = getenv("QUPS_B200_TILE")) { // "tA,lpa" override for experiments
+            int v1 = 0, v2 = 0;
+            if (sscanf(e, "%d,%d", &v1, &v2) == 2 && v2 >= 1 && v2 <= 32 && (v2 & (v2 - 1)) == 0 && v1 >= v2 && v1 / v2 <= kCW &&
+                v1 % v2 == 0 && ((v1 / v2) & (v1 / v2 - 1)) == 0) { tA = (uint32_t)v1; lpa = (uint32_t)v2; }
+        }
+        t.tA = tA; t.lpa = lpa; t.tB = kTilePix / tA;
+    }
+    t.tilesA = (t.IA + t.tA - 1) / t.tA;
+    t.tilesB = (t.IB + t.tB - 1) / t.tB;
     // closed-form apodization: 1 = transmit weights only, 2 = receive weights (shared-memory table) [+ transmit weights]
     const int fused = !a.fused ? 0 : (a.fa.rx_kind != AP_RX_NONE ? 2 : (a.fa.tx_kind != AP_TX_NONE ? 1 : 0));
     t.fa = a.fa;
     t.I3 = (uint32_t)a.I3;
-    uint32_t wmax = QUPS_WMAX;
+    // ---- ring geometry: slot length (samples) x depth.  The window one tile needs is at most ~ 2 fs/c x its spatial extent;
+    // fine grids take 4 slots of 128 samples, coarse grids trade depth for length (2 x 256, or 2 x 512 at one CTA per SM)
+    uint32_t wmax = QUPS_WMAX, stages = kStages;
+    {
+        float cinv_h = 0.f;
+        static thread_local const void *c_ptr = nullptr;
+        static thread_local float c_val = 0.f;
+        if (span_m > 0.0) {
+            if (c_ptr == a.cinv && c_val > 0.f) cinv_h = c_val;
+            else if (cudaMemcpyAsync(&cinv_h, a.cinv, sizeof(float), cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) { c_ptr = a.cinv; c_val = cinv_h; }
+        }
+        // upper bound of the window: every pixel step changes the round-trip path by at most twice its length
+        const double west = (cinv_h > 0.f) ? 2.0 * (double)a.fs * cinv_h * span_m + 8.0 : 0.0;
+        if (west > 256) { wmax = 512; stages = 2; }
+        else if (west > 170) { wmax = 256; stages = 2; }
+        else if (west > 128) { wmax = 170; stages = 3; }
+    }
     if (const char *e = getenv("QUPS_B200_WMAX")) { int v = atoi(e); if (v >= 8 && v <= 1024) wmax = (uint32_t)(v & ~1); }
-    while (wmax > 16 && tiled_smem_bytes(t.N, t.M, wmax, fused) > 200 * 1024 / QUPS_MINBLOCKS) wmax -= 16;
+    if (const char *e = getenv("QUPS_B200_STAGES")) { int v = atoi(e); if (v >= 2 && v <= kStages) stages = (uint32_t)v; }
+    wmax &= ~1u;
+    const size_t budget = (wmax > 256 ? 200 * 1024 : 200 * 1024 / QUPS_MINBLOCKS);
+    while (wmax > 16 && tiled_smem_bytes(t.N, t.M, wmax, fused, stages) > budget) wmax -= 16;
     t.wmax = wmax;
-    const size_t smem = tiled_smem_bytes(t.N, t.M, wmax, fused);
+    t.stages = stages;
+    const size_t smem = tiled_smem_bytes(t.N, t.M, wmax, fused, stages);
     const uint64_t tiles = (uint64_t)t.tilesA * t.tilesB * t.IC;
     if (tiles == 0 || tiles > 0x7fffffffull) return (int)cudaErrorInvalidValue;
 
@@ -905,6 +972,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
         unsigned long long h[8] = {0};
         cudaStreamSynchronize(st);
         cudaMemcpyFromSymbol(h, g_stats, sizeof(h));
+        fprintf(stderr, "[das_tiled stats] tile %u x %u lpa %u wmax %u stages %u nsplit %u grid %llu\n", t.tA, t.tB, t.lpa, t.wmax, t.stages, t.nsplit, (unsigned long long)(tiles * nsplit));
         fprintf(stderr, "[das_tiled stats] traces FAST %llu SKIP %llu SLOW %llu EDGE %llu split %llu | stages all-fast %llu general %llu\n",
                 h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
         unsigned long long z[8] = {0};
