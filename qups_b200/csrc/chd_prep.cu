@@ -30,12 +30,15 @@ namespace qups {
 void count_launch(uint64_t n);
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// in-place radix-2 FFT of s[0..n) in shared memory, all threads of the CTA; tw[j] = exp(-2*pi*i*j/n), j < n/2
-// (built once per CTA by fft_twiddles); inverse = conjugate twiddles (unscaled)
+// in-place radix-2 FFT of s[0..n) in shared memory, all threads of the CTA.  Twiddles: one contiguous table PER STAGE,
+// tw[half - 1 + k] = exp(-i*pi*k/half) for half = 1, 2, 4 .. n/2 (n - 1 entries, built once per CTA): a single table of
+// exp(-2*pi*i*j/n) read at stride n/(2 half) put 16 lanes on one bank in the middle stages (ncu: 63 % of the shared
+// wavefronts were conflicts).  inverse = conjugate twiddles (unscaled)
 __device__ void fft_twiddles(float2 *tw, uint32_t n) {
-    for (uint32_t j = threadIdx.x; j < (n >> 1); j += blockDim.x) {
+    for (uint32_t j = threadIdx.x; j + 1 < n; j += blockDim.x) {
+        const uint32_t half = 1u << (31 - __clz(j + 1)), k = j + 1 - half;
         float sn, cs;
-        sincospif(-2.0f * (float)j / (float)n, &sn, &cs); // exact dyadic argument
+        sincospif(-(float)k / (float)half, &sn, &cs); // exact dyadic argument
         tw[j] = make_float2(cs, sn);
     }
     __syncthreads();
@@ -48,11 +51,12 @@ __device__ void fft_pow2(float2 *s, const float2 *tw, uint32_t n, uint32_t log2n
     }
     __syncthreads();
     for (uint32_t st = 1; st <= log2n; ++st) {
-        const uint32_t half = 1u << (st - 1), tshift = log2n - st;
+        const uint32_t half = 1u << (st - 1);
+        const float2 *tws = tw + (half - 1);
         for (uint32_t b = tid; b < (n >> 1); b += nt) {
             const uint32_t k = b & (half - 1);
             const uint32_t i0 = ((b >> (st - 1)) << st) + k, i1 = i0 + half;
-            float2 w = tw[k << tshift]; // exp(-i*pi*k/half)
+            float2 w = tws[k];
             if (inverse) w.y = -w.y;
             const float2 a = s[i0], t = cmulf(s[i1], w);
             s[i0] = make_float2(a.x + t.x, a.y + t.y);
@@ -100,8 +104,8 @@ __device__ void dft_bluestein(float2 *s, const float2 *tw, const float2 *cb, con
 __global__ void __launch_bounds__(1024) chd_prep_kernel(const PrepArgs a) {
     extern __shared__ __align__(16) unsigned char prep_smem[];
     float2 *s = reinterpret_cast<float2 *>(prep_smem);
-    float2 *tw = s + (a.hilbert ? a.nfft : 0);        // twiddles exp(-2*pi*i*j/nfft), j < nfft/2
-    float2 *cb = tw + (a.nfft >> 1);                  // Bluestein: FFT of the wrapped conjugate chirp (nfft)
+    float2 *tw = s + (a.hilbert ? a.nfft : 0);        // per-stage twiddle tables, nfft - 1 (+1 pad) entries
+    float2 *cb = tw + a.nfft;                         // Bluestein: FFT of the wrapped conjugate chirp (nfft)
     float2 *ch = cb + a.nfft;                         // Bluestein: chirp c[n], n < L
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint64_t L = a.L;
@@ -197,8 +201,8 @@ int launch_chd_prep(PrepArgs a, cudaStream_t st) {
         const uint64_t need = pow2 ? a.L : 2 * a.L - 1;
         while (n < need) { n <<= 1; ++lg; if (lg > 20) return -1000; }
         a.nfft = n; a.log2n = lg; a.bluestein = !pow2;
-        smem = sizeof(float2) * ((size_t)n + n / 2 + (a.bluestein ? (size_t)n + a.L : 0));
-        if (smem > 200 * 1024) return -1000;
+        smem = sizeof(float2) * ((size_t)n + n + (a.bluestein ? (size_t)n + a.L : 0));
+        if (smem > 227 * 1024) return -1000;
     }
     cudaError_t e = cudaFuncSetAttribute(chd_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024));
     if (e != cudaSuccess) return (int)e;
@@ -210,7 +214,7 @@ int launch_chd_prep(PrepArgs a, cudaStream_t st) {
     unsigned threads = 256;
     uint64_t grid = a.K;
     if (a.hilbert) {
-        int per_sm = (int)((200 * 1024) / smem);
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
         if (per_sm > 8) per_sm = 8;
         if (per_sm < 1) per_sm = 1;
         threads = per_sm >= 4 ? 256 : (per_sm >= 2 ? 512 : 1024);
