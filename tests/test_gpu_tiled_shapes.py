@@ -1,0 +1,81 @@
+"""GPU parity of the staged DAS kernel across its run-time geometry choices (tile shape, lane patch, ring depth / slot
+length — csrc/das_tiled.cu picks them from the pixel spacing) and on the grids that exercise them: anisotropic / coarse
+pixel grids, volumes, focal-plane sign flips (dual-cluster windows), per-transmit t0.  Oracle = CPU restatement of
+kern/das_spec.m:393-482; nearest is bit-exact (integer data), linear / cubic <= 1e-5 relative L-inf."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import small_problem, oracle_kwargs, rel_linf
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def _tiled(P, interp, **env):
+    import qups_b200
+    from qups_b200 import _lib
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        out = qups_b200.das_spec("DAS", P["Pi"].astype(f32), P["Pr"].astype(f32), P["Pv"].astype(f32), P["Nv"].astype(f32), P["x"],
+                                 P["t0"], P["fs"], P["c"], *P["opts"], "interp", interp, _path=_lib.PATH_TILED)
+    finally:
+        for k, v in old.items():
+            if v is None: os.environ.pop(k, None)
+            else: os.environ[k] = v
+    assert qups_b200.last_das_kernel() == "das_tiled"
+    return out
+
+
+def _oracle(oracle_c, P, interp):
+    return oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp=interp,
+                             **oracle_kwargs(P["opts"]))[..., 0]
+
+
+@pytest.mark.parametrize("tile", ["32,8", "8,2", "256,32", "1,1", "16,4", "64,8", "4,4"])
+@pytest.mark.parametrize("kind", ["FC", "PW"])
+def test_forced_tile_shapes(oracle_c, tile, kind):
+    P = small_problem(kind, nz=83, nx=71, N=20, M=6, T=420, zlim=(2e-3, 15e-3))
+    ref = _oracle(oracle_c, P, "cubic")
+    got = _tiled(P, "cubic", QUPS_B200_TILE=tile)
+    assert rel_linf(got, ref) < 1e-5
+    Pn = small_problem(kind, nz=83, nx=71, N=20, M=6, T=420, zlim=(2e-3, 15e-3), int_data=True)
+    assert np.array_equal(_tiled(Pn, "nearest", QUPS_B200_TILE=tile), _oracle(oracle_c, Pn, "nearest"))
+
+
+@pytest.mark.parametrize("ring", [(2, 256), (3, 170), (4, 128), (2, 64), (4, 32), (2, 512)])
+def test_forced_ring_geometry(oracle_c, ring):
+    """Short slots push traces onto the EDGE / SLOW / dual-window paths; long ones onto one CTA per SM."""
+    P = small_problem("FC", nz=90, nx=64, N=18, M=7, T=500, zlim=(2e-3, 16e-3), t0=np.linspace(-3e-7, 4e-7, 7))
+    ref = _oracle(oracle_c, P, "cubic")
+    got = _tiled(P, "cubic", QUPS_B200_STAGES=ring[0], QUPS_B200_WMAX=ring[1])
+    assert rel_linf(got, ref) < 1e-5
+    for interp in ("linear", "nearest"):
+        assert rel_linf(_tiled(P, interp, QUPS_B200_STAGES=ring[0], QUPS_B200_WMAX=ring[1]), _oracle(oracle_c, P, interp)) < 1e-5
+
+
+@pytest.mark.parametrize("aniso", [(8.0, 1.0), (1.0, 6.0), (16.0, 1.0)])
+def test_anisotropic_grids_pick_their_own_shape(oracle_c, aniso):
+    """Coarse lateral (or axial) sampling: the automatic tile / ring choice must stay exact (it only affects speed)."""
+    from qups_b200 import synth
+    dz = 1540.0 / 20e6 / 4
+    nx, nz = 48, 96
+    xs = (np.arange(nx) - nx / 2) * dz * aniso[0]
+    zs = 2e-3 + np.arange(nz) * dz * aniso[1]
+    P = small_problem("FC", N=16, M=5, T=900)
+    P["Pi"] = synth.scan_cartesian(xs, zs)
+    ref = _oracle(oracle_c, P, "cubic")
+    assert np.any(ref != 0)
+    assert rel_linf(_tiled(P, "cubic"), ref) < 1e-5
+
+
+def test_volume_and_focal_plane_inside_every_tile(oracle_c):
+    """3-D grid (slices along I3) with the foci in the middle of the depth range: dv flips sign inside the tiles."""
+    P = small_problem("FC", nz=40, nx=36, ny=3, N=12, M=5, T=300, zlim=(3e-3, 7e-3))
+    ref = _oracle(oracle_c, P, "cubic")
+    assert rel_linf(_tiled(P, "cubic"), ref) < 1e-5
+    assert rel_linf(_tiled(P, "cubic", QUPS_B200_WMAX=48, QUPS_B200_STAGES=4), ref) < 1e-5  # forces split windows
+    Pn = small_problem("FC", nz=40, nx=36, ny=3, N=12, M=5, T=300, zlim=(3e-3, 7e-3), int_data=True)
+    assert np.array_equal(_tiled(Pn, "nearest", QUPS_B200_WMAX=48), _oracle(oracle_c, Pn, "nearest"))
