@@ -190,6 +190,25 @@ typedef struct {
 } qups_prep_params;
 QUPS_API int qups_chd_prep(const qups_prep_params *p, void *out, const void *in, const void *t0, qups_stream_t stream);
 
+/* ---- aperture-domain post-processing -------------------------------- */
+/* One-pass reductions along the aperture dimension of a beamformed cube (DAS 'keep_rx' output), viewed as
+ * C x A x S complex (A = the reduced dimension `dim`, C / S = product of the dimensions before / after it):
+ *   COHFAC         kern/cohfac.m   out real  C x S :  |sum b|^2 / sum |b|^2 / A
+ *   DMAS           kern/dmas.m     out cplx  C x S :  exp(1j angle(z)) sqrt(|z|), z = sum_{lag} sum_n b(n) b(n+lag)
+ *   PCF            kern/pcf.m      out real  C x S (weights w), out2 real C x S (sf, may be NULL); gamma
+ *   SLSC_AVERAGE / SLSC_ENSEMBLE   kern/slsc.m (kdim singleton)   out cplx C x S
+ * lags: HOST array of nlags lag values (dmas: only 1..A-1 are used; slsc: L = nlags normalises the average). */
+typedef enum { QUPS_APD_COHFAC = 0, QUPS_APD_DMAS = 1, QUPS_APD_PCF = 2, QUPS_APD_SLSC_AVERAGE = 3, QUPS_APD_SLSC_ENSEMBLE = 4 } qups_aperture_op;
+typedef struct {
+    uint32_t struct_size;
+    int32_t dtype; /* QUPS_F32 | QUPS_F64 */
+    int32_t op;    /* qups_aperture_op */
+    uint32_t nlags;
+    uint64_t C, A, S;
+    double gamma;
+} qups_aperture_params;
+QUPS_API int qups_aperture(const qups_aperture_params *p, void *out, void *out2, const void *b, const uint32_t *lags, qups_stream_t stream);
+
 /* ---- wsinterpd / wsinterpd2 ------------------------------------------ */
 /* y(l) = sum over dims with ystride==0 of  exp(1i*omega*t) * w(k) * interp1(x(:,v), 1+t, interp, 0),  t = t1(r)+t2(u)
  * Image of the reference argument list (src/interpd.cu:344-349): D broadcast dims of size sizes[d]; dstride is

@@ -19,7 +19,7 @@ INTERP = {"nearest": NEAREST, "linear": LINEAR, "cubic": CUBIC, "lanczos3": LANC
 
 EXPORTS = (
     "qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
-    "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_greens", "qups_convd", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
+    "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_greens", "qups_convd", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
 )
 
 
@@ -95,6 +95,16 @@ class PrepParams(C.Structure):
 
 
 IN_REAL_F32, IN_CPLX_F32, IN_REAL_I16, IN_REAL_F64 = range(4)
+
+
+class ApertureParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("dtype", C.c_int32), ("op", C.c_int32), ("nlags", C.c_uint32),
+        ("C", C.c_uint64), ("A", C.c_uint64), ("S", C.c_uint64), ("gamma", C.c_double),
+    ]
+
+
+APD_COHFAC, APD_DMAS, APD_PCF, APD_SLSC_AVERAGE, APD_SLSC_ENSEMBLE = range(5)
 AP_RX_NONE, AP_RX_ACCEPTANCE_ANGLE, AP_RX_COSINE_ANGLE, AP_RX_APERTURE_GROWTH, AP_RX_TRANSLATING = range(5)
 AP_TX_NONE, AP_TX_SCANLINE, AP_TX_TRANSLATING, AP_TX_PARALLELOGRAM = range(4)
 
@@ -117,6 +127,7 @@ def lib() -> C.CDLL:
     L.qups_apod_generate.argtypes = [C.POINTER(ApodFused), C.c_int32, vp, C.c_int32, vp, vp, C.c_uint64, C.c_uint64,
                                      C.c_uint64, C.c_uint64, vp]
     L.qups_chd_prep.argtypes = [C.POINTER(PrepParams), vp, vp, vp, vp]
+    L.qups_aperture.argtypes = [C.POINTER(ApertureParams), vp, vp, vp, C.POINTER(C.c_uint32), vp]
     L.qups_delays.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, u64p, vp]
     L.qups_das_host.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, u64p, vp,
                                 C.c_int]
@@ -127,7 +138,7 @@ def lib() -> C.CDLL:
     L.qups_greens.argtypes = [C.POINTER(GreensParams), vp, vp, vp, vp, vp, vp, vp]
     L.qups_convd.argtypes = [C.POINTER(ConvdParams), vp, vp, vp, vp]
     L.qups_convd.restype = C.c_int
-    for f in ("qups_das", "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
+    for f in ("qups_das", "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
               "qups_greens", "qups_version"):
         getattr(L, f).restype = C.c_int
     L.qups_last_error.restype = C.c_char_p

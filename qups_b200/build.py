@@ -30,6 +30,7 @@ UNITS = {
     "convd.cu": ["-fmad=false"],
     "apod_gen.cu": ["-fmad=false"],
     "chd_prep.cu": [],
+    "aperture.cu": [],
     "das_tiled.cu": [],
     "qups_b200.cu": [],
 }

@@ -28,4 +28,7 @@ struct PrepArgs {
 
 // returns 0, a cudaError_t (> 0) or -1000 (hilbert length not supported)
 int launch_chd_prep(PrepArgs a, cudaStream_t st);
+
+// aperture-domain post-processing (aperture.cu); lags is a HOST array of p.nlags entries
+int launch_aperture(const qups_aperture_params &p, void *out, void *out2, const void *b, const uint32_t *lags, cudaStream_t st);
 } // namespace qups

@@ -363,6 +363,22 @@ int qups_chd_prep(const qups_prep_params *p, void *out, const void *in, const vo
     return 0;
 }
 
+int qups_aperture(const qups_aperture_params *p, void *out, void *out2, const void *b, const uint32_t *lags, qups_stream_t stream) {
+    g_err[0] = 0;
+    if (!p) return fail(QUPS_ERR_INVALID, "params is NULL");
+    if (p->struct_size != sizeof(qups_aperture_params)) return fail(QUPS_ERR_INVALID, "params.struct_size mismatch");
+    if (p->dtype != QUPS_F32 && p->dtype != QUPS_F64) return fail(QUPS_ERR_INVALID, "dtype must be F32 or F64");
+    if (p->op < QUPS_APD_COHFAC || p->op > QUPS_APD_SLSC_ENSEMBLE) return fail(QUPS_ERR_INVALID, "unknown aperture op %d", p->op);
+    if (p->C * p->S == 0) return 0;
+    if (!out || (!b && p->A)) return fail(QUPS_ERR_INVALID, "NULL array argument");
+    const bool need_lags = p->op == QUPS_APD_DMAS || p->op == QUPS_APD_SLSC_AVERAGE || p->op == QUPS_APD_SLSC_ENSEMBLE;
+    if (need_lags && p->nlags && !lags) return fail(QUPS_ERR_INVALID, "lags is NULL");
+    const int e = launch_aperture(*p, out, out2, b, lags, (cudaStream_t)stream);
+    if (e == -4) return fail(QUPS_ERR_ALLOC, "host allocation failed");
+    if (e) return cuda_fail(e, "aperture kernel");
+    return 0;
+}
+
 int qups_delays(const qups_das_params *p, void *tau, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
                 const void *cinv, const uint64_t *cstride, qups_stream_t stream) {
     g_err[0] = 0;

@@ -466,3 +466,68 @@ def convd(x, y=None, dim=None, shape="full"):
     lag_shape[d0] = -1
     lags = lags.reshape(lag_shape)
     return (np.asfortranarray(out.cpu().numpy()) if numpy_out else out), lags
+
+
+# ---- aperture-domain post-processing (kern/cohfac.m, kern/dmas.m, kern/pcf.m, kern/slsc.m) ---------------------------
+def _aperture(op, b, dim, lags=(), gamma=1.0, two=False):
+    bt = _as_tensor(b)
+    numpy_out = not (isinstance(b, torch.Tensor) and b.is_cuda)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dbl = bt.dtype in (torch.float64, torch.complex128)
+    ct, rt = (torch.complex128, torch.float64) if dbl else (torch.complex64, torch.float32)
+    nd = max(bt.ndim, dim)
+    sz = _sz(bt, nd)
+    d0 = dim - 1
+    Cn, A, Sn = int(np.prod(sz[:d0])) if d0 else 1, sz[d0], int(np.prod(sz[d0 + 1:])) if d0 + 1 < nd else 1
+    dB = _colmajor(bt.reshape(sz).to(ct), ct, dev)
+    cplx_out = op in (_lib.APD_DMAS, _lib.APD_SLSC_AVERAGE, _lib.APD_SLSC_ENSEMBLE)
+    out = torch.empty(Cn * Sn, dtype=ct if cplx_out else rt, device=dev)
+    out2 = torch.empty(Cn * Sn, dtype=rt, device=dev) if two else None
+    p = _lib.ApertureParams()
+    p.struct_size = C.sizeof(_lib.ApertureParams)
+    p.dtype, p.op, p.nlags = (_lib.F64 if dbl else _lib.F32), op, len(lags)
+    p.C, p.A, p.S, p.gamma = Cn, A, Sn, float(gamma)
+    lg = (C.c_uint32 * max(1, len(lags)))(*[int(v) for v in lags])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().qups_aperture(C.byref(p), _ptr(out), _ptr(out2), _ptr(dB), lg, _stream(dev)))
+    osz = tuple(sz[:d0]) + (1,) + tuple(sz[d0 + 1:])
+    cv = lambda t: (np.asfortranarray(_from_colmajor(t, osz).cpu().numpy()) if numpy_out else _from_colmajor(t, osz))
+    return (cv(out), cv(out2)) if two else cv(out)
+
+
+def _last_nonsingleton(x):
+    sh = tuple(np.shape(x)) if not isinstance(x, torch.Tensor) else tuple(x.shape)
+    nz = [d + 1 for d, s in enumerate(sh) if s != 1]
+    return nz[-1] if nz else 1
+
+
+def cohfac(b, dim=None):
+    """r = |sum(b,dim)|^2 ./ sum(|b|^2,dim) / size(b,dim) — mirror of ``kern/cohfac.m``."""
+    return _aperture(_lib.APD_COHFAC, b, _last_nonsingleton(b) if dim is None else int(dim))
+
+
+def dmas(bn, dim=None, L=None):
+    """Delay-multiply-and-sum across the aperture — mirror of ``kern/dmas.m`` (scalar L -> lags 1:L)."""
+    dim = _last_nonsingleton(bn) if dim is None else int(dim)
+    N = (tuple(bn.shape) + (1,) * dim)[dim - 1]
+    lags = range(1, N) if L is None else (range(1, int(L) + 1) if np.ndim(L) == 0 else [int(v) for v in np.ravel(L)])
+    return _aperture(_lib.APD_DMAS, bn, dim, [v for v in lags if 1 <= v < N])
+
+
+def pcf(b, dim=None, gamma=1.0):
+    """Phase coherence factor [w, sf] — mirror of ``kern/pcf.m`` (auxiliary unwrap)."""
+    bt = _as_tensor(b)
+    if not bt.is_complex():
+        raise ValueError("Input must be complex.")  # QUPS:pcf:realInput
+    return _aperture(_lib.APD_PCF, b, max(1, _last_nonsingleton(b)) if dim is None else int(dim), gamma=gamma, two=True)
+
+
+def slsc(x, dim=None, L=None, method="average"):
+    """Short-lag spatial coherence — mirror of ``kern/slsc.m`` with a singleton time-sample dimension (kdim)."""
+    if method not in ("average", "ensemble"):
+        raise ValueError("method must be 'average' or 'ensemble'")
+    dim = _last_nonsingleton(x) if dim is None else int(dim)
+    A = (tuple(x.shape) + (1,) * dim)[dim - 1]
+    L = max(1, A // 4) if L is None else L
+    lags = list(range(1, int(L) + 1)) if np.ndim(L) == 0 else [int(v) for v in np.ravel(L)]
+    return _aperture(_lib.APD_SLSC_AVERAGE if method == "average" else _lib.APD_SLSC_ENSEMBLE, x, dim, lags)
