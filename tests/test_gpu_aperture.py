@@ -15,6 +15,8 @@ def _data(shape, dtype=np.complex64, seed=0):
 def _close(a, b, tol):
     a, b = np.asarray(a), np.asarray(b)
     assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b))  # 0/0 (an all-zero aperture) is NaN in the reference too
+    a, b = np.nan_to_num(a), np.nan_to_num(b)
     assert np.max(np.abs(a - b)) <= tol * max(1.0, np.max(np.abs(b)))
 
 
@@ -67,4 +69,4 @@ def test_coherence_factor_on_beamformed_receive_cube(oracle_c):
     cf = qups_b200.cohfac(bn, 4)
     assert cf.shape == bn.shape[:3] + (1,) + bn.shape[4:]
     _close(cf, ap.cohfac(ref.astype(np.complex128), 4), 2e-5)
-    assert np.all((cf >= 0) & (cf <= 1 + 1e-5))
+    assert np.all((cf >= 0) & (cf <= 1 + 1e-5) | np.isnan(cf))
