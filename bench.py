@@ -352,10 +352,20 @@ def main():
     loc = DasProblem(P.name, Pi_slab, P.Pr, np.zeros((3, M_loc)), np.zeros((3, M_loc)), P.T, P.fs, P.t0, P.c0, P.opts, P.interp)
     bytes_launch = loc.bytes_alg()
     achieved = bytes_launch / (float(tmax[1]) * 1e-3) / 1e9
-    traffic = None
+    traffic, smem = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(kern_name)
+            tj = json.load(f)
+        traffic = tj.get(kern_name)
+        # what actually bounds the kernel: shared-memory wavefronts per launch from the committed ncu capture,
+        # scaled to this rank's share of the pixels, over the live kernel time, against 1 wavefront / clk / SM
+        wf = tj.get(kern_name + "_smem_wavefronts")
+        if wf and clocks and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            rate = wf * (I_loc / P.I) / (float(tmax[1]) * 1e-3)
+            smem = {"bound": "shared-memory", "achieved": rate * 128 / 1e12, "peak": sms * clocks["sm_mhz"] * 1e6 * 128 / 1e12,
+                    "unit": "TB/s", "frac": rate / (sms * clocks["sm_mhz"] * 1e6),
+                    "source": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum of the ncu capture (profiles/), live kernel time"}
     except Exception:
         pass
     line = {
@@ -364,7 +374,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": kern_name, "kernel_ms": float(tmax[1]),
-                     "bytes_per_launch": bytes_launch, "peak_source": peak_src,
+                     "bytes_per_launch": bytes_launch, "peak_source": peak_src, "limiter": smem,
                      "note": "algorithmic (no-reuse gather) bytes per SURVEY.md §8d; neighbouring pixels share "
                              "samples so this legitimately exceeds 1 — the kernel is issue/LDS bound, see DESIGN.md §6"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
