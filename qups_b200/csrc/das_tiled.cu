@@ -367,8 +367,15 @@ __device__ __forceinline__ int tap_window(float xlo, float xhi, float Tf, int T,
 
 // FUSED: 0 = none; 1 = closed-form TRANSMIT weights only (one weight per pixel and stage, folded into the stage sum);
 //        2 = closed-form RECEIVE weights (per-thread table in shared memory, refreshed per receive tile) + optional transmit weights
-template <int INTERP, int NAP, int FUSED>
+// KEEP: 0 = sum both apertures (DAS); 1 = keep the transmit dimension (MUL, y is I x M): every stage (receive tile, m) adds
+//        its sum to y(:,m); 2 = keep the receive dimension (SYN, y is I x N): the ROLES of the apertures are swapped — the 16
+//        traces of a stage are 16 transmits of ONE receive, the registers hold dv(i, m) of a transmit tile and the stage
+//        scalar is dr(i, n) — so every stage adds to y(:,n).  (sample_pos only adds dv + dr: the swap is bit-neutral.)
+//        y is pre-zeroed by the launcher; a CTA owns its pixels (nsplit = 1), so the read-modify-write needs no atomics.
+template <int INTERP, int NAP, int FUSED, int KEEP>
 __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(const TiledArgs a) {
+    constexpr bool kInnerTx = (KEEP == 2); // the 16 traces of a stage run over transmits instead of receives
+    static_assert(KEEP == 0 || (NAP == 0 && FUSED == 0), "kept apertures: plain weights only");
     static_assert(kR == 2, "the packed fp32x2 inner loop assumes two pixel rows per thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [0,64) full/empty mbarriers | stage_hdr[kStages] int4 | desc[kStages][kNT] int4 |
@@ -488,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                 }
             }
         }
-        for (uint32_t n = nt0 * kNT; n < min(nt1 * kNT, a.N); ++n) {
+        for (uint32_t n = kInnerTx ? 0u : nt0 * kNT; n < (kInnerTx ? a.N : min(nt1 * kNT, a.N)); ++n) {
             const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
             int lo = INT_MAX, hi = INT_MIN;
 #pragma unroll
@@ -523,28 +530,55 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             mbar_wait(bar_full + 8 * s, ph);
             const int4 hdr = stage_hdr[s]; // kind, m, nt
             if (hdr.x == ST_END) break;
-            const uint32_t m = (uint32_t)hdr.y, nt = (uint32_t)hdr.z;
-            const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
-            const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
-            if ((int)nt != cur_nt) { // new receive tile: dr(i,n) for its 16 receives goes to registers
+            // hdr.y = outer index of the stage (transmit m; receive n when kInnerTx), hdr.z = inner tile (16 receives; 16 transmits)
+            const uint32_t outer = (uint32_t)hdr.y, nt = (uint32_t)hdr.z;
+            const uint32_t m = kInnerTx ? 0u : outer;
+            float t0m = 0.f;
+            if ((int)nt != cur_nt) { // new inner tile: its 16 path lengths go to registers
                 cur_nt = (int)nt;
 #pragma unroll
                 for (int j = 0; j < kNT; ++j) {
-                    const uint32_t n = min(nt * kNT + j, a.N - 1);
-                    const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
-                    dr[j].x = rx_dist(px[0], py[0], pz[0], rx, ry, rz);
-                    dr[j].y = rx_dist(px[1], py[1], pz[1], rx, ry, rz);
-                    if constexpr (FUSED == 2) { // this thread's receive weights for the tile: its own table column
-                        const float w0 = ap_rx_weight(a.fa, px[0], py[0], pz[0], plat[0], a.Pr, n);
-                        const float w1 = ap_rx_weight(a.fa, px[1], py[1], pz[1], plat[1], a.Pr, n);
-                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wtab + (uint32_t)(j * kCW * 32 + tid) * 8u), "f"(w0), "f"(w1) : "memory");
+                    if constexpr (kInnerTx) {
+                        const uint32_t mj = min(nt * kNT + j, a.M - 1);
+                        const float4 pvj = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + mj);
+                        const float nxj = __ldg(a.Nv + 3 * mj), nyj = __ldg(a.Nv + 3 * mj + 1), nzj = __ldg(a.Nv + 3 * mj + 2);
+                        dr[j].x = tx_dist(px[0], py[0], pz[0], pvj.x, pvj.y, pvj.z, nxj, nyj, nzj, VS, DV);
+                        dr[j].y = tx_dist(px[1], py[1], pz[1], pvj.x, pvj.y, pvj.z, nxj, nyj, nzj, VS, DV);
+                    } else {
+                        const uint32_t n = min(nt * kNT + j, a.N - 1);
+                        const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
+                        dr[j].x = rx_dist(px[0], py[0], pz[0], rx, ry, rz);
+                        dr[j].y = rx_dist(px[1], py[1], pz[1], rx, ry, rz);
+                        if constexpr (FUSED == 2) { // this thread's receive weights for the tile: its own table column
+                            const float w0 = ap_rx_weight(a.fa, px[0], py[0], pz[0], plat[0], a.Pr, n);
+                            const float w1 = ap_rx_weight(a.fa, px[1], py[1], pz[1], plat[1], a.Pr, n);
+                            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wtab + (uint32_t)(j * kCW * 32 + tid) * 8u), "f"(w0), "f"(w1) : "memory");
+                        }
                     }
                 }
             }
-            pk.dv.x = tx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
-            pk.dv.y = tx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
-            const float t0m = pv.w;
+            if constexpr (kInnerTx) { // stage scalar = receive path length; t0 is per trace (fetched in the loop, warp-uniform)
+                const float rx = __ldg(a.Pr + 3 * outer), ry = __ldg(a.Pr + 3 * outer + 1), rz = __ldg(a.Pr + 3 * outer + 2);
+                pk.dv.x = rx_dist(px[0], py[0], pz[0], rx, ry, rz);
+                pk.dv.y = rx_dist(px[1], py[1], pz[1], rx, ry, rz);
+            } else {
+                const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
+                const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
+                pk.dv.x = tx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+                pk.dv.y = tx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+                t0m = pv.w;
+            }
             pk.t0 = t0m;
+            // kept aperture: fetch the output element early so the read-modify-write at the end of the stage is latency-free
+            float2 yold0 = make_float2(0.f, 0.f), yold1 = make_float2(0.f, 0.f);
+            if constexpr (KEEP != 0) {
+                if (valid[0]) yold0 = a.y[pix[0] + (uint64_t)outer * a.I];
+                if (valid[1]) yold1 = a.y[pix[1] + (uint64_t)outer * a.I];
+            }
+            auto t0_of = [&](int j) -> float { // start time of trace j of this stage
+                if constexpr (kInnerTx) return __ldg(a.Pv4 + 4 * min(nt * kNT + (uint32_t)j, a.M - 1) + 3);
+                else return t0m;
+            };
             const int4 *dsc = desc + s * kNT; // .x = slot offset of the dv < 0 cluster, .y = flag, .z = offset of the dv >= 0 cluster
             // two-level accumulation: the 16 x 4 taps of a stage are summed into stage-local accumulators first
             // (pairwise-style error growth: sqrt(64) + sqrt(#stages) instead of sqrt(#terms))
@@ -583,6 +617,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
 #pragma unroll
                 for (int j = 0; j < kNT; ++j) {
                     const uint32_t so = (uint32_t)dsc[j].x;
+                    if constexpr (kInnerTx) pk.t0 = t0_of(j);
                     if constexpr (!kWeighted) {
                         fast_pair2<INTERP>(pk, dr[j], so, so, sa0, sa1);
                     } else { // a .* interp1(...): sample into temporaries, then one weighted accumulate per pixel
@@ -597,7 +632,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                 // general stage: one CTA-uniform branch per trace (SKIP / FAST / rare); each pixel picks the window of
                 // its own dv cluster.  Kept ROLLED (dr read through a local-memory copy): unrolling it a second time
                 // next to the all-fast body overflows the instruction cache (measured: no_instruction stalls 0.15 -> 1.05)
-                const bool neg0 = pk.dv.x < 0.f, neg1 = pk.dv.y < 0.f;
+                bool neg0 = pk.dv.x < 0.f, neg1 = pk.dv.y < 0.f; // dv cluster of the two pixels (per trace when kInnerTx)
                 float2 drl[kNT];
 #pragma unroll
                 for (int j = 0; j < kNT; ++j) drl[j] = dr[j];
@@ -606,15 +641,17 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                     const int4 d = dsc[j];
                     if (d.y == TR_SKIP) continue;
                     const float2 drj = drl[j];
+                    float t0j = t0m;
+                    if constexpr (kInnerTx) { neg0 = drj.x < 0.f; neg1 = drj.y < 0.f; t0j = t0_of(j); pk.t0 = t0j; }
                     const uint32_t so0 = (uint32_t)(neg0 ? d.x : d.z), so1 = (uint32_t)(neg1 ? d.x : d.z);
                     float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
                     if (d.y == TR_FAST) {
                         fast_pair2<INTERP>(pk, drj, so0, so1, t0, t1);
                     } else {
-                        const uint32_t n = nt * kNT + j;
-                        const uint64_t nm = a.tpose ? ((uint64_t)m + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)m * a.N);
-                        const float xq0 = sample_pos(pk.dv.x, drj.x, cinv, t0m, fs);
-                        const float xq1 = sample_pos(pk.dv.y, drj.y, cinv, t0m, fs);
+                        const uint32_t n = kInnerTx ? outer : nt * kNT + j, mm = kInnerTx ? nt * kNT + j : outer;
+                        const uint64_t nm = a.tpose ? ((uint64_t)mm + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)mm * a.N);
+                        const float xq0 = sample_pos(pk.dv.x, drj.x, cinv, t0j, fs);
+                        const float xq1 = sample_pos(pk.dv.y, drj.y, cinv, t0j, fs);
                         // an EDGE trace crosses the end of the data somewhere in the TILE; most warps of the tile are
                         // still entirely interior (-> packed fast path) or entirely outside (-> contribute 0)
                         const bool in2 = interior<INTERP>(xq0, Tf) && interior<INTERP>(xq1, Tf);
@@ -637,7 +674,10 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                 }
             }
             } // live
-            if constexpr (FUSED != 0) { // the transmit weight is constant over the stage: one multiply per pixel
+            if constexpr (KEEP != 0) { // y(:, outer) += stage sum; this CTA is the only writer of its pixels
+                if (valid[0]) a.y[pix[0] + (uint64_t)outer * a.I] = make_float2(yold0.x + sa0.x, yold0.y + sa0.y);
+                if (valid[1]) a.y[pix[1] + (uint64_t)outer * a.I] = make_float2(yold1.x + sa1.x, yold1.y + sa1.y);
+            } else if constexpr (FUSED != 0) { // the transmit weight is constant over the stage: one multiply per pixel
                 acc0.x = fmaf(wt0, sa0.x, acc0.x); acc0.y = fmaf(wt0, sa0.y, acc0.y);
                 acc1.x = fmaf(wt1, sa1.x, acc1.x); acc1.y = fmaf(wt1, sa1.y, acc1.y);
             } else {
@@ -646,7 +686,9 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         }
-        if (a.nsplit > 1) { // partial image of this receive range; das_reduce_kernel sums the splits in order
+        if constexpr (KEEP != 0) {
+            // nothing left to write: every stage updated y in place
+        } else if (a.nsplit > 1) { // partial image of this receive range; das_reduce_kernel sums the splits in order
             if (valid[0]) a.part[(uint64_t)split * a.I + pix[0]] = acc0;
             if (valid[1]) a.part[(uint64_t)split * a.I + pix[1]] = acc1;
         } else {
@@ -663,28 +705,47 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
         const bool cinv_ok = (cinv > 0.f) && (fs > 0.f);
         const int Ti = (int)a.T;
         uint32_t it = 0;
+        // inner tiles: 16 receives (16 transmits when kInnerTx); outer index: transmit m (receive n when kInnerTx)
+        const uint32_t n_inner = kInnerTx ? a.M : a.N, n_outer = kInnerTx ? a.N : a.M;
         for (uint32_t nt = nt0; nt < nt1; ++nt) {
-            const uint32_t n = nt * kNT + lane;
-            const bool has = (lane < kNT) && (n < a.N);
+            const uint32_t il = nt * kNT + lane;
+            const bool has = (lane < kNT) && (il < n_inner);
+            // tile-level bounds of the inner path length (and of t0 when the inner traces are transmits): one conservative
+            // skip test per outer index, 32 outer indices per pass
             int olo = INT_MAX, ohi = INT_MIN;
-            if (has) { olo = s_drmin[n]; ohi = s_drmax[n]; }
-            const float rlo = o2f(olo), rhi = o2f(ohi);
-            // receive-tile bounds of dr: one conservative skip test per transmit, 32 transmits per pass
+            float tlo = 0.f, thi = 0.f;
+            if (has) {
+                if constexpr (kInnerTx) { olo = min(s_dvnmin[il], s_dvpmin[il]); ohi = max(s_dvnmax[il], s_dvpmax[il]); tlo = thi = __ldg(a.Pv4 + 4 * il + 3); }
+                else { olo = s_drmin[il]; ohi = s_drmax[il]; }
+            }
             const float rlo_t = o2f(__reduce_min_sync(0xffffffffu, olo)), rhi_t = o2f(__reduce_max_sync(0xffffffffu, ohi));
-            for (uint32_t m0 = 0; m0 < a.M; m0 += 32) {
+            float t0lo_t = 0.f, t0hi_t = 0.f;
+            if constexpr (kInnerTx) {
+                t0lo_t = o2f(__reduce_min_sync(0xffffffffu, has ? f2o(tlo) : INT_MAX));
+                t0hi_t = o2f(__reduce_max_sync(0xffffffffu, has ? f2o(thi) : INT_MIN));
+            }
+            for (uint32_t m0 = 0; m0 < n_outer; m0 += 32) {
                 const uint32_t ml = m0 + lane;
                 bool skip = true;
-                if (ml < a.M) {
-                    const float t0l = __ldg(a.Pv4 + 4 * ml + 3);
-                    const float xl = sample_pos(o2f(min(s_dvnmin[ml], s_dvpmin[ml])), rlo_t, cinv, t0l, fs);
-                    const float xh = sample_pos(o2f(max(s_dvnmax[ml], s_dvpmax[ml])), rhi_t, cinv, t0l, fs);
+                if (ml < n_outer) {
+                    float xl, xh;
+                    if constexpr (kInnerTx) { // outer = receive ml
+                        xl = sample_pos(rlo_t, o2f(s_drmin[ml]), cinv, t0hi_t, fs);
+                        xh = sample_pos(rhi_t, o2f(s_drmax[ml]), cinv, t0lo_t, fs);
+                    } else {
+                        const float t0l = __ldg(a.Pv4 + 4 * ml + 3);
+                        xl = sample_pos(o2f(min(s_dvnmin[ml], s_dvpmin[ml])), rlo_t, cinv, t0l, fs);
+                        xh = sample_pos(o2f(max(s_dvnmax[ml], s_dvpmax[ml])), rhi_t, cinv, t0l, fs);
+                    }
                     skip = cinv_ok && (xl <= xh) && (xh < 1.0f || xl > Tf);
                     if constexpr (FUSED != 0) skip = skip || (s_txany[ml] == 0); // no pixel of the tile uses this transmit
                 }
                 uint32_t todo = ~__ballot_sync(0xffffffffu, skip);
                 while (todo) {
-                    const uint32_t m = m0 + (uint32_t)(__ffs((int)todo) - 1);
+                    const uint32_t outer = m0 + (uint32_t)(__ffs((int)todo) - 1);
                     todo &= todo - 1;
+                    // this lane's trace: (receive n, transmit m)
+                    const uint32_t m = kInnerTx ? il : outer, n = kInnerTx ? outer : il;
                     const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
                     int flag = TR_SKIP;
                     // up to two windows per trace: [0] single window / dv < 0 cluster, [1] dv >= 0 cluster
@@ -693,6 +754,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                     if (has) {
                         const float t0m = __ldg(a.Pv4 + 4 * m + 3);
                         const int nmin = s_dvnmin[m], nmax = s_dvnmax[m], pmin = s_dvpmin[m], pmax = s_dvpmax[m];
+                        const float rlo = o2f(s_drmin[n]), rhi = o2f(s_drmax[n]); // receive path-length bounds of this trace
                         const float xlo = sample_pos(o2f(min(nmin, pmin)), rlo, cinv, t0m, fs);
                         const float xhi = sample_pos(o2f(max(nmax, pmax)), rhi, cinv, t0m, fs);
                         flag = TR_SLOW;
@@ -761,17 +823,12 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
 #endif
                     mbar_wait(bar_empty + 8 * s, ph ^ 1); // slot free (first lap passes immediately)
                     if (lane < kNT) desc[s * kNT + lane] = make_int4((int)soff[0], flag, (int)soff[1], 0);
-                    if (lane == 0) stage_hdr[s] = make_int4(all_fast ? ST_ALL_FAST : ST_MIXED, (int)m, (int)nt, 0);
+                    if (lane == 0) stage_hdr[s] = make_int4(all_fast ? ST_ALL_FAST : ST_MIXED, (int)outer, (int)nt, 0);
                     __syncwarp();
                     if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * s, total);
                     __syncwarp();
-#if QUPS_EXP == 3
-                    // experiment (timing only, wrong data): the stage's bytes as ONE bulk copy instead of up to 32
-                    if (lane == 0 && total) bulk_g2s(ring + s * kNT * a.wmax * 8u, a.x + (((uint64_t)m * a.N + nt * kNT) * a.T & ~1ull), total, bar_full + 8 * s);
-#else
                     if (bytes[0]) bulk_g2s(dst[0], src[0], bytes[0], bar_full + 8 * s);
                     if (bytes[1]) bulk_g2s(dst[1], src[1], bytes[1], bar_full + 8 * s);
-#endif
                     ++it;
                 }
             }
@@ -811,7 +868,8 @@ static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax, int fused 
 TiledPlan das_tiled_plan(const DasArgs<float> &a, int dtype_in, int dtype_out) {
     TiledPlan p{0, ""};
     if (dtype_in != 0 || dtype_out != 0) { p.why = "tiled path is fp32 only"; return p; }
-    if (a.keep_rx || a.keep_tx) { p.why = "tiled path sums both apertures"; return p; }
+    if (a.keep_rx && a.keep_tx) { p.why = "tiled path keeps at most one aperture"; return p; }
+    if ((a.keep_rx || a.keep_tx) && (a.S > 0 || a.fused)) { p.why = "tiled path: kept apertures take no apodization"; return p; }
     if (a.S > 2 || (a.S > 0 && !a.apod_real)) { p.why = "tiled path takes at most two REAL apodization arrays"; return p; }
     if (a.fused && a.S > 1) { p.why = "tiled path: closed-form apodization combines with at most one apodization array"; return p; }
     for (int q = 0; q < a.S; ++q) { // 32-bit index arithmetic inside the kernel
@@ -841,7 +899,8 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     t.N = (uint32_t)a.N; t.M = (uint32_t)a.M; t.T = (uint32_t)a.T;
     t.fs = a.fs; t.VS = a.VS; t.DV = a.DV; t.tpose = a.tpose; t.accumulate = a.accumulate;
     t.total_elems = a.T * a.N * a.M;
-    t.numNT = (t.N + kNT - 1) / kNT;
+    const int keep = a.keep_tx ? 1 : (a.keep_rx ? 2 : 0);
+    t.numNT = ((keep == 2 ? t.M : t.N) + kNT - 1) / kNT; // inner tiles: receives, or transmits when the receive dimension is kept
     // axis assignment: lanes along I2 (the slow axis of a ZXY ScanCartesian, src/ScanCartesian.m:11) when
     // it is wide enough, rows along I1; overridable for experiments (QUPS_B200_LANE_AXIS=1|2)
     int lane_axis = (a.I2 >= 8) ? 2 : 1;
@@ -935,8 +994,9 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     }
     void (*kern)(const TiledArgs) = nullptr;
     const int ip = a.interp < 0 ? 0 : (a.interp > 2 ? 2 : a.interp);
-#define QUPS_PICK(I_, N_, F_) if (ip == I_ && a.S == N_ && fused == F_) kern = das_tiled_kernel<I_, N_, F_>;
-#define QUPS_PICK_I(I_) QUPS_PICK(I_, 0, 0) QUPS_PICK(I_, 1, 0) QUPS_PICK(I_, 2, 0) QUPS_PICK(I_, 0, 1) QUPS_PICK(I_, 1, 1) QUPS_PICK(I_, 0, 2) QUPS_PICK(I_, 1, 2)
+#define QUPS_PICK(I_, N_, F_, K_) if (ip == I_ && a.S == N_ && fused == F_ && keep == K_) kern = das_tiled_kernel<I_, N_, F_, K_>;
+#define QUPS_PICK_I(I_) QUPS_PICK(I_, 0, 0, 0) QUPS_PICK(I_, 1, 0, 0) QUPS_PICK(I_, 2, 0, 0) QUPS_PICK(I_, 0, 1, 0) QUPS_PICK(I_, 1, 1, 0) \
+                        QUPS_PICK(I_, 0, 2, 0) QUPS_PICK(I_, 1, 2, 0) QUPS_PICK(I_, 0, 0, 1) QUPS_PICK(I_, 0, 0, 2)
     QUPS_PICK_I(0) QUPS_PICK_I(1) QUPS_PICK_I(2)
 #undef QUPS_PICK_I
 #undef QUPS_PICK
@@ -952,8 +1012,10 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     uint32_t nsplit = 1;
     if (tiles < want) nsplit = (uint32_t)((want + tiles - 1) / tiles);
     if (nsplit > t.numNT / 2) nsplit = t.numNT / 2;   // at least two receive tiles per CTA
+    if (keep) nsplit = 1;                             // kept apertures: each CTA is the only writer of its pixels
     if (nsplit < 1) nsplit = 1;
     if (const char *e2 = getenv("QUPS_B200_NSPLIT")) { int v = atoi(e2); if (v >= 1 && (uint32_t)v <= t.numNT) nsplit = (uint32_t)v; }
+    if (keep) nsplit = 1;
     if (tiles * nsplit > 0x7fffffffull) nsplit = 1;
     t.nsplit = nsplit;
     t.rev = 1;
@@ -962,6 +1024,10 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     t.part = nullptr;
     if (nsplit > 1) {
         e = cudaMallocAsync((void **)&t.part, sizeof(float2) * a.I * nsplit, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (keep && !t.accumulate) { // every stage adds into y(:, n | m)
+        e = cudaMemsetAsync(t.y, 0, sizeof(float2) * a.I * (keep == 1 ? a.M : a.N), st);
         if (e != cudaSuccess) return (int)e;
     }
     kern<<<(unsigned)(tiles * nsplit), kThreads, smem, st>>>(t);

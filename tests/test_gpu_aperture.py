@@ -61,8 +61,9 @@ def test_coherence_factor_on_beamformed_receive_cube(oracle_c):
     from tests.util import small_problem, oracle_kwargs
     f32 = np.float32
     P = small_problem("FC", nz=24, nx=20, N=10, M=4, T=200)
+    from qups_b200 import _lib
     bn = qups_b200.das_spec("SYN", P["Pi"].astype(f32), P["Pr"].astype(f32), P["Pv"].astype(f32), P["Nv"].astype(f32), P["x"], P["t0"],
-                            P["fs"], P["c"], *P["opts"], "interp", "cubic")
+                            P["fs"], P["c"], *P["opts"], "interp", "cubic", _path=_lib.PATH_GENERIC)
     ref = oracle_c.das_spec("SYN", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp="cubic",
                             **oracle_kwargs(P["opts"]))[..., 0]
     assert np.array_equal(bn, ref)

@@ -174,9 +174,11 @@ def test_auto_dispatch_and_errors():
     _gpu("DAS", P, "cubic", "auto")
     assert qups_b200.last_das_kernel() == "das_tiled"
     _gpu("SYN", P, "cubic", "auto")
-    assert qups_b200.last_das_kernel() == "das_generic"
+    assert qups_b200.last_das_kernel() == "das_tiled"      # one kept aperture: staged kernel (roles swapped for keep_rx)
+    _gpu("BF", P, "cubic", "auto")
+    assert qups_b200.last_das_kernel() == "das_generic"    # both kept: one output element per pair, nothing to stage for
     with pytest.raises(QupsError):
-        _gpu("SYN", P, "cubic", "tiled")
+        _gpu("BF", P, "cubic", "tiled")
     with pytest.raises(ValueError):
         _gpu("DAS", P, "spline", "auto")
     with pytest.raises(AssertionError):

@@ -79,3 +79,50 @@ def test_volume_and_focal_plane_inside_every_tile(oracle_c):
     assert rel_linf(_tiled(P, "cubic", QUPS_B200_WMAX=48, QUPS_B200_STAGES=4), ref) < 1e-5  # forces split windows
     Pn = small_problem("FC", nz=40, nx=36, ny=3, N=12, M=5, T=300, zlim=(3e-3, 7e-3), int_data=True)
     assert np.array_equal(_tiled(Pn, "nearest", QUPS_B200_WMAX=48), _oracle(oracle_c, Pn, "nearest"))
+
+
+# ---- kept apertures on the staged kernel: MUL (keep_tx) and SYN (keep_rx, roles of the apertures swapped) --------------
+def _tiled_fun(fun, P, interp, **env):
+    import qups_b200
+    from qups_b200 import _lib
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        out = qups_b200.das_spec(fun, P["Pi"].astype(f32), P["Pr"].astype(f32), P["Pv"].astype(f32), P["Nv"].astype(f32), P["x"],
+                                 P["t0"], P["fs"], P["c"], *P["opts"], "interp", interp, _path=_lib.PATH_TILED)
+    finally:
+        for k, v in old.items():
+            if v is None: os.environ.pop(k, None)
+            else: os.environ[k] = v
+    assert qups_b200.last_das_kernel() == "das_tiled"
+    return out
+
+
+@pytest.mark.parametrize("fun", ["SYN", "MUL"])
+@pytest.mark.parametrize("kind", ["FC", "PW", "DV", "FSA"])
+def test_kept_aperture_on_the_staged_kernel(oracle_c, fun, kind):
+    M = 21 if kind != "FSA" else 19
+    P = small_problem(kind, nz=70, nx=45, N=19, M=M, T=400, zlim=(2e-3, 14e-3), t0=np.linspace(-2e-7, 3e-7, M))
+    for interp in ("cubic", "linear"):
+        ref = oracle_c.das_spec(fun, P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp=interp,
+                                **oracle_kwargs(P["opts"]))[..., 0]
+        got = _tiled_fun(fun, P, interp)
+        assert got.shape == ref.shape
+        assert rel_linf(got, ref) < 1e-5, (fun, kind, interp)
+    Pn = small_problem(kind, nz=70, nx=45, N=19, M=M, T=400, zlim=(2e-3, 14e-3), int_data=True)
+    refn = oracle_c.das_spec(fun, Pn["Pi"], Pn["Pr"], Pn["Pv"], Pn["Nv"], Pn["x"], Pn["t0"], Pn["fs"], Pn["c"], interp="nearest",
+                             **oracle_kwargs(Pn["opts"]))[..., 0]
+    assert np.array_equal(_tiled_fun(fun, Pn, "nearest"), refn)
+
+
+@pytest.mark.parametrize("fun", ["SYN", "MUL"])
+def test_kept_aperture_short_slots_and_sum_consistency(oracle_c, fun):
+    """Short slots force the EDGE / dual-window / global-memory paths; summing the kept dimension gives back DAS."""
+    P = small_problem("FC", nz=64, nx=40, ny=2, N=12, M=5, T=300, zlim=(3e-3, 8e-3))
+    ref = oracle_c.das_spec(fun, P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp="cubic",
+                            **oracle_kwargs(P["opts"]))[..., 0]
+    for env in (dict(), dict(QUPS_B200_WMAX=48, QUPS_B200_STAGES=4), dict(QUPS_B200_WMAX=24, QUPS_B200_STAGES=2), dict(QUPS_B200_TILE="8,2")):
+        got = _tiled_fun(fun, P, "cubic", **env)
+        assert rel_linf(got, ref) < 1e-5, env
+    das = _tiled(P, "cubic")
+    assert rel_linf(got.sum(axis=(3, 4)), das[..., 0, 0] if das.ndim == 5 else das) < 1e-5
