@@ -244,6 +244,216 @@ __global__ void __launch_bounds__(kGThreads) greens_binned_kernel(const GreensDe
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Convolution variant (default for fsr == 1, fp32, nearest / linear / cubic).
+//
+// With the kernel sampled at the output rate every scatterer contributes a SHIFTED copy of the same interpolated
+// waveform: for output sample t = ci + p (ci = ceil(arrival), f = ci - arrival in [0,1)) the interpolation weights
+// w_j(f) do not depend on p, so
+//     x(t) = sum_j sum_{p=0}^{K-2} kx[p-1+j] * I_j[t-p]  +  kx[K-1] * I_z[t-(K-1)],
+//     I_j[tau] = sum_{scatterers with ci = tau} att * w_j(f)      (I_z: those with f == 0, the closed end xq == K)
+// where kx is the kernel extended by interp1's end padding (kx[-1] = 3k0-3k1+k2, kx[K] likewise).  The p-range is
+// exactly the support of interp1(kern, xq, interp, 0) (xq in [1,K]), so the result is the oracle's sum, re-associated:
+// I x K x 4 multiply-adds per trace become S x K x 4 (10 k scatterers, S ~ 2.5 k samples: 4x fewer, and regular).
+// Per trace: (1) arrival / attenuation / weights per scatterer in chunks, (2) stable counting sort of the chunk by
+// 32-sample bucket (warp-ordered ranks, no atomics), (3) each train position gathers the entries of its bucket with
+// ci == tau in sorted order (deterministic), (4) the five short real x complex convolutions from shared memory.
+// Arrival times are evaluated in fp64 from the fp32 geometry: at ~4000 samples an fp32 delay carries ~1e-4 samples
+// of rounding noise (the fp32 oracle has it too, the reference's own CPU-vs-GPU bar is 1e-3, test/SimTest.m:327-357);
+// with fp64 delays this kernel matches the fp64 oracle to ~2e-6 instead.  greens_kernel / greens_binned_kernel keep
+// the oracle's fp32 sequence (QUPS_B200_GREENS=simple|binned).
+constexpr int kCChunk = 1024;   // scatterer entries staged per pass
+constexpr int kCBW = 32;        // bucket width (train positions)
+constexpr int kCNB = 136;       // max buckets: (kCBlock + K) / 32 + 1
+constexpr int kCBlock = 3072;   // output samples per train window
+
+template <typename DOUT>
+__global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<float> p, DOUT *y, const float *Pi, const float *amp,
+                                                                const float *Pr, const float *Pv, const float2 *kern, int blk,
+                                                                double c0, double fs, double t0s, double R0) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    const int K = (int)p.T;
+    const int W = blk + K - 1;                                   // train window: tau in [tau0, tau0 + W)
+    const int Wp = (W + 3) & ~3;
+    float2 *kx = reinterpret_cast<float2 *>(gsm);                // kx[q + 1], q = -1 .. K
+    float *trains = reinterpret_cast<float *>(kx + ((K + 2 + 1) & ~1)); // 5 x Wp
+    float4 *s_w = reinterpret_cast<float4 *>(trains + 5 * Wp + ((5 * Wp) & 3 ? 4 - ((5 * Wp) & 3) : 0));
+    float *s_z = reinterpret_cast<float *>(s_w + kCChunk);
+    int *s_ci = reinterpret_cast<int *>(s_z + kCChunk);
+    int *s_cnt = s_ci + kCChunk;                                 // [kW][kCNB]
+    int *s_start = s_cnt + (kGThreads / 32) * kCNB;              // [kCNB + 1]
+    unsigned short *s_perm = reinterpret_cast<unsigned short *>(s_start + kCNB + 1);
+    constexpr int kW = kGThreads / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t n = blockIdx.x, m = blockIdx.y;
+    const uint64_t EE = p.E * p.E, total = p.I * EE;
+    DOUT *yt = y + p.S * (n + p.N * m);
+
+    // extended kernel (interp1's end padding for cubic: v(0) = 3v(1)-3v(2)+v(3), v(T+1) = 3v(T)-3v(T-1)+v(T-2))
+    for (int q = tid; q < K; q += kGThreads) kx[q + 1] = __ldg(kern + q);
+    if (tid == 0) {
+        float2 lo = make_float2(0.f, 0.f), hi = lo;
+        if (p.interp == 2 && K >= 3) {
+            const float2 a = __ldg(kern), b = __ldg(kern + 1), c = __ldg(kern + 2);
+            lo = make_float2(3.f * a.x - 3.f * b.x + c.x, 3.f * a.y - 3.f * b.y + c.y);
+            const float2 d = __ldg(kern + K - 1), e = __ldg(kern + K - 2), f = __ldg(kern + K - 3);
+            hi = make_float2(3.f * d.x - 3.f * e.x + f.x, 3.f * d.y - 3.f * e.y + f.y);
+        }
+        kx[0] = lo; kx[K + 1] = hi;
+    }
+    const int nbk = min(kCNB, (W + kCBW - 1) / kCBW);
+
+    for (uint64_t sb = 0; sb < p.S; sb += (uint64_t)blk) {
+        const long long tau0 = p.n0 + (long long)sb - (K - 1);
+        for (int r = tid; r < 5 * Wp; r += kGThreads) trains[r] = 0.f;
+        for (uint64_t e0 = 0; e0 < total; e0 += kCChunk) {
+            const int cnt = (int)((total - e0 < (uint64_t)kCChunk) ? (total - e0) : kCChunk);
+            __syncthreads();
+            for (int q = tid; q < kW * kCNB; q += kGThreads) s_cnt[q] = 0;
+            // ---- (1) per-entry arrival, attenuation, interpolation weights --------------------------------------
+            for (int q = tid; q < cnt; q += kGThreads) {
+                const uint64_t e = e0 + q, i = e / EE, em = (e % EE) / p.E, en = e % p.E;
+                const double sx = Pi[3 * i], sy = Pi[3 * i + 1], sz = Pi[3 * i + 2];
+                const float *pr = Pr + 3 * (n + p.N * en), *pv = Pv + 3 * (m + p.M * em);
+                const double ax = sx - pr[0], ay = sy - pr[1], az = sz - pr[2];
+                const double bx = sx - pv[0], by = sy - pv[1], bz = sz - pv[2];
+                const double r_rx = sqrt(ax * ax + ay * ay + az * az), r_tx = sqrt(bx * bx + by * by + bz * bz);
+                double att = (double)amp[i];
+                if (R0 != 0.0) att /= (fmax(r_rx, R0) * fmax(r_tx, R0));
+                const double c = (r_rx + r_tx) / c0 * fs + t0s;      // arrival: kernel position of sample t is d = t - c
+                const double cc = ceil(c);
+                const float f = (float)(cc - c), a = (float)att;
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.interp == 2) {            // Keys a = -1/2
+                    const float u = f, u2 = u * u;
+                    w.x = fmaf(fmaf(-0.5f, u, 1.0f), u, -0.5f) * u;
+                    w.y = fmaf(fmaf(1.5f, u, -2.5f), u2, 1.0f);
+                    w.z = fmaf(fmaf(-1.5f, u, 2.0f), u, 0.5f) * u;
+                    w.w = fmaf(0.5f, u, -0.5f) * u2;
+                } else if (p.interp == 1) {     // v(k) + u (v(k+1) - v(k))
+                    w.y = 1.f - f; w.z = f;
+                } else {                        // round half away from zero
+                    if (f < 0.5f) w.y = 1.f; else w.z = 1.f;
+                }
+                s_w[q] = make_float4(a * w.x, a * w.y, a * w.z, a * w.w);
+                s_z[q] = (f == 0.f) ? a : 0.f;
+                const double rel = cc - (double)tau0;
+                s_ci[q] = (rel >= 0.0 && rel < (double)W && c == c) ? (int)rel : -1;
+            }
+            __syncthreads();
+            // ---- (2) stable counting sort of the chunk by bucket: warp w owns a contiguous, ascending range ----
+            const int per = ((cnt + kW * 32 - 1) / (kW * 32)) * 32;
+            const int q0 = warp * per, q1 = min(cnt, q0 + per);
+            for (int qb = q0; qb < q1; qb += 32) {
+                const int q = qb + lane;
+                int b = -1;
+                if (q < q1 && s_ci[q] >= 0) b = min(s_ci[q] / kCBW, nbk - 1);
+                const unsigned mk = __match_any_sync(0xffffffffu, b);
+                if (b >= 0 && lane == (__ffs((int)mk) - 1)) s_cnt[warp * kCNB + b] += __popc(mk);
+                __syncwarp();
+            }
+            __syncthreads();
+            if (tid < nbk) {
+                int tot = 0;
+                for (int w = 0; w < kW; ++w) tot += s_cnt[w * kCNB + tid];
+                s_start[tid + 1] = tot;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int carry = 0;
+                for (int b0 = 0; b0 < nbk; b0 += 32) {
+                    const int b = b0 + lane;
+                    int v = (b < nbk) ? s_start[b + 1] : 0, incl = v;
+                    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+                    if (b < nbk) s_start[b + 1] = carry + incl;
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) s_start[0] = 0;
+            }
+            __syncthreads();
+            if (tid < nbk) {
+                int run = s_start[tid];
+                for (int w = 0; w < kW; ++w) { const int c = s_cnt[w * kCNB + tid]; s_cnt[w * kCNB + tid] = run; run += c; }
+            }
+            __syncthreads();
+            for (int qb = q0; qb < q1; qb += 32) {
+                const int q = qb + lane;
+                int b = -1;
+                if (q < q1 && s_ci[q] >= 0) b = min(s_ci[q] / kCBW, nbk - 1);
+                const unsigned mk = __match_any_sync(0xffffffffu, b);
+                if (b >= 0) s_perm[s_cnt[warp * kCNB + b] + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)q;
+                __syncwarp();
+                if (b >= 0 && lane == (__ffs((int)mk) - 1)) s_cnt[warp * kCNB + b] += __popc(mk);
+                __syncwarp();
+            }
+            __syncthreads();
+            // ---- (3) each train position gathers the entries that arrive exactly there (sorted order) -----------
+            for (int r = tid; r < W; r += kGThreads) {
+                const int b = min(r / kCBW, nbk - 1);
+                const int e_lo = s_start[b], e_hi = s_start[b + 1];
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, az = 0.f;
+                for (int e = e_lo; e < e_hi; ++e) {
+                    const int q = s_perm[e];
+                    if (s_ci[q] == r) {
+                        const float4 w = s_w[q];
+                        a0 += w.x; a1 += w.y; a2 += w.z; a3 += w.w; az += s_z[q];
+                    }
+                }
+                if (e_hi > e_lo) {
+                    trains[r] += a0; trains[Wp + r] += a1; trains[2 * Wp + r] += a2; trains[3 * Wp + r] += a3; trains[4 * Wp + r] += az;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- (4) x(t) = sum_p sum_j kx[p-1+j] I_j[t-p] + kx[K-1] I_z[t-(K-1)] ----------------------------------
+        for (int s0 = 0; s0 < blk; s0 += kGThreads * 8) {
+            float2 acc[8];
+            int rt[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { acc[i] = make_float2(0.f, 0.f); rt[i] = s0 + tid + i * kGThreads + (K - 1); }
+            float2 k0 = kx[0], k1 = kx[1], k2 = kx[2], k3 = (K >= 2) ? kx[3] : make_float2(0.f, 0.f); // kx[p-1+j], p = 0
+            for (int pp = 0; pp <= K - 2; ++pp) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = rt[i] - pp;
+                    if (r < W) {
+                        const float i0 = trains[r], i1 = trains[Wp + r], i2 = trains[2 * Wp + r], i3 = trains[3 * Wp + r];
+                        acc[i].x = fmaf(k0.x, i0, acc[i].x); acc[i].y = fmaf(k0.y, i0, acc[i].y);
+                        acc[i].x = fmaf(k1.x, i1, acc[i].x); acc[i].y = fmaf(k1.y, i1, acc[i].y);
+                        acc[i].x = fmaf(k2.x, i2, acc[i].x); acc[i].y = fmaf(k2.y, i2, acc[i].y);
+                        acc[i].x = fmaf(k3.x, i3, acc[i].x); acc[i].y = fmaf(k3.y, i3, acc[i].y);
+                    }
+                }
+                k0 = k1; k1 = k2; k2 = k3;
+                k3 = (pp + 4 <= K + 1) ? kx[pp + 4] : make_float2(0.f, 0.f);
+            }
+            const float2 kl = kx[K]; // kernel sample K-1: the closed end of interp1's support (xq == K)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rt[i] - (K - 1);
+                if (r < W) {
+                    const float iz = trains[4 * Wp + r];
+                    acc[i].x = fmaf(kl.x, iz, acc[i].x); acc[i].y = fmaf(kl.y, iz, acc[i].y);
+                }
+                const uint64_t sidx = sb + (uint64_t)(s0 + tid + i * kGThreads);
+                if (s0 + tid + i * kGThreads < blk && sidx < p.S)
+                    data_traits<DOUT>::store(yt, sidx, {acc[i].x, acc[i].y});
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static size_t greens_conv_smem(int K, int blk) {
+    const int W = blk + K - 1, Wp = (W + 3) & ~3;
+    size_t b = sizeof(float2) * ((K + 2 + 1) & ~1);
+    b += sizeof(float) * (5 * Wp + 4);
+    b += sizeof(float4) * kCChunk + sizeof(float) * kCChunk + sizeof(int) * kCChunk;
+    b += sizeof(int) * ((kGThreads / 32) * kCNB + kCNB + 1);
+    b += sizeof(unsigned short) * kCChunk + 16;
+    return b;
+}
+
 int launch_greens(const qups_greens_params &p, void *y, const void *Pi, const void *a, const void *Pr, const void *Pv,
                   const void *kern, cudaStream_t st) {
     if (p.S == 0 || p.N == 0 || p.M == 0) return 0;
@@ -254,11 +464,24 @@ int launch_greens(const qups_greens_params &p, void *y, const void *Pi, const vo
     // scatterer-order variant is requested (tests pin bit-exactness on it)
     bool binned = ((double)p.T / p.fsr + 4.0 + kGThreads * 8) / kGBW + 2 <= kGNB;
     if (const char *ev = getenv("QUPS_B200_GREENS")) { if (!strcmp(ev, "simple")) binned = false; }
+    // convolution kernel: kernel sampled at the output rate, fp32, tap-linear interpolators, enough scatterers to pay for it
+    bool conv = p.dtype == QUPS_F32 && p.fsr == 1.0 && p.interp >= 0 && p.interp <= 2 && p.T >= 3 && p.T <= 1024 && p.I * E * E >= 64;
+    if (const char *ev = getenv("QUPS_B200_GREENS")) {
+        if (!strcmp(ev, "simple") || !strcmp(ev, "binned")) conv = false;
+        else if (strcmp(ev, "conv")) { /* unknown value: keep the automatic choice */ }
+    }
     if (p.dtype == QUPS_F32) {
         GreensDev<float> d{p.I, p.S, p.T, p.N, p.M, E, (long long)p.n0, p.interp,
                            (float)p.t0x * (float)p.fs, (float)p.fs, (float)p.fsr, (float)p.c0, (float)p.R0,
                            (float)((double)p.T / p.fsr)};
-        if (binned)
+        if (conv) {
+            const int blk = (int)(p.S <= (uint64_t)kCBlock ? ((p.S + 255) / 256) * 256 : 2048);
+            const size_t smem = greens_conv_smem((int)p.T, blk);
+            cudaError_t e = cudaFuncSetAttribute(greens_conv_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            greens_conv_kernel<float2><<<grid, block, smem, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a, (const float *)Pr,
+                                                                  (const float *)Pv, (const float2 *)kern, blk, p.c0, p.fs, p.t0x * p.fs, p.R0);
+        } else if (binned)
             greens_binned_kernel<float2, float2, float><<<grid, block, 0, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a,
                                                                                 (const float *)Pr, (const float *)Pv, (const float2 *)kern);
         else

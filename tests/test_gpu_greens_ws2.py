@@ -23,8 +23,16 @@ def test_greens_bitexact_vs_oracle(oracle_c, interp, R0, monkeypatch):
     amp = rng.standard_normal(S)
     n0, T = 40, 2600
     ref = oracle_c.greens(ps, amp, pn, pv, kern, n0, T, fs, c0, wt0, 1.0, R0, interp)
-    got = greens_raw(ps, amp, pn, pv, kern, n0, T, fs, c0, wt0, 1.0, R0, interp).cpu().numpy()   # bucketed kernel
+    f32 = np.float32  # the fp64 oracle on the SAME fp32-rounded inputs: the arbiter for the convolution kernel's fp64 delays
+    ref64 = oracle_c.greens(ps.astype(f32), amp.astype(f32), pn.astype(f32), pv.astype(f32), kern, n0, T, fs, c0, wt0, 1.0, R0, interp,
+                            dtype=np.float64)
     assert np.abs(ref).max() > 0
+    got = greens_raw(ps, amp, pn, pv, kern, n0, T, fs, c0, wt0, 1.0, R0, interp).cpu().numpy()   # default: convolution kernel
+    if interp != "nearest":  # nearest flips a tap where an fp32 delay lands on the other side of .5: compare where it cannot
+        assert rel_linf(got, ref64) < 5e-6, rel_linf(got, ref64)
+        assert rel_linf(got, ref) < 1e-3                          # vs the fp32 oracle: its own delay rounding (SimTest bar)
+    monkeypatch.setenv("QUPS_B200_GREENS", "binned")             # the oracle's fp32 sequence, bucket order
+    got = greens_raw(ps, amp, pn, pv, kern, n0, T, fs, c0, wt0, 1.0, R0, interp).cpu().numpy()
     assert rel_linf(got, ref) < 2e-6, rel_linf(got, ref)          # same terms, bucket order instead of scatterer order
     monkeypatch.setenv("QUPS_B200_GREENS", "simple")             # exact scatterer-order variant: bit-exact
     got = greens_raw(ps, amp, pn, pv, kern, n0, T, fs, c0, wt0, 1.0, R0, interp).cpu().numpy()
@@ -167,3 +175,27 @@ def test_greens_focustx_das_psf(seqtype):
     assert b.max() > 0
     iz, ix = np.unravel_index(np.argmax(b), b.shape)
     assert abs(zs[iz] - 15e-3) <= 1.1e-3 and abs(xs[ix] - 2e-3) <= 1.1e-3
+
+
+@pytest.mark.parametrize("interp", ["nearest", "linear", "cubic"])
+def test_greens_convolution_kernel_exact_cases(oracle_c, interp, monkeypatch):
+    """The convolution form on delays that are exact in fp32 AND fp64 (dyadic geometry): integer and half-integer arrivals hit
+    the closed ends of interp1's support (xq == 1, xq == K), the cubic end padding and the nearest tie; must equal the
+    fp32 oracle to summation order, for every interpolator, across block boundaries and many chunks."""
+    from qups_b200.ultrasound import greens_raw
+    fs, c0 = 2.0 ** 24, 2.0 ** 10                     # fs / c0 = 2^14 samples per metre: distances k/2^15 m are exact half-samples
+    rng = np.random.default_rng(7)
+    K = 37
+    kern = (rng.standard_normal(K) + 1j * rng.standard_normal(K)).astype(np.complex64)
+    pn = np.array([[0.0], [0.0], [0.0]])
+    S = 2500
+    zs = rng.integers(40, 9000, S) / 2.0 ** 16         # one-way path z => arrival 2 z 2^14 = k / 2 samples exactly
+    ps = np.stack([np.zeros(S), np.zeros(S), zs], 0)
+    amp = rng.integers(-4, 5, S).astype(np.float64)
+    n0, T = 10, 5000                                   # two train windows
+    ref = oracle_c.greens(ps, amp, pn, pn, kern, n0, T, fs, c0, 0.0, 1.0, 0.0, interp)
+    got = greens_raw(ps, amp, pn, pn, kern, n0, T, fs, c0, 0.0, 1.0, 0.0, interp).cpu().numpy()
+    assert np.abs(ref).max() > 0
+    assert rel_linf(got, ref) < 3e-6, rel_linf(got, ref)
+    z = np.abs(ref) == 0
+    assert np.all(got[z] == 0)                         # exact zeros outside every scatterer's support
