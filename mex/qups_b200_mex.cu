@@ -15,6 +15,8 @@
 //   y = qups_b200_mex('das',    C, yg, ..., [fs fmod], rx_aux, tx_aux, lat)   closed-form apodization (C.ap_rx_kind / C.ap_tx_kind,
 //                                                                               C.ap_rx_p, C.ap_tx_p, C.ap_lat_dim; empty [] for unused arrays)
 //   a = qups_b200_mex('apod',   C, a0, Pi, Pr, rx_aux, tx_aux, lat)           dense image of the same generator (C.which = 0 rx | 1 tx)
+//   r = qups_b200_mex('aperture', C, r0, b)                                    cohfac / dmas / pcf / slsc along one dimension
+//                                                                               (C.op, C.C, C.A, C.S, C.lags (uint32), C.gamma)
 //   y = qups_b200_mex('prep',   C, y0, x, t0)                                 zeropad -> hilbert -> downmix -> cast (C.B, C.A, C.hilbert, C.fmix, C.fs, C.N)
 // where C is a scalar struct holding what the reference puts in __constant__ memory with k.setConstantMemory
 // (kern/das_spec.m:294-298): C.I1,C.I2,C.I3,C.N,C.M,C.T,C.S,C.VS,C.DV,C.flag  (+ ws2: C.T,C.interp,C.omega ;
@@ -144,6 +146,20 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         check(qups_apod_generate(&f, which, y, mxGPUGetComplexity(out) == mxCOMPLEX, RO(Pi), RO(Pr), (uint64_t)fld(C, "I1", 1),
                                  (uint64_t)fld(C, "I2", 1), (uint64_t)fld(C, "I3", 1), (uint64_t)fld(C, which ? "M" : "N", 1), NULL));
         mxGPUDestroyGPUArray(Pi); mxGPUDestroyGPUArray(Pr); mxGPUDestroyGPUArray(rxa); mxGPUDestroyGPUArray(txa); mxGPUDestroyGPUArray(lat);
+    } else if (!strcmp(op, "aperture")) {
+        if (nrhs != 4) mexErrMsgIdAndTxt("QUPS:b200:usage", "'aperture' takes 4 arguments");
+        const mxGPUArray *b = IN(3);
+        qups_aperture_params p;
+        memset(&p, 0, sizeof(p));
+        p.struct_size = sizeof(p);
+        p.dtype = dtype_of(b);
+        p.op = (int32_t)fld(C, "op", 0);
+        p.C = (uint64_t)fld(C, "C", 1); p.A = (uint64_t)fld(C, "A", 1); p.S = (uint64_t)fld(C, "S", 1);
+        p.gamma = fld(C, "gamma", 1);
+        const mxArray *lg = mxGetField(C, 0, "lags");          /* host uint32 vector */
+        p.nlags = lg ? (uint32_t)mxGetNumberOfElements(lg) : 0;
+        check(qups_aperture(&p, y, NULL, RO(b), lg ? (const uint32_t *)mxGetData(lg) : NULL, NULL));
+        mxGPUDestroyGPUArray(b);
     } else if (!strcmp(op, "prep")) {
         if (nrhs != 5) mexErrMsgIdAndTxt("QUPS:b200:usage", "'prep' takes 5 arguments");
         const mxGPUArray *x = IN(3), *t0 = IN(4);            /* y0: complex single (B+T+A) x N x M prototype; t0: single */

@@ -21,6 +21,7 @@ ap.add_argument("--interp", default="cubic")
 ap.add_argument("--path", default="auto")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--config", default="c2")
+ap.add_argument("--slab", default="", help="k/n: beamform only the k-th of n pixel slabs along x (what rank k of n GPUs does)")
 a = ap.parse_args()
 
 if a.config == "c5":
@@ -28,6 +29,10 @@ if a.config == "c5":
     P.interp = a.interp
 else:
     P = {"c2": synth.config_c2, "c3": synth.config_c3}[a.config](a.nz, a.nx, a.N, a.M, a.T, a.interp)
+if a.slab:
+    from qups_b200 import shard
+    k, n = (int(v) for v in a.slab.split("/"))
+    P.Pi = np.ascontiguousarray(shard.pixel_shard(P.Pi, k, n)[0])
 t = time.time()
 x = torch.from_numpy(synth.noise_cube(P.T, P.N, P.M)).cuda()
 print(f"data gen {time.time()-t:.1f}s", flush=True)
