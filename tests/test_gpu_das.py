@@ -297,3 +297,43 @@ def test_full_size_headline_parity_on_pixel_subsets(oracle_c):
     assert np.max(np.abs(left.reshape(1024, 512, order="F") - full[:, :512])) / scale < TOL   # receive-split changes the sum order
     twice = qups_b200.das_spec("DAS", dev(P.Pi[:, :, 512:]), *g, 2 * xd, 0.0, P.fs, P.c0, "interp", "cubic").cpu().numpy()
     assert np.max(np.abs(twice.reshape(1024, 512, order="F") - 2 * full[:, 512:])) / scale < 2 * TOL
+
+
+def test_full_size_kept_aperture_and_fused_mask_properties():
+    """Headline size, size-independent properties: (a) summing the staged SYN / MUL outputs over the kept dimension gives the
+    staged DAS image; (b) the in-kernel f-number mask equals the same mask passed as a dense array, bit for bit in the mask
+    and to tolerance in the image; (c) on 2048 random pixels both equal the bit-exact generic kernel."""
+    import torch
+    import qups_b200
+    from qups_b200 import synth, _lib, ultrasound as U
+    P = synth.config_c2()
+    x = synth.noise_cube(P.T, P.N, P.M, seed=0)
+    f32 = np.float32
+    dev = lambda v: torch.from_numpy(np.ascontiguousarray(np.asarray(v, f32))).cuda()
+    xd = torch.from_numpy(x).cuda()
+    g = (dev(P.Pi), dev(P.Pr), dev(P.Pv), dev(P.Nv))
+    full = qups_b200.das_spec("DAS", *g, xd, 0.0, P.fs, P.c0, "interp", "cubic").reshape(1024, 1024)
+    scale = float(full.abs().max())
+    rng = np.random.default_rng(11)
+    iz, ix = rng.integers(0, 1024, 2048), rng.integers(0, 1024, 2048)
+    sub = dev(np.ascontiguousarray(P.Pi[:, iz, ix, 0]).reshape(3, -1, 1, 1))
+    for fun, axis in (("SYN", 3), ("MUL", 4)):
+        b = qups_b200.das_spec(fun, *g, xd, 0.0, P.fs, P.c0, "interp", "cubic")
+        assert qups_b200.last_das_kernel() == "das_tiled"
+        tot = b.sum(dim=(3, 4)).reshape(1024, 1024)
+        assert float((tot - full).abs().max()) / scale < 2 * TOL, fun
+        gen = qups_b200.das_spec(fun, sub, *g[1:], xd, 0.0, P.fs, P.c0, "interp", "cubic", _path=_lib.PATH_GENERIC)
+        pick = b.reshape(1024, 1024, b.shape[3], b.shape[4])[torch.from_numpy(iz).cuda(), torch.from_numpy(ix).cuda()]
+        assert float((pick.reshape(gen.shape[0], -1) - gen.reshape(gen.shape[0], -1)).abs().max()) / float(gen.abs().max()) < TOL, fun
+        del b, tot, gen, pick
+        torch.cuda.empty_cache()
+    us = U.UltrasoundSystem(tx=P.Pr, rx=P.Pr, seq=U.Sequence("FC", P.Pv), scan=P.Pi, fs=P.fs)
+    spec = us.apApertureGrowth(1.5)
+    fused = qups_b200.das_spec("DAS", *g, xd, 0.0, P.fs, P.c0, "interp", "cubic", "apod", spec)
+    dense = spec.dense(g[0], g[1], which="rx")
+    viaarr = qups_b200.das_spec("DAS", *g, xd, 0.0, P.fs, P.c0, "interp", "cubic", "apod", dense)
+    assert float((fused - viaarr).abs().max()) / float(viaarr.abs().max()) < TOL
+    genm = qups_b200.das_spec("DAS", sub, *g[1:], xd, 0.0, P.fs, P.c0, "interp", "cubic", "apod", spec, _path=_lib.PATH_GENERIC)
+    assert qups_b200.last_das_kernel() == "das_generic+apod_generate"
+    pick = fused.reshape(1024, 1024)[torch.from_numpy(iz).cuda(), torch.from_numpy(ix).cuda()]
+    assert float((pick - genm.reshape(-1)).abs().max()) / float(genm.abs().max()) < TOL
