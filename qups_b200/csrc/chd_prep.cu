@@ -43,13 +43,27 @@ __device__ void fft_twiddles(float2 *tw, uint32_t n) {
     }
     __syncthreads();
 }
-__device__ void fft_pow2(float2 *s, const float2 *tw, uint32_t n, uint32_t log2n, bool inverse) {
+// The transform pair never permutes: the FORWARD transform is decimation-in-frequency (natural order in, bit-reversed
+// order out), the INVERSE is decimation-in-time on bit-reversed input (natural order out).  Everything in between
+// (hilbert weights, Bluestein's spectrum product) is element-wise and simply indexes by the bit-reversed position.
+// (A bit-reversal pass put consecutive lanes n/2 elements apart: 32-way bank conflicts, most of the shared wavefronts.)
+__device__ void fft_fwd_dif(float2 *s, const float2 *tw, uint32_t n, uint32_t log2n) {
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    for (uint32_t i = tid; i < n; i += nt) {
-        const uint32_t j = __brev(i) >> (32 - log2n);
-        if (i < j) { const float2 a = s[i]; s[i] = s[j]; s[j] = a; }
+    for (uint32_t st = log2n; st >= 1; --st) {
+        const uint32_t half = 1u << (st - 1);
+        const float2 *tws = tw + (half - 1);
+        for (uint32_t b = tid; b < (n >> 1); b += nt) {
+            const uint32_t k = b & (half - 1);
+            const uint32_t i0 = ((b >> (st - 1)) << st) + k, i1 = i0 + half;
+            const float2 a = s[i0], c = s[i1], w = tws[k];
+            s[i0] = make_float2(a.x + c.x, a.y + c.y);
+            s[i1] = cmulf(make_float2(a.x - c.x, a.y - c.y), w);
+        }
+        __syncthreads();
     }
-    __syncthreads();
+}
+__device__ void fft_inv_dit(float2 *s, const float2 *tw, uint32_t n, uint32_t log2n) { // unscaled
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
     for (uint32_t st = 1; st <= log2n; ++st) {
         const uint32_t half = 1u << (st - 1);
         const float2 *tws = tw + (half - 1);
@@ -57,7 +71,7 @@ __device__ void fft_pow2(float2 *s, const float2 *tw, uint32_t n, uint32_t log2n
             const uint32_t k = b & (half - 1);
             const uint32_t i0 = ((b >> (st - 1)) << st) + k, i1 = i0 + half;
             float2 w = tws[k];
-            if (inverse) w.y = -w.y;
+            w.y = -w.y;
             const float2 a = s[i0], t = cmulf(s[i1], w);
             s[i0] = make_float2(a.x + t.x, a.y + t.y);
             s[i1] = make_float2(a.x - t.x, a.y - t.y);
@@ -88,10 +102,10 @@ __device__ void dft_bluestein(float2 *s, const float2 *tw, const float2 *cb, con
         s[i] = v;
     }
     __syncthreads();
-    fft_pow2(s, tw, nfft, log2n, false);
-    for (uint32_t i = tid; i < nfft; i += nt) s[i] = cmulf(s[i], cb[i]);
+    fft_fwd_dif(s, tw, nfft, log2n);
+    for (uint32_t i = tid; i < nfft; i += nt) s[i] = cmulf(s[i], cb[i]); // both spectra in bit-reversed order
     __syncthreads();
-    fft_pow2(s, tw, nfft, log2n, true);
+    fft_inv_dit(s, tw, nfft, log2n);
     const float sc = 1.0f / (float)nfft;
     for (uint32_t i = tid; i < L; i += nt) {
         float2 v = cmulf(make_float2(s[i].x * sc, s[i].y * sc), ch[i]);
@@ -121,7 +135,7 @@ __global__ void __launch_bounds__(1024) chd_prep_kernel(const PrepArgs a) {
             cb[i] = v;
         }
         __syncthreads();
-        fft_pow2(cb, tw, a.nfft, a.log2n, false);
+        fft_fwd_dif(cb, tw, a.nfft, a.log2n);
     }
 
     for (uint64_t k = blockIdx.x; k < a.K; k += gridDim.x) {
@@ -141,20 +155,22 @@ __global__ void __launch_bounds__(1024) chd_prep_kernel(const PrepArgs a) {
             __syncthreads();
             // ---- analytic signal: fft, weights [1, 2 x (Nd2-1), 1+mod(L,2), 0 ...], ifft (src/ChannelData.m:960-964) ----
             if (a.bluestein) dft_bluestein(s, tw, cb, ch, L, a.nfft, a.log2n, false);
-            else fft_pow2(s, tw, a.nfft, a.log2n, false);
+            else fft_fwd_dif(s, tw, a.nfft, a.log2n);
             const uint64_t nd2 = L / 2;
             for (uint64_t j = tid; j < L; j += nt) {
+                // frequency index held at position j: natural order after Bluestein, bit-reversed after the in-place DIF
+                const uint64_t kf = (a.bluestein || a.log2n == 0) ? j : (uint64_t)(__brev((uint32_t)j) >> (32 - a.log2n));
                 float w;
-                if (j == 0) w = 1.f;
-                else if (j < nd2) w = 2.f;
-                else if (j == nd2) w = (L & 1) ? 2.f : 1.f;
+                if (kf == 0) w = 1.f;
+                else if (kf < nd2) w = 2.f;
+                else if (kf == nd2) w = (L & 1) ? 2.f : 1.f;
                 else w = 0.f;
                 if (L == 1) w = 1.f;
                 s[j] = make_float2(s[j].x * w, s[j].y * w);
             }
             __syncthreads();
             if (a.bluestein) dft_bluestein(s, tw, cb, ch, L, a.nfft, a.log2n, true);
-            else fft_pow2(s, tw, a.nfft, a.log2n, true);
+            else fft_inv_dit(s, tw, a.nfft, a.log2n);
         }
         // ---- downmix + cast + store ----------------------------------------------------------------------
         float t0 = 0.f;
