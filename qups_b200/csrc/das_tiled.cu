@@ -909,6 +909,8 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     else                { t.IA = (uint32_t)a.I1; t.sA = 1;    t.IB = (uint32_t)a.I2; t.sB = a.I1; }
     t.IC = (uint32_t)a.I3; t.sC = a.I1 * a.I2;
     double span_m = 0.0; // path-length spread across one tile (metres, sum of the two tile extents)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool noprobe = (cudaStreamIsCapturing(st, &cap) != cudaSuccess) || cap != cudaStreamCaptureStatusNone || getenv("QUPS_B200_NOPROBE");
     // ---- tile shape: 512 pixels as tA x tB with a lpa x (32/lpa) x 2 warp patch, chosen so that the delay spread across the
     // tile (~ pixel spacing x extent) is smallest: square-ish on isotropic grids (32 x 16, patch 8 x 4 x 2 — measured best on the
     // headline grid), narrow along a coarsely sampled axis (e.g. one image column per element pitch).  The spacing is read
@@ -917,8 +919,12 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
         struct ShapeCache { const void *Pi; uint64_t I1, I2, I3; int lane_axis; uint32_t tA, lpa; double span; };
         static thread_local ShapeCache sc = {nullptr, 0, 0, 0, 0, 0, 0, 0.0};
         uint32_t tA = 32, lpa = QUPS_LPA;
+        // the probe synchronises the stream once per new grid: not allowed while the stream is being captured into a CUDA
+        // graph (and skippable with QUPS_B200_NOPROBE=1) — the default shape / ring are then used, results are unaffected
         if (sc.Pi == a.Pi && sc.I1 == a.I1 && sc.I2 == a.I2 && sc.I3 == a.I3 && sc.lane_axis == lane_axis) {
             tA = sc.tA; lpa = sc.lpa; span_m = sc.span;
+        } else if (noprobe) {
+            span_m = 0.0;
         } else {
             float P0[3], PA[3], PB[3];
             double dA = 1.0, dB = 1.0;
@@ -966,9 +972,9 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
         float cinv_h = 0.f;
         static thread_local const void *c_ptr = nullptr;
         static thread_local float c_val = 0.f;
-        if (span_m > 0.0) {
+        if (span_m > 0.0) { // (span_m stays 0 when the probe was skipped)
             if (c_ptr == a.cinv && c_val > 0.f) cinv_h = c_val;
-            else if (cudaMemcpyAsync(&cinv_h, a.cinv, sizeof(float), cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) { c_ptr = a.cinv; c_val = cinv_h; }
+            else if (!noprobe && cudaMemcpyAsync(&cinv_h, a.cinv, sizeof(float), cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) { c_ptr = a.cinv; c_val = cinv_h; }
         }
         // upper bound of the window: every pixel step changes the round-trip path by at most twice its length
         const double west = (cinv_h > 0.f) ? 2.0 * (double)a.fs * cinv_h * span_m + 8.0 : 0.0;
