@@ -79,7 +79,7 @@ constexpr int kTilePix = kCW * 32 * kR; // pixels per tile; its SHAPE (tA x tB, 
 
 // QUPS_MAGIC: the cubic fast path derives the tap address from the bits of 2^23 + floor(xq); the constant
 // (0x4B000000 << 3) mod 2^32 is folded into the published slot offset
-template <int INTERP> struct magic_off { static constexpr uint32_t value = (QUPS_MAGIC && INTERP == 2) ? (0x4B000000u << 3) : 0u; };
+template <int INTERP> struct magic_off { static constexpr uint32_t value = QUPS_MAGIC ? (0x4B000000u << 3) : 0u; };
 
 #if QUPS_STATS
 __device__ unsigned long long g_stats[8]; // [0..3] traces by flag, [4] split traces, [5] all-fast stages, [6] general stages
@@ -270,8 +270,28 @@ __device__ __forceinline__ void fast_pair2(const Pack2 &c, float2 dr, uint32_t s
         acc1.x = fmaf(w3.y, q3.x, acc1.x); acc1.y = fmaf(w3.y, q3.y, acc1.y);
 #endif
     } else {
+#if QUPS_MAGIC
+        // linear / nearest with the same magic-number index (published offsets carry -kMagicOff for every interpolator)
+        const float2 xr = (INTERP == 1) ? xq : make_float2(__fadd_rn(xq.x, 0.5f), __fadd_rn(xq.y, 0.5f)); // round half away == floor(xq + .5)
+        const float2 tm = make_float2(__fadd_rd(xr.x, 8388608.f), __fadd_rd(xr.y, 8388608.f));
+        const uint32_t a0 = soff + (__float_as_uint(tm.x) << 3);
+        const uint32_t a1 = soff1 + (__float_as_uint(tm.y) << 3);
+        if (INTERP == 1) {
+            const float2 kf = __fadd2_rn(tm, make_float2(-8388608.f, -8388608.f)); // exact
+            const float2 u = __ffma2_rn(kf, make_float2(-1.f, -1.f), xq);          // exact
+            const float2 p0 = lds64(a0), p1 = lds64(a0 + 8), q0 = lds64(a1), q1 = lds64(a1 + 8);
+            // v0 + u (v1 - v0), (re, im) packed: same three roundings as the scalar form
+            const float2 d0 = __ffma2_rn(p0, make_float2(-1.f, -1.f), p1), d1 = __ffma2_rn(q0, make_float2(-1.f, -1.f), q1);
+            acc0 = __fadd2_rn(acc0, __ffma2_rn(d0, make_float2(u.x, u.x), p0));
+            acc1 = __fadd2_rn(acc1, __ffma2_rn(d1, make_float2(u.y, u.y), q0));
+        } else {
+            acc0 = __fadd2_rn(acc0, lds64(a0));
+            acc1 = __fadd2_rn(acc1, lds64(a1));
+        }
+#else
         fast_pair<INTERP>(xq.x, soff, acc0.x, acc0.y);
         fast_pair<INTERP>(xq.y, soff1, acc1.x, acc1.y);
+#endif
     }
 }
 
