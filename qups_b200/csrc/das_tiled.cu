@@ -54,7 +54,12 @@ constexpr int kNT = QUPS_NT;          // traces (receives) per stage
 constexpr int kR = 2;                 // pixel rows per thread
 constexpr int kCW = QUPS_CW;          // consumer warps
 constexpr int kStages = QUPS_STAGES;  // smem ring depth
-constexpr int kThreads = (kCW + 1) * 32;
+#ifndef QUPS_PW
+#define QUPS_PW 2
+#endif
+constexpr int kPW = QUPS_PW;          // producer warps: they take the published stages in turn (stage index mod kPW)
+// threads per CTA: the 1-tap (nearest) kernel runs kPW producer warps, linear / cubic one (a tenth warp cost them 2 %)
+constexpr int threads_of(int interp) { return (kCW + (interp == 0 ? kPW : 1)) * 32; }
 #ifndef QUPS_STATS
 #define QUPS_STATS 0
 #endif
@@ -393,7 +398,8 @@ __device__ __forceinline__ int tap_window(float xlo, float xhi, float Tf, int T,
 //        scalar is dr(i, n) — so every stage adds to y(:,n).  (sample_pos only adds dv + dr: the swap is bit-neutral.)
 //        y is pre-zeroed by the launcher; a CTA owns its pixels (nsplit = 1), so the read-modify-write needs no atomics.
 template <int INTERP, int NAP, int FUSED, int KEEP>
-__global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(const TiledArgs a) {
+__global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_kernel(const TiledArgs a) {
+    constexpr int kThreads = threads_of(INTERP);
     constexpr bool kInnerTx = (KEEP == 2); // the 16 traces of a stage run over transmits instead of receives
     static_assert(KEEP == 0 || (NAP == 0 && FUSED == 0), "kept apertures: plain weights only");
     static_assert(kR == 2, "the packed fp32x2 inner loop assumes two pixel rows per thread");
@@ -720,7 +726,15 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
             if (valid[1]) a.y[pix[1]] = acc1;
         }
     } else {
-        // =========================== producer warp =================================
+        // =========================== producer warps ================================
+        // One warp needs ~400 mostly dependent instructions per stage (ncu: with one producer the consumers of the
+        // 1- and 2-tap kernels spent 29 % of their time waiting for data).  kPW warps run the same candidate loop and
+        // take the candidates in turn; the stage index is the CANDIDATE index, so no warp needs the other's result
+        // (a candidate whose exact per-trace test finds nothing is then published as an all-SKIP stage).
+        // Measured (C2): nearest 42.6 -> 37.7 ms with two producers; linear unchanged and cubic 2 % slower with a tenth warp in
+        // the CTA (their consumers are shared-memory / issue bound) — so only the 1-tap kernel is launched with the second.
+        const uint32_t pw = (uint32_t)warp - kCW;
+        constexpr uint32_t nprod = (uint32_t)(kThreads / 32 - kCW);
         __syncthreads(); // matches the consumers' post-phase-0 barrier
         const bool cinv_ok = (cinv > 0.f) && (fs > 0.f);
         const int Ti = (int)a.T;
@@ -764,6 +778,7 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                 while (todo) {
                     const uint32_t outer = m0 + (uint32_t)(__ffs((int)todo) - 1);
                     todo &= todo - 1;
+                    if (nprod > 1 && (it % nprod) != pw) { ++it; continue; } // another producer warp's stage
                     // this lane's trace: (receive n, transmit m)
                     const uint32_t m = kInnerTx ? il : outer, n = kInnerTx ? outer : il;
                     const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
@@ -834,10 +849,11 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
                     if constexpr (FUSED == 2) { // receive n is masked for every pixel of the tile: nothing to stage
                         if (has && s_rxany[n] == 0) { flag = TR_SKIP; bytes[0] = bytes[1] = 0u; }
                     }
-                    if (__all_sync(0xffffffffu, flag == TR_SKIP)) continue; // exact per-trace test: nothing to do
+                    if (nprod == 1 && __all_sync(0xffffffffu, flag == TR_SKIP)) continue; // exact per-trace test: nothing to do
                     const bool all_fast = __all_sync(0xffffffffu, (flag == TR_FAST && bytes[1] == 0u) || lane >= kNT);
                     const uint32_t total = __reduce_add_sync(0xffffffffu, bytes[0] + bytes[1]);
 #if QUPS_STATS
+                    if (lane == 0 && total == 0) atomicAdd(&g_stats[7], 1ull);
                     if (lane < kNT) { atomicAdd(&g_stats[flag], 1ull); if (bytes[1]) atomicAdd(&g_stats[4], 1ull); }
                     if (lane == 0) atomicAdd(&g_stats[all_fast ? 5 : 6], 1ull);
 #endif
@@ -856,8 +872,8 @@ __global__ void __launch_bounds__(kThreads, QUPS_MINBLOCKS) das_tiled_kernel(con
         // end-of-work marker
         {
             const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            if (lane == 0) {
+            if ((it % nprod) == pw) mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            if ((it % nprod) == pw && lane == 0) {
                 stage_hdr[s] = make_int4(ST_END, 0, 0, 0);
                 mbar_arrive(bar_full + 8 * s);
             }
@@ -1056,7 +1072,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
         e = cudaMemsetAsync(t.y, 0, sizeof(float2) * a.I * (keep == 1 ? a.M : a.N), st);
         if (e != cudaSuccess) return (int)e;
     }
-    kern<<<(unsigned)(tiles * nsplit), kThreads, smem, st>>>(t);
+    kern<<<(unsigned)(tiles * nsplit), threads_of(ip), smem, st>>>(t);
     count_launch();
     e = cudaGetLastError();
 #if QUPS_STATS
@@ -1065,8 +1081,8 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
         cudaStreamSynchronize(st);
         cudaMemcpyFromSymbol(h, g_stats, sizeof(h));
         fprintf(stderr, "[das_tiled stats] tile %u x %u lpa %u wmax %u stages %u nsplit %u grid %llu\n", t.tA, t.tB, t.lpa, t.wmax, t.stages, t.nsplit, (unsigned long long)(tiles * nsplit));
-        fprintf(stderr, "[das_tiled stats] traces FAST %llu SKIP %llu SLOW %llu EDGE %llu split %llu | stages all-fast %llu general %llu\n",
-                h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+        fprintf(stderr, "[das_tiled stats] traces FAST %llu SKIP %llu SLOW %llu EDGE %llu split %llu | stages all-fast %llu general %llu (empty %llu)\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
         unsigned long long z[8] = {0};
         cudaMemcpyToSymbol(g_stats, z, sizeof(z));
     }
