@@ -18,6 +18,8 @@
 
 namespace qups {
 void count_launch(uint64_t n);
+cudaError_t ws_alloc(void **p, size_t bytes, cudaStream_t st);
+cudaError_t ws_free(void *p, cudaStream_t st);
 
 template <typename R> struct c2 { using type = float2; };
 template <> struct c2<double> { using type = double2; };
@@ -134,11 +136,11 @@ int launch_aperture(const qups_aperture_params &p, void *out, void *out2, const 
         if (!h) return -4;
         for (uint32_t k = 0; k < p.nlags; ++k)
             if (lags[k] < p.A && (lags[k] >= 1 || p.op != QUPS_APD_DMAS) && !h[lags[k]]) { h[lags[k]] = 1; ++nl; } // dmas: intersect(1:N-1, L)
-        cudaError_t e = cudaMallocAsync((void **)&mask, p.A + 1, st);
+        cudaError_t e = ws_alloc((void **)&mask, p.A + 1, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(mask, h, p.A + 1, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st); // h is freed below
         free(h);
-        if (e != cudaSuccess) { if (mask) cudaFreeAsync(mask, st); return (int)e; }
+        if (e != cudaSuccess) { if (mask) ws_free(mask, st); return (int)e; }
     }
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
@@ -150,7 +152,7 @@ int launch_aperture(const qups_aperture_params &p, void *out, void *out2, const 
     else aperture_kernel<float><<<grid, 256, 0, st>>>(p.op, out, out2, b, mask, p.C, p.A, p.S, p.nlags, (float)p.gamma);
     count_launch(1);
     const cudaError_t e = cudaGetLastError();
-    if (mask) cudaFreeAsync(mask, st);
+    if (mask) ws_free(mask, st);
     (void)nl;
     return (int)e;
 }

@@ -57,4 +57,9 @@ int launch_apod_generate(const FusedApod &fa, int which, float *out, int as_comp
 
 void count_launch(uint64_t n = 1);
 
+// Stream-ordered scratch from the library's OWN memory pool (one per device, release threshold = keep): the default pool
+// returns memory to the driver at every synchronisation point, so a per-call cudaMallocAsync would re-map it each time.
+cudaError_t ws_alloc(void **p, size_t bytes, cudaStream_t st);
+cudaError_t ws_free(void *p, cudaStream_t st);
+
 } // namespace qups

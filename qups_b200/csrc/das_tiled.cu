@@ -1065,7 +1065,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     t.I = a.I;
     t.part = nullptr;
     if (nsplit > 1) {
-        e = cudaMallocAsync((void **)&t.part, sizeof(float2) * a.I * nsplit, st);
+        e = ws_alloc((void **)&t.part, sizeof(float2) * a.I * nsplit, st);
         if (e != cudaSuccess) return (int)e;
     }
     if (keep && !t.accumulate) { // every stage adds into y(:, n | m)
@@ -1094,7 +1094,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
             count_launch();
             e = cudaGetLastError();
         }
-        cudaFreeAsync(t.part, st);
+        ws_free(t.part, st);
     }
     return (int)e;
 }

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <type_traits>
+#include <mutex>
 
 #include "../../include/qups_b200.h"
 #include "das_args.cuh"
@@ -18,6 +19,32 @@ static thread_local uint64_t g_launches = 0;
 static thread_local const char *g_last_das = "none";
 static thread_local const qups_apod_fused *g_fused = nullptr; // set by qups_das_fused around das_impl
 void count_launch(uint64_t n) { g_launches += n; }
+
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64] = {};
+cudaError_t ws_alloc(void **p, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(p, bytes, st);
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pools[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            if ((e = cudaMemPoolCreate(&g_pools[dev], &props)) != cudaSuccess) { g_pools[dev] = nullptr; return cudaMallocAsync(p, bytes, st); }
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool = g_pools[dev];
+    }
+    return cudaMallocFromPoolAsync(p, bytes, pool, st);
+}
+cudaError_t ws_free(void *p, cudaStream_t st) { return p ? cudaFreeAsync(p, st) : cudaSuccess; }
 
 static int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -146,8 +173,8 @@ static int run_das_typed(const qups_das_params *p, void *y, const void *Pi, cons
                 }
                 const uint64_t nrx = a.fa.rx_kind != AP_RX_NONE ? a.I * a.N : 0, ntx = a.fa.tx_kind != AP_TX_NONE ? a.I * a.M : 0;
                 DA *buf = nullptr;
-                cudaError_t ce = cudaMallocAsync((void **)&buf, sizeof(DA) * (have + nrx + ntx), st); // complex-sized: enough for either element type
-                if (ce != cudaSuccess) return fail(QUPS_ERR_ALLOC, "cudaMallocAsync(dense apodization, %llu elements): %s", (unsigned long long)(have + nrx + ntx), cudaGetErrorString(ce));
+                cudaError_t ce = ws_alloc((void **)&buf, sizeof(DA) * (have + nrx + ntx), st); // complex-sized: enough for either element type
+                if (ce != cudaSuccess) return fail(QUPS_ERR_ALLOC, "ws_alloc(dense apodization, %llu elements): %s", (unsigned long long)(have + nrx + ntx), cudaGetErrorString(ce));
                 if (have) ce = cudaMemcpyAsync(buf, a.apod, (a.apod_real ? sizeof(DA) / 2 : sizeof(DA)) * have, cudaMemcpyDeviceToDevice, st);
                 DasArgs<R> g = a;
                 g.fused = 0;
@@ -171,11 +198,11 @@ static int run_das_typed(const qups_das_params *p, void *y, const void *Pi, cons
                         ++g.S;
                     }
                 } else {
-                    cudaFreeAsync(buf, st);
+                    ws_free(buf, st);
                     return fail(QUPS_ERR_UNSUPPORTED, "closed-form apodization outside the staged kernel needs fp32 apodization arrays");
                 }
                 if (ce == cudaSuccess && rc == 0) rc = launch_das_generic<DIN, DA, DOUT, R>(g, st);
-                cudaFreeAsync(buf, st);
+                ws_free(buf, st);
                 if (ce != cudaSuccess) return cuda_fail(ce, "dense apodization copy");
                 g_last_das = "das_generic+apod_generate";
             } else {
@@ -212,8 +239,8 @@ static int das_impl(const qups_das_params *p, void *y, const void *Pi, const voi
         bool own = false;
         if (p->workspace && p->workspace_bytes >= esz * nel) scratch = p->workspace;
         else {
-            cudaError_t e = cudaMallocAsync(&scratch, esz * nel, st);
-            if (e != cudaSuccess) return fail(QUPS_ERR_ALLOC, "cudaMallocAsync(%zu): %s", esz * nel, cudaGetErrorString(e));
+            cudaError_t e = ws_alloc(&scratch, esz * nel, st);
+            if (e != cudaSuccess) return fail(QUPS_ERR_ALLOC, "ws_alloc(%zu): %s", esz * nel, cudaGetErrorString(e));
             own = true;
         }
         qups_das_params q = *p;
@@ -243,7 +270,7 @@ static int das_impl(const qups_das_params *p, void *y, const void *Pi, const voi
                 rc = run_das_typed<double2, double2, double2, double>(&q, (double2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 2, 2);
             }
         }
-        if (own) cudaFreeAsync(scratch, st);
+        if (own) ws_free(scratch, st);
         return rc;
     }
 
@@ -261,9 +288,9 @@ static int das_impl(const qups_das_params *p, void *y, const void *Pi, const voi
                     const uint64_t F = p->F ? p->F : 1, nel = p->T * p->N * p->M, I = p->I1 * p->I2 * p->I3;
                     const uint64_t xfs = p->x_frame_stride ? p->x_frame_stride : nel, yfs = p->y_frame_stride ? p->y_frame_stride : I;
                     float2 *xs = nullptr, *ys = nullptr;
-                    cudaError_t e = cudaMallocAsync((void **)&xs, sizeof(float2) * nel, st);
-                    if (e == cudaSuccess && !p->y_f32) e = cudaMallocAsync((void **)&ys, sizeof(float2) * I, st);
-                    if (e != cudaSuccess) { if (xs) cudaFreeAsync(xs, st); return fail(QUPS_ERR_ALLOC, "cudaMallocAsync: %s", cudaGetErrorString(e)); }
+                    cudaError_t e = ws_alloc((void **)&xs, sizeof(float2) * nel, st);
+                    if (e == cudaSuccess && !p->y_f32) e = ws_alloc((void **)&ys, sizeof(float2) * I, st);
+                    if (e != cudaSuccess) { if (xs) ws_free(xs, st); return fail(QUPS_ERR_ALLOC, "cudaMallocAsync: %s", cudaGetErrorString(e)); }
                     qups_das_params q = *p;
                     q.dtype = QUPS_F32; q.F = 1; q.path = QUPS_PATH_TILED;
                     int rc = 0;
@@ -274,8 +301,8 @@ static int das_impl(const qups_das_params *p, void *y, const void *Pi, const voi
                         if (rc == 0 && !p->y_f32)
                             if (int ce = launch_float2_to_half2((__half2 *)y + f * yfs, ys, I, st)) rc = cuda_fail(ce, "float2->half2");
                     }
-                    cudaFreeAsync(xs, st);
-                    if (ys) cudaFreeAsync(ys, st);
+                    ws_free(xs, st);
+                    if (ys) ws_free(ys, st);
                     return rc;
                 }
             }
