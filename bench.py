@@ -102,6 +102,14 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arm must not inherit that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port(P, x_np, budget_s=15.0, threads=None):
     """Time the oracle port of kern/das_spec.m:462-481 on the host cores, bounded sample: all pixels of a
     pixel subset x a transmit subset, scaled to the metric's unit."""
@@ -162,9 +170,9 @@ def main():
         x_np = synth.noise_cube(P.T, P.N, min(P.M, 16))
         vals, tts = [], []
         for _ in range(max(1, a.warmup if a.warmup < 2 else 1)):
-            cpu_port(P, x_np, budget_s=2.0)
+            cpu_port(P, x_np, budget_s=2.0, threads=host_threads())
         for _ in range(max(1, a.steps)):
-            cb, tt = cpu_port(P, x_np, budget_s=max(2.0, 60.0 / max(1, a.steps)))
+            cb, tt = cpu_port(P, x_np, budget_s=max(2.0, 60.0 / max(1, a.steps)), threads=host_threads())
             vals.append(cb["value"]); tts.append(tt)
         cb["value"] = float(np.mean(vals))
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
@@ -407,7 +415,7 @@ def main():
         "pairs_per_s": I_tot * P.N * P.M / (ms_step * 1e-3), "checksum": ysum,
     }
     if not a.no_cpu and world == 1:
-        line["cpu_baseline"], _ = cpu_port(P, x_np[:, :, :min(P.M, 16)], budget_s=15.0)
+        line["cpu_baseline"], _ = cpu_port(P, x_np[:, :, :min(P.M, 16)], budget_s=15.0, threads=host_threads())
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

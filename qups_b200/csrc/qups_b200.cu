@@ -42,7 +42,12 @@ cudaError_t ws_alloc(void **p, size_t bytes, cudaStream_t st) {
         }
         pool = g_pools[dev];
     }
-    return cudaMallocFromPoolAsync(p, bytes, pool, st);
+    e = cudaMallocFromPoolAsync(p, bytes, pool, st);
+    if (e != cudaSuccess) { // fall back to the default pool rather than fail the call
+        (void)cudaGetLastError();
+        e = cudaMallocAsync(p, bytes, st);
+    }
+    return e;
 }
 cudaError_t ws_free(void *p, cudaStream_t st) { return p ? cudaFreeAsync(p, st) : cudaSuccess; }
 
