@@ -240,19 +240,75 @@ class UltrasoundSystem:
         rt = np.float32 if np.asarray(chd.data).dtype in (np.complex64, np.float32) else np.float64
         tau_rx = (dr / c).astype(rt).reshape(Isz + (chd.N, 1), order="F")
         tau_tx = (dv / c).astype(rt).reshape(Isz + (1, chd.M), order="F")
-        # ChannelData.sample2sep (src/ChannelData.m:1414-1445): data lifted to T x 1 x 1 x N x M
+        return self.bfDASLUT(chd, tau_rx, tau_tx, apod, fmod=fmod, interp=interp, keep_tx=keep_tx, keep_rx=keep_rx)
+
+    def bfDASLUT(self, chd: ChannelData, tau_rx, tau_tx=None, *apod, fmod=0.0, interp="cubic", keep_tx=False, keep_rx=False,
+                 bsize=None):
+        """b = bfDASLUT(us, chd, tau_rx, tau_tx, A1..An, 'fmod', 'interp', 'keep_tx', 'keep_rx', 'bsize')
+        (src/UltrasoundSystem.m:4476-4673): look-up-table delay-and-sum.  Validates / reshapes the delay tables (same error
+        identifiers), splices the transmits in blocks of bsize, reduces the apodization per block and hands each block to
+        ChannelData.sample2sep -> wsinterpd2 (src/ChannelData.m:1338-1447, kern/wsinterpd2.m); blocks are summed (or
+        concatenated when keep_tx).  Output I1 x I2 x I3 x [1|N] x [1|M]."""
+        Isz = tuple(self.scan.shape[1:]) + (1,) * (4 - self.scan.ndim)
+        nPix, N, M = int(np.prod(Isz)), chd.N, chd.M
+        tau_rx = np.asarray(tau_rx)
+        tau_tx = np.swapaxes(tau_rx.reshape(tau_rx.shape + (1,) * (5 - tau_rx.ndim)), 3, 4) if tau_tx is None else np.asarray(tau_tx)
+        sz = lambda a, k: tuple(a.shape) + (1,) * (k - a.ndim)
+        if sz(tau_rx, 4)[:4] != Isz + (N,) or tau_rx.ndim > 4 and any(v != 1 for v in tau_rx.shape[4:]):
+            D = tau_rx.ndim
+            I_, L_ = int(np.prod(tau_rx.shape[:D - 1])), tau_rx.shape[D - 1]
+            if I_ == nPix and L_ == N:
+                tau_rx = tau_rx.reshape(Isz + (N,), order="F")
+            else:
+                raise _lib.QupsError(-1, "QUPS:UltrasoundSystem:bfDASLUT:incompatibleReceiveDelayTable: Expected a table with "
+                                     f"{nPix} pixels and {N} receives but instead there are {I_} pixels and {L_} receives.")
+        if sz(tau_tx, 5)[:5] != Isz + (1, M):
+            D = tau_tx.ndim
+            I_, L_ = int(np.prod(tau_tx.shape[:D - 1])), tau_tx.shape[D - 1]
+            if I_ == nPix and L_ == M:
+                tau_tx = tau_tx.reshape(Isz + (1, M), order="F")
+            else:
+                raise _lib.QupsError(-1, "QUPS:UltrasoundSystem:bfDASLUT:incompatibleTransmitDelayTable: Expected a table with "
+                                     f"{nPix} pixels and {M} transmits but instead there are {I_} pixels and {L_} transmits.")
+        tau_rx = tau_rx.reshape(Isz + (N, 1), order="F")
+        tau_tx = tau_tx.reshape(Isz + (1, M), order="F")
+        rt = np.float32 if np.asarray(chd.data).dtype in (np.complex64, np.float32) else np.float64
+        tau_rx, tau_tx = tau_rx.astype(rt), tau_tx.astype(rt)
+        apods = [np.asarray(a) for a in (apod if apod else (1,))]
+        apods = [a.reshape(tuple(a.shape) + (1,) * (5 - a.ndim), order="F") if a.ndim else a.reshape((1,) * 5) for a in apods]
+        for a in apods:
+            if not all(a.shape[d] in (1, (Isz + (N, M))[d]) for d in range(5)):
+                raise AssertionError("Apodization data size inconsistent with the scan / receive / transmit sizes")
+        # sample2sep (src/ChannelData.m:1414-1445): data lifted to T x 1 x 1 x 1 x N x M; ntau = (tau - t0) * fs
         fs, t0 = rt(chd.fs), np.asarray(chd.t0, dtype=rt).reshape(-1)
-        t0b = t0.reshape((1, 1, 1, 1, -1)) if t0.size > 1 else t0.reshape((1,) * 5)
-        ntau_rx = (tau_rx * fs).reshape((1,) + tau_rx.shape, order="F")
-        ntau_tx = ((tau_tx - t0b) * fs).reshape((1,) + tau_tx.shape, order="F")
         x = np.asarray(chd.data)
-        x6 = x.reshape((x.shape[0], 1, 1, 1) + x.shape[1:3], order="F")
-        sdim = tuple(d for d, keep in ((5, keep_rx), (6, keep_tx)) if not keep)
-        w = np.asarray(apod)
-        w = w.reshape((1,) + tuple(w.shape) + (1,) * (5 - w.ndim), order="F") if w.ndim else w
         omega = 2j * np.pi * fmod / float(chd.fs)
-        y = kern.wsinterpd2(x6, ntau_rx, ntau_tx, 1, w, sdim, interp, 0, omega)
-        return y.reshape(y.shape[1:], order="F") if isinstance(y, np.ndarray) else y[0]
+        sdim = tuple(d for d, keep in ((5, keep_rx), (6, keep_tx)) if not keep)
+        ntau_rx = (tau_rx * fs).reshape((1,) + tau_rx.shape, order="F")
+        bsize = M if bsize is None else int(bsize)
+        if bsize < 1: raise ValueError("bsize must be a positive integer")
+        a0 = 1
+        for a in apods:  # apodization common to all transmits is reduced once (:4643-4644)
+            if a.shape[4] == 1: a0 = a0 * a
+        out, acc = [], 0
+        for m0 in range(0, M, bsize):  # splice(chd, mdim, bsize) (:4641)
+            ms = slice(m0, min(M, m0 + bsize))
+            a = a0
+            for ap_ in apods:
+                if ap_.shape[4] != 1: a = a * ap_[:, :, :, :, ms]
+            a = np.asarray(a)
+            w = a.reshape((1,) + tuple(a.shape), order="F") if a.ndim else a
+            t0b = t0[ms].reshape((1, 1, 1, 1, -1)) if t0.size > 1 else t0.reshape((1,) * 5)
+            ntau_tx = ((tau_tx[:, :, :, :, ms] - t0b) * fs).reshape((1,) + Isz + (1, ms.stop - ms.start), order="F")
+            xm = x[:, :, ms]
+            x6 = xm.reshape((xm.shape[0], 1, 1, 1) + xm.shape[1:3], order="F")
+            y = kern.wsinterpd2(x6, ntau_rx, ntau_tx, 1, w, sdim, interp, 0, omega)
+            y = y.reshape(y.shape[1:], order="F") if isinstance(y, np.ndarray) else y[0]
+            if keep_tx: out.append(y)
+            else: acc = acc + y
+        if keep_tx:
+            return np.concatenate(out, axis=4) if isinstance(out[0], np.ndarray) else torch.cat(out, dim=4)
+        return acc
 
     # ---- greens ---------------------------------------------------------------------------------
     def greens(self, scat_pos, scat_amp, c0=None, interp="cubic", R0=None, fsk=None, device=None, sort=True):

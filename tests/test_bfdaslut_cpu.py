@@ -1,0 +1,86 @@
+"""CPU test of the host logic of ultrasound.bfDAS / bfDASLUT (mirror of src/UltrasoundSystem.m:4334-4673): delay tables,
+validation (the reference's error identifiers, test/USTest.m:260-279), transmit blocking (bsize) and apodization reduction.
+The GPU call (kern.wsinterpd2) is replaced by the NumPy oracle's wsinterpd2, so only the mirror's own code is under test;
+the result must equal the oracle's das_spec (kern/das_spec.m CPU branch) up to the table rounding (tau = d/c0 vs cinv*d)."""
+import numpy as np
+import pytest
+
+from tests.util import small_problem, oracle_kwargs, rel_linf
+
+
+@pytest.fixture()
+def cpu_ws2(monkeypatch, oracle_np):
+    from qups_b200 import kern
+    monkeypatch.setattr(kern, "wsinterpd2", lambda *a, **k: oracle_np.wsinterpd2(*a, **k))
+
+
+def _us(P, kind):
+    from qups_b200 import ultrasound as U
+    foc = P["Nv"] if kind == "PW" else P["Pv"]
+    return U.UltrasoundSystem(tx=P["Pv"] if kind == "FSA" else P["Pr"], rx=P["Pr"], seq=U.Sequence(kind, foc, c0=P["c"]), scan=P["Pi"], fs=P["fs"])
+
+
+@pytest.mark.parametrize("kind", ["FC", "PW", "FSA"])
+@pytest.mark.parametrize("keep", [(False, False), (True, False), (False, True)])
+def test_bfdas_equals_das_spec_oracle(cpu_ws2, oracle_np, kind, keep):
+    from qups_b200 import ultrasound as U
+    M = 5
+    P = small_problem(kind, nz=9, nx=7, N=6, M=M, T=160, t0=np.linspace(-1e-7, 2e-7, M))
+    us = _us(P, kind)
+    chd = U.ChannelData(P["x"], P["t0"], P["fs"])
+    keep_rx, keep_tx = keep
+    fun = {(False, False): "DAS", (True, False): "SYN", (False, True): "MUL"}[keep]
+    ref = oracle_np.das_spec(fun, P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp="cubic",
+                             **oracle_kwargs(P["opts"]))
+    ref = ref.reshape(ref.shape[:5])
+    for bsize in (None, 2, 1):
+        b = us.bfDASLUT(chd, *_tables(us, chd), interp="cubic", keep_rx=keep_rx, keep_tx=keep_tx, bsize=bsize)
+        assert b.shape == ref.shape
+        assert rel_linf(b, ref) < 2e-4, (kind, keep, bsize)   # fp32 tables: tau = d / c0 rounds differently from cinv * (dv + dr)
+    b2 = us.bfDAS(chd, interp="cubic", keep_rx=keep_rx, keep_tx=keep_tx)
+    assert rel_linf(b2, ref) < 2e-4
+
+
+def _tables(us, chd):
+    """What bfDAS builds (src/UltrasoundSystem.m:4431-4463), in float64 for the test."""
+    Pv, Nv, _ = us._pos_args()
+    Isz = tuple(us.scan.shape[1:])
+    Pi = np.asarray(us.scan, np.float64).reshape(3, -1, order="F")
+    Pv = np.broadcast_to(np.asarray(Pv, np.float64), (3, chd.M))
+    rv = Pi[:, :, None] - Pv[:, None, :]
+    t = us.seq.type
+    if t in ("DV", "FSA"): dv = np.linalg.norm(rv, axis=0)
+    elif t == "PW": dv = (rv * np.asarray(Nv, np.float64)[:, None, :]).sum(0)
+    else:
+        nf = np.asarray(us.seq.focus, np.float64) - us.tx_offset
+        nf = nf / np.linalg.norm(nf, axis=0, keepdims=True)
+        dv = np.linalg.norm(rv, axis=0) * np.sign((rv * nf[:, None, :]).sum(0))
+    dr = np.linalg.norm(Pi[:, :, None] - np.asarray(us.rx, np.float64)[:, None, :], axis=0)
+    return (dr / us.seq.c0).reshape(Isz + (chd.N,), order="F"), (dv / us.seq.c0).reshape(Isz + (1, chd.M), order="F")
+
+
+def test_bfdaslut_apodization_blocks_and_errors(cpu_ws2, oracle_np):
+    import qups_b200
+    from qups_b200 import ultrasound as U
+    P = small_problem("FC", nz=8, nx=6, N=5, M=4, T=160)
+    us = _us(P, "FC")
+    chd = U.ChannelData(P["x"], P["t0"], P["fs"])
+    trx, ttx = _tables(us, chd)
+    rng = np.random.default_rng(0)
+    Isz = P["Pi"].shape[1:]
+    a_rx = rng.uniform(0, 1, Isz + (5, 1))            # common to all transmits: reduced once
+    a_tx = rng.uniform(0, 1, (1, 1, 1, 1, 4))         # per transmit: sliced per block
+    ref = oracle_np.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp="linear",
+                             apod=[a_rx, a_tx], **oracle_kwargs(P["opts"]))
+    ref = ref.reshape(ref.shape[:5])
+    for bsize in (None, 3, 1):
+        b = us.bfDASLUT(chd, trx, ttx, a_rx, a_tx, interp="linear", bsize=bsize)
+        assert rel_linf(b, ref) < 2e-4
+    # flattened tables are accepted when the element counts match (:4588-4627) ...
+    b = us.bfDASLUT(chd, trx.reshape(-1, 5, order="F"), ttx.reshape(-1, 4, order="F"), a_rx, a_tx, interp="linear")
+    assert rel_linf(b, ref) < 2e-4
+    # ... and rejected with the reference's identifiers otherwise
+    with pytest.raises(qups_b200.QupsError, match="incompatibleReceiveDelayTable"):
+        us.bfDASLUT(chd, trx[:-1], ttx)
+    with pytest.raises(qups_b200.QupsError, match="incompatibleTransmitDelayTable"):
+        us.bfDASLUT(chd, trx, ttx[..., :-1])
