@@ -263,7 +263,7 @@ def main():
         y = run_step()
     kern_name = qups_b200.last_das_kernel()
     barrier()
-    sampler = ClockSampler(local).start() if rank == 0 else None
+    sampler = ClockSampler(local).start()  # every rank samples ITS GPU: a clock-locked / throttled peer must show up in the line
     time.sleep(0.25)
     _lib.launch_count(reset=True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
@@ -288,10 +288,22 @@ def main():
         torch.cuda.synchronize()
         kern_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
     tmax = torch.tensor([ms_total, kern_ms], device=dev, dtype=torch.float64)
+    per_rank_ms = [kern_ms]
     if world > 1:
+        gath = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gath, tmax[1:2].clone())
+        per_rank_ms = [float(g[0]) for g in gath]   # a single slow GPU (clock lock, throttling) is visible in the line
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_step = float(tmax[0]) / a.steps
-    clocks = sampler.stop(tw0, tw1) if sampler else None
+    clocks = sampler.stop(tw0, tw1)
+    if world > 1:  # report the slowest GPU of the job (median SM clock under load) and the union of the throttle reasons
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        meds = [c["sm_mhz"] for c in allc if c and c.get("sm_mhz")]
+        clocks = {"sm_mhz": min(meds) if meds else None,
+                  "sm_max_mhz": max((c["sm_max_mhz"] for c in allc if c and c.get("sm_max_mhz")), default=None),
+                  "reasons": sorted(set(r for c in allc if c for r in c.get("reasons", []))),
+                  "samples": sum(c.get("samples", 0) for c in allc if c), "per_gpu_sm_mhz": [c.get("sm_mhz") if c else None for c in allc]}
     ysum = float(torch.view_as_real(y).abs().sum())
 
     # ---------------- e2e: host buffers through the C ABI (H2D + kernel + D2H timed) ----------------
@@ -408,7 +420,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": kern_name, "kernel_ms": float(tmax[1]),
-                     "bytes_per_launch": bytes_launch, "peak_source": peak_src, "limiter": smem,
+                     "kernel_ms_per_rank": per_rank_ms, "bytes_per_launch": bytes_launch, "peak_source": peak_src, "limiter": smem,
                      "note": "algorithmic (no-reuse gather) bytes per SURVEY.md §8d; neighbouring pixels share "
                              "samples so this legitimately exceeds 1 — the kernel is issue/LDS bound, see DESIGN.md §6"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
