@@ -63,9 +63,6 @@ constexpr int threads_of(int interp) { return (kCW + (interp == 0 ? kPW : 1)) * 
 #ifndef QUPS_STATS
 #define QUPS_STATS 0
 #endif
-#ifndef QUPS_EXP
-#define QUPS_EXP 0
-#endif
 #ifndef QUPS_MAGIC
 #define QUPS_MAGIC 1
 #endif
@@ -78,7 +75,6 @@ constexpr int threads_of(int interp) { return (kCW + (interp == 0 ? kPW : 1)) * 
 #ifndef QUPS_LPA
 #define QUPS_LPA 8
 #endif
-constexpr int kLPA = QUPS_LPA;        // lanes of a warp along the lane axis (32, 16 or 8)
 constexpr int kBarBytes = ((2 * kStages * 8 + 63) / 64) * 64;  // full[] + empty[] mbarriers
 constexpr int kTilePix = kCW * 32 * kR; // pixels per tile; its SHAPE (tA x tB, lane patch lpa) is chosen per call from the pixel spacing
 
@@ -806,11 +802,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                             bytes[q] = (uint32_t)wlen * 8u;
                             dst[q] = slot + at * 8u;
                             soff[q] = dst[q] - (uint32_t)(w0 + tap0) * 8u - magic_off<INTERP>::value;
-#if QUPS_EXP == 2
-                            src[q] = a.x + (abs_al & 0xfffe); // experiment: every window from an L2-resident 512 KB
-#else
                             src[q] = a.x + abs_al;
-#endif
                             return (uint32_t)wlen;
                         };
                         if (cinv_ok && xlo <= xhi) {
