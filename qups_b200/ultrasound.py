@@ -92,6 +92,83 @@ class ChannelData:
     def singleT(self): return self.prep(out="single")
     def halfT(self): return self.prep(out="halfT")
 
+    # ---- sampling (src/ChannelData.m:1230-1447): delays in seconds -> wsinterpd / wsinterpd2 ------------------------------
+    def _lifted(self, apdim):
+        """Data and t0 with the receive / transmit dimensions moved to apdim (1-based), frames behind max(apdim)
+        (swapdimD(chd, [ndim, mdim, 4:D], [apdim, max(apdim) + (1:D-3)]), src/ChannelData.m:1304-1305)."""
+        x = self.data
+        is_t = isinstance(x, torch.Tensor)
+        shp = tuple(x.shape) + (1,) * (3 - x.ndim)
+        D = len(shp)
+        nd = max(apdim) + (D - 3)
+        new = [1] * nd
+        new[0], new[apdim[0] - 1], new[apdim[1] - 1] = shp[0], shp[1], shp[2]
+        for k in range(3, D):
+            new[max(apdim) + (k - 3)] = shp[k]
+        # T, N, M, F.. keep their relative memory order only if apdim is increasing; build by explicit permutation
+        src_of = {0: 0, apdim[0] - 1: 1, apdim[1] - 1: 2}
+        for k in range(3, D):
+            src_of[max(apdim) + (k - 3)] = k
+        xr = x.reshape(shp) if is_t else np.asarray(x).reshape(shp)
+        extra = nd - D
+        xr = xr.reshape(shp + (1,) * extra)
+        free = iter(range(D, nd))
+        perm = [src_of[d] if d in src_of else next(free) for d in range(nd)]
+        xl = xr.permute(*perm) if is_t else np.transpose(xr, perm)
+        t0 = np.asarray(self.t0, np.float64).reshape(-1)
+        t0s = [1] * nd
+        if t0.size > 1:
+            t0s[apdim[1] - 1] = t0.size
+        return xl, t0.reshape(t0s)
+
+    def sample(self, tau, interp="linear", w=1, sdim=(), fmod=0.0, apdim=(2, 3)):
+        """y = sample(chd, tau, interp, w, sdim, fmod, apdim): ntau = (tau - t0) .* fs; wsinterpd(data, ntau, 1, w, sdim,
+        interp, 0, 2i*pi*fmod/fs)   (src/ChannelData.m:1230-1336).  tau: time along dim 1, singleton-or-matching elsewhere."""
+        xl, t0 = self._lifted(tuple(apdim))
+        tau = np.asarray(tau.cpu() if isinstance(tau, torch.Tensor) else tau)
+        nd = max(tau.ndim, xl.ndim)
+        ts, xs = tuple(tau.shape) + (1,) * (nd - tau.ndim), tuple(xl.shape) + (1,) * (nd - xl.ndim)
+        for d in range(1, nd):
+            if not (ts[d] == xs[d] or ts[d] == 1 or xs[d] == 1):
+                raise AssertionError(f"Delay size must match the data size ({xs[d]}) or be singleton in dimension {d + 1}.")
+        rt = np.float32 if (xl.dtype in (torch.complex64, torch.float32) if isinstance(xl, torch.Tensor) else xl.dtype in (np.complex64, np.float32)) else np.float64
+        ntau = ((tau.reshape(ts) - t0.reshape(tuple(t0.shape) + (1,) * (nd - t0.ndim))) * float(self.fs)).astype(rt)
+        return kern.wsinterpd(xl, ntau, 1, w, sdim, interp, 0, 2j * np.pi * fmod / float(self.fs))
+
+    def sample2sep(self, tau1, tau2, interp="linear", w=1, sdim=(), fmod=0.0, apdim=(2, 3)):
+        """Separable delays tau = tau1 + tau2 (src/ChannelData.m:1338-1447): t0 is subtracted from the table that gives the
+        smaller broadcast, then wsinterpd2(data, ntau1, ntau2, 1, w, sdim, interp, 0, 2i*pi*fmod/fs)."""
+        xl, t0 = self._lifted(tuple(apdim))
+        t1, t2 = (np.asarray(t.cpu() if isinstance(t, torch.Tensor) else t) for t in (tau1, tau2))
+        nd = max(t1.ndim, t2.ndim, xl.ndim, t0.ndim)
+        pad = lambda a: a.reshape(tuple(a.shape) + (1,) * (nd - a.ndim))
+        t1, t2, t0 = pad(t1), pad(t2), pad(t0)
+        xs = tuple(xl.shape) + (1,) * (nd - xl.ndim)
+        for tt in (t1, t2):
+            for d in range(1, nd):
+                if not (tt.shape[d] == xs[d] or tt.shape[d] == 1 or xs[d] == 1):
+                    raise AssertionError(f"Delay size must match the data size ({xs[d]}) or be singleton in dimension {d + 1}.")
+        rt = np.float32 if (xl.dtype in (torch.complex64, torch.float32) if isinstance(xl, torch.Tensor) else xl.dtype in (np.complex64, np.float32)) else np.float64
+        fs = float(self.fs)
+        bsz = lambda a: int(np.prod(np.maximum(a.shape, t0.shape)))
+        if bsz(t1) < bsz(t2):
+            n1, n2 = ((t1 - t0) * fs).astype(rt), (t2 * fs).astype(rt)
+        else:
+            n1, n2 = (t1 * fs).astype(rt), ((t2 - t0) * fs).astype(rt)
+        return kern.wsinterpd2(xl, n1, n2, 1, w, sdim, interp, 0, 2j * np.pi * fmod / fs)
+
+    def rectifyt0(self, interp="cubic", t0_=None):
+        """Collapse t0 to a scalar by resampling every transmit onto one time axis (src/ChannelData.m:1205-1228)."""
+        t0 = np.asarray(self.t0, np.float64).reshape(-1)
+        if t0.size <= 1:
+            return ChannelData(self.data, float(t0[0]) if t0.size else 0.0, self.fs)
+        t0_ = float(t0.min()) if t0_ is None else float(t0_)
+        npad = int(np.ceil((t0 - t0_).max() * float(self.fs)))
+        T = self.T + npad
+        tau = (t0_ + np.arange(T) / float(self.fs)).reshape(-1, 1, 1)
+        y = self.sample(tau, interp)        # zeropad(chd, 0, npad) is implicit: samples past the end are 0 (extrapval)
+        return ChannelData(y, t0_, self.fs)
+
 
 @dataclass
 class Sequence:
@@ -279,31 +356,23 @@ class UltrasoundSystem:
         for a in apods:
             if not all(a.shape[d] in (1, (Isz + (N, M))[d]) for d in range(5)):
                 raise AssertionError("Apodization data size inconsistent with the scan / receive / transmit sizes")
-        # sample2sep (src/ChannelData.m:1414-1445): data lifted to T x 1 x 1 x 1 x N x M; ntau = (tau - t0) * fs
-        fs, t0 = rt(chd.fs), np.asarray(chd.t0, dtype=rt).reshape(-1)
-        x = np.asarray(chd.data)
-        omega = 2j * np.pi * fmod / float(chd.fs)
-        sdim = tuple(d for d, keep in ((5, keep_rx), (6, keep_tx)) if not keep)
-        ntau_rx = (tau_rx * fs).reshape((1,) + tau_rx.shape, order="F")
+        t0 = np.asarray(chd.t0, np.float64).reshape(-1)
+        x = chd.data
+        sdim = tuple(d for d, keep in ((4, keep_rx), (5, keep_tx)) if not keep)   # dims to sum after apodization (:4630-4632)
         bsize = M if bsize is None else int(bsize)
         if bsize < 1: raise ValueError("bsize must be a positive integer")
         a0 = 1
         for a in apods:  # apodization common to all transmits is reduced once (:4643-4644)
             if a.shape[4] == 1: a0 = a0 * a
         out, acc = [], 0
-        for m0 in range(0, M, bsize):  # splice(chd, mdim, bsize) (:4641)
+        for m0 in range(0, M, bsize):  # [chds, im] = splice(chd, chd.mdim, bsize) (:4641)
             ms = slice(m0, min(M, m0 + bsize))
             a = a0
-            for ap_ in apods:
+            for ap_ in apods:  # reduce apodization per tx block (:4646-4649)
                 if ap_.shape[4] != 1: a = a * ap_[:, :, :, :, ms]
-            a = np.asarray(a)
-            w = a.reshape((1,) + tuple(a.shape), order="F") if a.ndim else a
-            t0b = t0[ms].reshape((1, 1, 1, 1, -1)) if t0.size > 1 else t0.reshape((1,) * 5)
-            ntau_tx = ((tau_tx[:, :, :, :, ms] - t0b) * fs).reshape((1,) + Isz + (1, ms.stop - ms.start), order="F")
-            xm = x[:, :, ms]
-            x6 = xm.reshape((xm.shape[0], 1, 1, 1) + xm.shape[1:3], order="F")
-            y = kern.wsinterpd2(x6, ntau_rx, ntau_tx, 1, w, sdim, interp, 0, omega)
-            y = y.reshape(y.shape[1:], order="F") if isinstance(y, np.ndarray) else y[0]
+            chdm = ChannelData(x[:, :, ms], t0[ms] if t0.size > 1 else float(t0[0]) if t0.size else 0.0, chd.fs)
+            # bim = sample2sep(chds(m), tau_txm, tau_rx, interp, a, sdim, fmod, [4, 5])   (:4651)
+            y = chdm.sample2sep(tau_tx[:, :, :, :, ms], tau_rx, interp, np.asarray(a), sdim, fmod, (4, 5))
             if keep_tx: out.append(y)
             else: acc = acc + y
         if keep_tx:

@@ -84,3 +84,50 @@ def test_bfdaslut_apodization_blocks_and_errors(cpu_ws2, oracle_np):
         us.bfDASLUT(chd, trx[:-1], ttx)
     with pytest.raises(qups_b200.QupsError, match="incompatibleTransmitDelayTable"):
         us.bfDASLUT(chd, trx, ttx[..., :-1])
+
+
+@pytest.fixture()
+def cpu_ws(monkeypatch, oracle_np):
+    from qups_b200 import kern
+    monkeypatch.setattr(kern, "wsinterpd2", lambda *a, **k: oracle_np.wsinterpd2(*a, **k))
+    monkeypatch.setattr(kern, "wsinterpd", lambda *a, **k: oracle_np.wsinterpd(*a, **k))
+
+
+def test_channeldata_sample_sample2sep_rectifyt0(cpu_ws, oracle_np):
+    """Mirrors of ChannelData.sample / sample2sep / rectifyt0 (src/ChannelData.m:1205-1447) against interp1 written out."""
+    from qups_b200 import ultrasound as U
+    rng = np.random.default_rng(4)
+    T, N, M, fs = 64, 4, 3, 10e6
+    x = (rng.standard_normal((T, N, M)) + 1j * rng.standard_normal((T, N, M))).astype(np.complex64)
+    t0 = np.array([1.03e-6, 1.31e-6, 0.8e-6])   # off the sample grid: no query lands exactly on the first / last sample
+    chd = U.ChannelData(x, t0, fs)
+    tau = (2e-6 + np.arange(9)[:, None, None] * 0.37e-6) + np.zeros((1, N, 1))     # I x N x 1, broadcast over M
+    y = chd.sample(tau, "linear")
+    assert y.shape == (9, N, M)
+    for n in range(N):
+        for m in range(M):
+            ref = oracle_np.interp1(x[:, n, m], 1 + (tau[:, n, 0] - t0[m]) * fs, "linear", 0)
+            assert np.max(np.abs(y[:, n, m] - ref)) < 1e-4
+    # separable: tau1 over (I, N), tau2 over (I, 1, M); sum over receives and transmits with weights
+    t1 = 1.5e-6 + rng.uniform(0, 2e-6, (9, N, 1))
+    t2 = rng.uniform(0, 1e-6, (9, 1, M))
+    w = rng.uniform(0.5, 1, (1, N, M))
+    y2 = chd.sample2sep(t1, t2, "cubic", w, (2, 3))
+    ref = np.zeros(9, np.complex128)
+    for n in range(N):
+        for m in range(M):
+            ref += w[0, n, m] * oracle_np.interp1(x[:, n, m], 1 + (t1[:, n, 0] + t2[:, 0, m] - t0[m]) * fs, "cubic", 0)
+    assert np.max(np.abs(np.asarray(y2).reshape(-1) - ref)) < 2e-4 * np.max(np.abs(ref))
+    # lifted to the beamforming layout (apdim = [4 5]): I1 x I2 x I3 x N x M, as bfDASLUT calls it (:4651)
+    t1b = t1.reshape(9, 1, 1, N, 1)[:, :, :, :, :]
+    y3 = chd.sample2sep(t1.reshape(9, 1, 1, N, 1), t2.reshape(9, 1, 1, 1, M), "cubic", w.reshape(1, 1, 1, N, M), (4, 5), 0.0, (4, 5))
+    assert np.max(np.abs(np.asarray(y3).reshape(-1) - ref)) < 2e-4 * np.max(np.abs(ref))
+    # rectifyt0: one scalar t0, every trace resampled onto the common axis
+    r = chd.rectifyt0("linear")
+    assert r.t0 == pytest.approx(t0.min())
+    tt = r.t0 + np.arange(r.data.shape[0]) / fs
+    for m in range(M):
+        ref = oracle_np.interp1(x[:, 1, m], 1 + (tt - t0[m]) * fs, "linear", 0)
+        assert np.max(np.abs(np.asarray(r.data)[:, 1, m] - ref)) < 1e-4
+    with pytest.raises(AssertionError):
+        chd.sample(np.zeros((5, N + 1, 1)))
