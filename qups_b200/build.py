@@ -57,6 +57,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
     env = dict(os.environ)
     env.pop("CC", None)  # the image exports a gcc wrapper without libgomp; nvcc should use PATH gcc
     env.pop("CXX", None)
+    jobs = []
     for unit, extra in UNITS.items():
         src = os.path.join(CSRC, unit)
         obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
@@ -66,7 +67,12 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)
-            r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+            jobs.append((unit, cmd))
+    if jobs:  # translation units are independent: compile them side by side (das_tiled.cu alone takes about a minute)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            results = list(ex.map(lambda j: (j[0], subprocess.run(j[1], capture_output=True, text=True, env=env)), jobs))
+        for unit, r in results:
             if verbose or r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode != 0:
