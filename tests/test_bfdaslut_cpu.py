@@ -131,3 +131,30 @@ def test_channeldata_sample_sample2sep_rectifyt0(cpu_ws, oracle_np):
         assert np.max(np.abs(np.asarray(r.data)[:, 1, m] - ref)) < 1e-4
     with pytest.raises(AssertionError):
         chd.sample(np.zeros((5, N + 1, 1)))
+
+
+def test_real_mirror_packing_through_the_abi_emulator(monkeypatch, oracle_np):
+    """kern.wsinterpd2's own host code (dim moves, sizes, 5 x D strides, column-major buffers) driven end to end on the CPU:
+    the C-ABI call is interpreted by tests/abi_emulator.py.  Covers the lifted 5-D layout bfDASLUT / sample2sep use."""
+    from tests.abi_emulator import emulated
+    from qups_b200 import kern, ultrasound as U
+    rng = np.random.default_rng(8)
+    with emulated(monkeypatch) as fake:
+        # plain N-D call, time along dim 2, sum over one dim, complex weights and a phasor
+        x = (rng.standard_normal((3, 20, 2)) + 1j * rng.standard_normal((3, 20, 2))).astype(np.complex64)
+        t1 = rng.uniform(2, 15, (3, 5, 1)).astype(np.float32)
+        t2 = rng.uniform(-1, 1, (1, 1, 2)).astype(np.float32)
+        w = (rng.uniform(0.5, 1, (3, 1, 2)) * np.exp(0.3j)).astype(np.complex64)
+        got = kern.wsinterpd2(x, t1, t2, 2, w, (3,), "cubic", 0, 0.4j)
+        ref = oracle_np.wsinterpd2(x, t1, t2, 2, w, (3,), "cubic", 0, 0.4j)
+        assert got.shape == ref.shape and rel_linf(got, ref) < 1e-5
+        # the beamforming layout: bfDAS -> bfDASLUT -> ChannelData.sample2sep(apdim = [4 5]) -> wsinterpd2
+        P = small_problem("FC", nz=5, nx=4, N=4, M=3, T=120, t0=np.array([0.0, 1e-7, -1e-7]))
+        us = _us(P, "FC")
+        chd = U.ChannelData(P["x"], P["t0"], P["fs"])
+        for keep_rx, keep_tx, fun in ((False, False, "DAS"), (True, False, "SYN")):
+            b = us.bfDAS(chd, interp="linear", keep_rx=keep_rx, keep_tx=keep_tx)
+            ref = oracle_np.das_spec(fun, P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp="linear",
+                                     **oracle_kwargs(P["opts"]))
+            assert rel_linf(np.asarray(b), ref.reshape(np.asarray(b).shape)) < 2e-4
+        assert fake.calls >= 3
