@@ -158,3 +158,26 @@ def test_real_mirror_packing_through_the_abi_emulator(monkeypatch, oracle_np):
                                      **oracle_kwargs(P["opts"]))
             assert rel_linf(np.asarray(b), ref.reshape(np.asarray(b).shape)) < 2e-4
         assert fake.calls >= 3
+
+
+def test_sample_and_rectifyt0_through_the_abi_emulator(monkeypatch, oracle_np):
+    """ChannelData.sample / rectifyt0 -> the real kern.wsinterpd (single-table entry point) on the CPU emulator."""
+    from tests.abi_emulator import emulated
+    from qups_b200 import ultrasound as U
+    rng = np.random.default_rng(12)
+    T, N, M, fs = 48, 3, 2, 10e6
+    x = (rng.standard_normal((T, N, M)) + 1j * rng.standard_normal((T, N, M))).astype(np.complex64)
+    t0 = np.array([0.93e-6, 1.27e-6])
+    chd = U.ChannelData(x, t0, fs)
+    with emulated(monkeypatch):
+        tau = (1.5e-6 + np.arange(7)[:, None, None] * 0.41e-6) + np.zeros((1, N, 1))
+        y = np.asarray(chd.sample(tau, "cubic"))
+        for n in range(N):
+            for m in range(M):
+                ref = oracle_np.interp1(x[:, n, m], 1 + (tau[:, n, 0] - t0[m]) * fs, "cubic", 0)
+                assert np.max(np.abs(y[:, n, m] - ref)) < 2e-4
+        r = chd.rectifyt0("linear")
+        tt = r.t0 + np.arange(np.asarray(r.data).shape[0]) / fs
+        for m in range(M):
+            ref = oracle_np.interp1(x[:, 2, m], 1 + (tt - t0[m]) * fs, "linear", 0)
+            assert np.max(np.abs(np.asarray(r.data)[:, 2, m] - ref)) < 1e-4
