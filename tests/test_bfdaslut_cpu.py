@@ -179,5 +179,8 @@ def test_sample_and_rectifyt0_through_the_abi_emulator(monkeypatch, oracle_np):
         r = chd.rectifyt0("linear")
         tt = r.t0 + np.arange(np.asarray(r.data).shape[0]) / fs
         for m in range(M):
-            ref = oracle_np.interp1(x[:, 2, m], 1 + (tt - t0[m]) * fs, "linear", 0)
+            # ntau in the data's precision (single), as ChannelData.sample computes it: the last sample of the earliest
+            # transmit lands exactly on xq == T there, while a float64 evaluation overshoots T by one ulp
+            xq = 1 + ((tt - t0[m]) * fs).astype(np.float32).astype(np.float64)
+            ref = oracle_np.interp1(x[:, 2, m], xq, "linear", 0)
             assert np.max(np.abs(np.asarray(r.data)[:, 2, m] - ref)) < 1e-4
