@@ -69,3 +69,115 @@ def emulated(monkeypatch):
     monkeypatch.setattr(kern.torch, "device", lambda *a, **k: real_device("cpu"))
     monkeypatch.setattr(kern, "_stream", lambda dev: C.c_void_p(0))
     yield fake
+
+
+# ---- qups_das / qups_das_fused -------------------------------------------------------------------------------------------
+def _val(v):
+    return v.value if hasattr(v, "value") else v
+
+
+def _das_emulated(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, fused=None):
+    """Interpret the qups_das argument list (include/qups_b200.h) with the C oracle: rebuild the MATLAB-shaped arrays from the
+    column-major buffers, sizes and strides the mirror packed, run oracle_c.das_spec, write y back column-major."""
+    from oracle import oracle_c, apod_np
+    assert p.dtype == 0, "emulator: fp32 calls only"
+    I1, I2, I3, N, M, T = (int(v) for v in (p.I1, p.I2, p.I3, p.N, p.M, p.T))
+    F, S, I = int(p.F) or 1, int(p.S), int(p.I1 * p.I2 * p.I3)
+    full = (I1, I2, I3, N, M)
+    f32, c64 = np.float32, np.complex64
+    Pi_ = _buf(_val(Pi), 3 * I, f32).reshape((3, I1, I2, I3), order="F")
+    Pr_ = _buf(_val(Pr), 3 * N, f32).reshape((3, N), order="F")
+    Pv4_ = _buf(_val(Pv4), 4 * M, f32).reshape((4, M), order="F")
+    Nv_ = _buf(_val(Nv), 3 * M, f32).reshape((3, M), order="F")
+    tpose = bool(p.flag & 32)
+    xs = (T, M, N, F) if tpose else (T, N, M, F)
+    x_ = _buf(_val(x), T * N * M * F, c64).reshape(xs, order="F")
+    acs = [int(acstride[k]) for k in range(6 + 6 * S)]
+
+    def strided(ptr, st6, dtype):
+        shp = tuple(full[d] if st6[d] else 1 for d in range(5))
+        n = int(np.prod(shp))
+        # the mirror packs every array densely in column-major order, so non-zero strides must be the dense ones
+        acc = 1
+        for d in range(5):
+            if shp[d] != 1:
+                assert st6[d] == acc, ("non-dense stride", st6, shp)
+                acc *= shp[d]
+        b = _buf(_val(ptr) + st6[5] * np.dtype(dtype).itemsize, n, dtype)
+        return b.reshape(shp, order="F")
+
+    c_arr = strided(cinv, acs[:5] + [0], f32)
+    apods = [strided(apod, acs[6 + 6 * s: 12 + 6 * s], f32 if p.apod_real else c64) for s in range(S)]
+    if fused is not None:
+        fa = fused
+        aux = lambda ptr, n: None if not ptr else _buf(ptr, n, f32).copy()
+        lat = None if not fa.lat else _buf(fa.lat, full[fa.lat_dim - 1], f32).astype(np.float64)
+        Pi64, Pn64 = Pi_.astype(np.float64), Pr_.astype(np.float64)
+        if fa.rx_kind in (1, 2):
+            nn = aux(fa.rx_aux, 3 * N).reshape((3, N), order="F").astype(np.float64)
+            th = np.rad2deg(np.arccos(np.float64(fa.rx_p[0]))) if fa.rx_kind == 1 else 90.0 / np.float64(fa.rx_p[0])
+            gen = apod_np.apAcceptanceAngle if fa.rx_kind == 1 else apod_np.apCosineAngle
+            a = gen(Pi64, Pn64, nn, th, literal=False)
+            if fa.rx_kind == 1:  # threshold exactly as passed (cosd(theta) was rounded to fp32 by the caller)
+                a = (apod_np._dircos(Pi64, Pn64, nn, False) >= f32(fa.rx_p[0])).astype(f32)
+            apods.append(a.astype(f32))
+        elif fa.rx_kind == 3:
+            ae = None
+            if fa.rx_p[2]:
+                cs = aux(fa.rx_aux, 2 * N).reshape((2, N), order="F")
+                ae = np.rad2deg(np.arctan2(cs[1].astype(np.float64), cs[0].astype(np.float64)))
+            apods.append(apod_np.apApertureGrowth(Pi64, Pn64, ae=ae, f=fa.rx_p[0], Dmax=fa.rx_p[1], literal=False).astype(f32))
+        elif fa.rx_kind == 4:
+            xn = aux(fa.rx_aux, N).astype(np.float64)
+            xi = apod_np._lateral(Pi64, lat, fa.lat_dim, f32)[..., None]
+            apods.append((np.abs(xi - xn.astype(f32).reshape(1, 1, 1, -1)) <= f32(fa.rx_p[0])).astype(f32))
+        if fa.tx_kind in (1, 2):
+            xv = aux(fa.tx_aux, M)
+            xi = apod_np._lateral(Pi64, lat, fa.lat_dim, f32)[..., None, None]
+            d = np.abs(xi - xv.reshape(1, 1, 1, 1, -1))
+            apods.append(((d < f32(fa.tx_p[0])) if fa.tx_kind == 1 else (d <= f32(fa.tx_p[0]))).astype(f32))
+        elif fa.tx_kind == 3:
+            q = aux(fa.tx_aux, 4 * M).reshape((4, M), order="F")
+            P = Pi_[..., None]
+            x0 = P[0] - q[0] * (P[2] / q[1])
+            x1 = P[0] - q[2] * (P[2] / q[3])
+            lo, hi = f32(fa.tx_p[0]), f32(fa.tx_p[1])
+            apods.append((((lo < x0) | (lo < x1)) & ((x0 <= hi) | (x1 <= hi))).astype(f32)[:, :, :, None, :])
+    keep_rx, keep_tx = bool(p.flag & 8), bool(p.flag & 16)
+    fun = {(False, False): "DAS", (True, False): "SYN", (False, True): "MUL", (True, True): "BF"}[(keep_rx, keep_tx)]
+    interp = {0: "nearest", 1: "linear", 2: "cubic", 3: "lanczos3"}[p.flag & 7]
+    with np.errstate(divide="ignore"):
+        c = (f32(1) / c_arr).astype(f32)
+    out = oracle_c.das_spec(fun, Pi_, Pr_, Pv4_[:3], Nv_, x_, Pv4_[3], p.fs, c, interp=interp, apod=apods, VS=bool(p.vs), DV=bool(p.dv),
+                            fmod=p.fmod, tpose=tpose)
+    On, Om = (N if keep_rx else 1), (M if keep_tx else 1)
+    yb = _buf(_val(y), I * On * Om * F, c64)
+    yb[:] = np.asarray(out, c64).reshape(-1, order="F")
+    return 0
+
+
+def _install_das(fake):
+    fake.last = "none"
+
+    def qups_das(p_ref, y, Pi, Pr, Pv4, Nv, apod, cinv, acs, x, stream):
+        fake.calls += 1
+        fake.last = "das"
+        return _das_emulated(p_ref._obj, y, Pi, Pr, Pv4, Nv, apod, cinv, acs, x)
+
+    def qups_das_fused(p_ref, f_ref, y, Pi, Pr, Pv4, Nv, apod, cinv, acs, x, stream):
+        fake.calls += 1
+        fake.last = "das_fused"
+        return _das_emulated(p_ref._obj, y, Pi, Pr, Pv4, Nv, apod, cinv, acs, x, fused=f_ref._obj)
+
+    fake.qups_das, fake.qups_das_fused = qups_das, qups_das_fused
+    fake.qups_last_das_kernel = lambda: b"emulated"
+
+
+_orig_emulated = emulated
+
+
+@contextlib.contextmanager
+def emulated(monkeypatch):  # noqa: F811  (extends the context above with the DAS entry points)
+    with _orig_emulated(monkeypatch) as fake:
+        _install_das(fake)
+        yield fake

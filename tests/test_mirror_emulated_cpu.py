@@ -1,0 +1,74 @@
+"""CPU tests of the REAL das_spec mirror (qups_b200/kern.py: option parsing, input lifting, broadcast checks, the [cstride,
+astride] matrix of kern/das_spec.m:256-260, column-major packing, the FusedApod parameter block) with the C-ABI call
+interpreted by tests/abi_emulator.py and evaluated by the C oracle.  What is under test is the boundary packing."""
+import numpy as np
+import pytest
+
+from tests.util import small_problem, oracle_kwargs, rel_linf
+
+f32 = np.float32
+
+
+def _call(fun, P, interp, *extra, x=None, t0=None, c=None):
+    import qups_b200
+    return qups_b200.das_spec(fun, P["Pi"].astype(f32), P["Pr"].astype(f32), P["Pv"].astype(f32), P["Nv"].astype(f32),
+                              P["x"] if x is None else x, P["t0"] if t0 is None else t0, P["fs"], P["c"] if c is None else c,
+                              *P["opts"], "interp", interp, *extra)
+
+
+@pytest.mark.parametrize("kind", ["FC", "PW", "FSA"])
+def test_das_spec_packing_all_funs(monkeypatch, oracle_c, kind):
+    from tests.abi_emulator import emulated
+    P = small_problem(kind, nz=7, nx=5, ny=2, N=4, M=3, T=120, F=2)
+    rng = np.random.default_rng(1)
+    Isz = P["Pi"].shape[1:]
+    apods = [rng.uniform(0, 1, Isz + (4, 1)).astype(f32), rng.uniform(0, 1, (1, 1, 1, 1, 3)).astype(f32),
+             (rng.uniform(0, 1, (Isz[0], 1, 1, 4, 3)) > 0.3).astype(f32)]
+    c = rng.uniform(1500, 1580, Isz).astype(f32)
+    t0 = rng.uniform(-2e-7, 2e-7, 3)
+    extra = sum((("apod", a) for a in apods), ())
+    with emulated(monkeypatch) as fake:
+        for fun in ("DAS", "SYN", "MUL", "BF"):
+            got = _call(fun, P, "cubic", *extra, t0=t0, c=c)
+            ref = oracle_c.das_spec(fun, P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], t0, P["fs"], c, interp="cubic", apod=apods,
+                                    **oracle_kwargs(P["opts"]))
+            assert got.shape == ref.shape, fun
+            assert rel_linf(got, ref) < 1e-5, fun
+        xt = np.asfortranarray(np.swapaxes(P["x"], 1, 2))
+        got = _call("DAS", P, "linear", "transpose", True, x=xt, t0=t0)
+        ref = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], t0, P["fs"], P["c"], interp="linear",
+                                **oracle_kwargs(P["opts"]))
+        assert rel_linf(got, ref) < 1e-5
+        ac = (apods[0] * np.exp(0.3j)).astype(np.complex64)    # complex weights: the type the reference GPU branch forces
+        got = _call("DAS", P, "linear", "apod", ac)
+        ref = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp="linear", apod=[ac],
+                                **oracle_kwargs(P["opts"]))
+        assert rel_linf(got, ref) < 1e-5
+        assert fake.calls == 6 and fake.last == "das"
+
+
+def test_fused_apod_block_packing(monkeypatch, oracle_c):
+    """FusedApod._struct: kinds, parameters and the column-major aux arrays reach the ABI as include/qups_b200.h documents."""
+    from tests.abi_emulator import emulated
+    from oracle import apod_np
+    from qups_b200 import ultrasound as U
+    P = small_problem("FC", nz=12, nx=10, N=6, M=4, T=160, zlim=(2e-3, 9e-3))
+    nn = np.stack([np.sin(np.deg2rad(np.linspace(-8, 8, 6))), np.zeros(6), np.cos(np.deg2rad(np.linspace(-8, 8, 6)))])
+    us = U.UltrasoundSystem(tx=P["Pr"], rx=P["Pr"], seq=U.Sequence("FC", P["Pv"]), scan=P["Pi"], fs=P["fs"], rx_normal=nn)
+    okw = oracle_kwargs(P["opts"])
+    cases = [(us.apAcceptanceAngle(28.0), [apod_np.apAcceptanceAngle(P["Pi"], P["Pr"], nn, 28.0, literal=False)]),
+             (us.apApertureGrowth(1.1, 2e-3), [apod_np.apApertureGrowth(P["Pi"], P["Pr"], f=1.1, Dmax=2e-3, literal=False)]),
+             (us.apScanline(0.6e-3), [apod_np.apScanline(P["Pi"], P["Pv"][0], 0.6e-3, literal=False)]),
+             (us.apTranslatingAperture((0.6e-3, 0.8e-3)), [apod_np.apTranslatingAperture(P["Pi"], P["Pv"][0], P["Pr"][0], (0.6e-3, 0.8e-3), literal=False)]),
+             (us.apTxParallelogram(np.linspace(-9, 9, 4), (-3.0, 3.0), (-0.7e-3, 0.7e-3)),
+              [apod_np.apTxParallelogram(P["Pi"], np.linspace(-9, 9, 4), (-3.0, 3.0), (-0.7e-3, 0.7e-3), literal=False)]),
+             (us.apCosineAngle(33.0).merged(us.apScanline(0.6e-3)),
+              [apod_np.apCosineAngle(P["Pi"], P["Pr"], nn, 33.0, literal=False), apod_np.apScanline(P["Pi"], P["Pv"][0], 0.6e-3, literal=False)])]
+    with emulated(monkeypatch) as fake:
+        for spec, dense in cases:
+            got = _call("DAS", P, "linear", "apod", spec)
+            assert fake.last == "das_fused"
+            ref = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp="linear",
+                                    apod=[np.asarray(a, f32) for a in dense], **okw)[..., 0]
+            assert np.any(ref != 0)
+            assert rel_linf(got, ref) < 1e-5, spec.name
