@@ -72,3 +72,24 @@ def test_fused_apod_block_packing(monkeypatch, oracle_c):
                                     apod=[np.asarray(a, f32) for a in dense], **okw)[..., 0]
             assert np.any(ref != 0)
             assert rel_linf(got, ref) < 1e-5, spec.name
+
+
+def test_l4_das_output_layout_and_apod_arguments(monkeypatch, oracle_c):
+    """UltrasoundSystem.DAS (src/UltrasoundSystem.m:3172-3372): argument assembly per sequence type, apodization arguments
+    (arrays and closed-form blocks mixed), output permute to I1 x I2 x I3 x F.. x [N] x [M]  (:3361)."""
+    from tests.abi_emulator import emulated
+    from oracle import apod_np
+    from qups_b200 import ultrasound as U
+    P = small_problem("FC", nz=9, nx=8, N=5, M=4, T=140, F=2, zlim=(2e-3, 8e-3))
+    us = U.UltrasoundSystem(tx=P["Pr"], rx=P["Pr"], seq=U.Sequence("FC", P["Pv"], P["c"]), scan=P["Pi"], fs=P["fs"])
+    chd = U.ChannelData(P["x"], P["t0"], P["fs"])
+    Pv, Nv, _ = us._pos_args()
+    w = np.random.default_rng(2).uniform(0.3, 1, (1, 1, 1, 5, 1)).astype(f32)
+    A = apod_np.apApertureGrowth(P["Pi"], P["Pr"], f=1.2, literal=False).astype(f32)
+    with emulated(monkeypatch):
+        for keep_rx, keep_tx, fun in ((False, False, "DAS"), (True, False, "SYN"), (False, True, "MUL")):
+            b = us.DAS(chd, w, us.apApertureGrowth(1.2), interp="linear", keep_rx=keep_rx, keep_tx=keep_tx)
+            ref = oracle_c.das_spec(fun, P["Pi"], P["Pr"], Pv, Nv, P["x"], P["t0"], P["fs"], P["c"], interp="linear", apod=[w, A])
+            ref = np.transpose(ref, [0, 1, 2, 5, 3, 4])      # I1 x I2 x I3 x N x M x F  ->  I1 x I2 x I3 x F x N x M
+            assert b.shape == ref.shape == P["Pi"].shape[1:] + (2, 5 if keep_rx else 1, 4 if keep_tx else 1)
+            assert rel_linf(b, ref) < 1e-5, fun
