@@ -181,3 +181,39 @@ def emulated(monkeypatch):  # noqa: F811  (extends the context above with the DA
     with _orig_emulated(monkeypatch) as fake:
         _install_das(fake)
         yield fake
+
+
+# ---- qups_greens -------------------------------------------------------------------------------------------------------------
+def _install_greens(fake):
+    def qups_greens(p_ref, y, Pi, a, Pr, Pv, kern, stream):
+        from oracle import oracle_c
+        p = p_ref._obj
+        fake.calls += 1
+        assert p.dtype == 0 and int(p.E) in (0, 1), "emulator: fp32, E = 1"
+        I, S, K, N, M = (int(v) for v in (p.I, p.S, p.T, p.N, p.M))
+        f32, c64 = np.float32, np.complex64
+        ps = _buf(_val(Pi), 3 * I, f32).reshape((3, I), order="F")
+        amp = _buf(_val(a), I, f32)
+        pn = _buf(_val(Pr), 3 * N, f32).reshape((3, N), order="F")
+        pv = _buf(_val(Pv), 3 * M, f32).reshape((3, M), order="F")
+        kn = _buf(_val(kern), K, c64)
+        interp = {0: "nearest", 1: "linear", 2: "cubic"}[int(p.interp)]
+        out = oracle_c.greens(ps, amp, pn, pv, kn, int(p.n0), S, p.fs, p.c0, p.t0x, p.fsr, p.R0, interp)   # S x N x M
+        _buf(_val(y), S * N * M, c64)[:] = np.asarray(out, c64).reshape(-1, order="F")
+        return 0
+
+    fake.qups_greens = qups_greens
+
+
+_emulated_das = emulated
+
+
+@contextlib.contextmanager
+def emulated(monkeypatch):  # noqa: F811  (adds the greens entry point and the device plumbing of ultrasound.py)
+    from qups_b200 import ultrasound
+    with _emulated_das(monkeypatch) as fake:
+        _install_greens(fake)
+        real_device = type(torch.zeros(1).device)
+        monkeypatch.setattr(ultrasound.torch, "device", lambda *a, **k: real_device("cpu"))
+        monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: type("S", (), {"cuda_stream": 0})())
+        yield fake

