@@ -119,3 +119,28 @@ def test_l4_greens_time_axis_and_known_answers(monkeypatch):
         b = np.abs(np.asarray(us.DAS(chd, interp="cubic")))[:, :, 0, 0, 0]
         iz, ix = np.unravel_index(np.argmax(b), b.shape)
         assert abs(xs[ix] - 1e-3) <= 1.1e-3 and abs(zs[iz] - 15e-3) <= 1.1e-3
+
+
+@pytest.mark.parametrize("seqtype", ["PW", "FC"])
+def test_l4_greens_focustx_das_psf(monkeypatch, seqtype):
+    """greens (FSA simulation) -> focusTx (src/UltrasoundSystem.m:3374-3503: delay-and-sum over the transmit ELEMENTS with the
+    sequence's delays / apodization, one wsinterpd2 call) -> DAS with the sequence's own delay model: the point target must
+    image where it is (test/BFTest.m:230-317, 1.1 mm), for plane-wave and focused sequences, on the CPU emulator."""
+    from tests.abi_emulator import emulated
+    from qups_b200 import synth
+    from qups_b200.ultrasound import UltrasoundSystem, Sequence
+    c0, N = 1500.0, 12
+    pn = synth.linear_array(N, 0.3e-3)
+    if seqtype == "PW":
+        th = np.deg2rad(np.array([-6.0, 0.0, 6.0]))
+        focus = np.stack([np.sin(th), 0 * th, np.cos(th)])
+    else:
+        focus = np.stack([np.array([-0.6e-3, 0.0, 0.6e-3]), np.zeros(3), np.full(3, 14e-3)])
+    xs, zs = np.linspace(-2e-3, 3e-3, 21), np.linspace(12e-3, 18e-3, 25)
+    with emulated(monkeypatch):
+        us = UltrasoundSystem(tx=pn, rx=pn, seq=Sequence(seqtype, focus, c0), scan=synth.scan_cartesian(xs, zs), fs=25e6, fc=6.25e6)
+        chd = us.greens(np.array([[0.5e-3], [0.0], [15e-3]]), np.ones(1), c0=c0, interp="linear")
+        assert chd.M == 3 and chd.N == N
+        b = np.abs(np.asarray(us.DAS(chd, interp="cubic")))[:, :, 0, 0, 0]
+        iz, ix = np.unravel_index(np.argmax(b), b.shape)
+        assert abs(xs[ix] - 0.5e-3) <= 1.1e-3 and abs(zs[iz] - 15e-3) <= 1.1e-3
