@@ -239,3 +239,65 @@ def emulated(monkeypatch):  # noqa: F811  (adds the greens entry point and the d
         monkeypatch.setattr(ultrasound.torch, "device", lambda *a, **k: real_device("cpu"))
         monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: type("S", (), {"cuda_stream": 0})())
         yield fake
+
+
+# ---- qups_chd_prep / qups_aperture / qups_apod_generate ------------------------------------------------------------------------
+def _install_misc(fake):
+    def qups_chd_prep(p_ref, out, inp, t0, stream):
+        from oracle import prep_np
+        p = p_ref._obj
+        fake.calls += 1
+        T, K, B, A = (int(v) for v in (p.T, p.K, p.B, p.A))
+        L = B + T + A
+        dt = {0: np.float32, 1: np.complex64, 2: np.int16, 3: np.float64}[int(p.in_dtype)]
+        x = _buf(_val(inp), T * K, dt).reshape((T, K), order="F")
+        n_t0, per = int(p.n_t0) or 1, int(p.traces_per_t0) or 1
+        t0v = _buf(_val(t0), n_t0, np.float32).astype(np.float64) if _val(t0) else np.zeros(1)
+        # trace k uses t0[(k / traces_per_t0) % n_t0]: evaluate the oracle per distinct t0
+        y = np.zeros((L, K), np.complex64)
+        for j in range(n_t0):
+            sel = [k for k in range(K) if (k // per) % n_t0 == j]
+            if not sel:
+                continue
+            xs = x[:, sel]
+            xs = xs if np.iscomplexobj(xs) and not p.hilbert else np.real(xs).astype(np.float64) if p.hilbert else xs
+            yy, _ = prep_np.prep(xs.reshape(T, len(sel), 1), float(t0v[j]), p.fs, B=B, A=A, hilbert=bool(p.hilbert), fmix=p.fmix)
+            y[:, sel] = yy[:, :, 0]
+        if int(p.out_dtype) == 1:   # half2 storage
+            ob = _buf(_val(out), 2 * L * K, np.float16)
+            ob[0::2] = y.real.reshape(-1, order="F").astype(np.float16)
+            ob[1::2] = y.imag.reshape(-1, order="F").astype(np.float16)
+        else:
+            _buf(_val(out), L * K, np.complex64)[:] = y.reshape(-1, order="F")
+        return 0
+
+    def qups_aperture(p_ref, out, out2, b, lags, stream):
+        from oracle import aperture_np as apd
+        p = p_ref._obj
+        fake.calls += 1
+        Cn, A, Sn = int(p.C), int(p.A), int(p.S)
+        cdt, rdt = (np.complex128, np.float64) if p.dtype == 2 else (np.complex64, np.float32)
+        x = _buf(_val(b), Cn * A * Sn, cdt).reshape((Cn, A, Sn), order="F")
+        lg = [int(lags[k]) for k in range(int(p.nlags))]
+        op = int(p.op)
+        if op == 0: r = apd.cohfac(x, 2)
+        elif op == 1: r = apd.dmas(x, 2, lg if lg else [A + 1])
+        elif op == 2: r, sf = apd.pcf(x, 2, p.gamma)
+        else: r = apd.slsc(x, 2, lg, "average" if op == 3 else "ensemble")
+        cplx = op in (1, 3, 4)
+        _buf(_val(out), Cn * Sn, cdt if cplx else rdt)[:] = np.asarray(r).reshape(-1, order="F").astype(cdt if cplx else rdt)
+        if op == 2 and _val(out2):
+            _buf(_val(out2), Cn * Sn, rdt)[:] = np.asarray(sf).reshape(-1, order="F").astype(rdt)
+        return 0
+
+    fake.qups_chd_prep, fake.qups_aperture = qups_chd_prep, qups_aperture
+
+
+_emulated_greens = emulated
+
+
+@contextlib.contextmanager
+def emulated(monkeypatch):  # noqa: F811  (adds the pre-processing and aperture entry points)
+    with _emulated_greens(monkeypatch) as fake:
+        _install_misc(fake)
+        yield fake

@@ -144,3 +144,31 @@ def test_l4_greens_focustx_das_psf(monkeypatch, seqtype):
         b = np.abs(np.asarray(us.DAS(chd, interp="cubic")))[:, :, 0, 0, 0]
         iz, ix = np.unravel_index(np.argmax(b), b.shape)
         assert abs(xs[ix] - 0.5e-3) <= 1.1e-3 and abs(zs[iz] - 15e-3) <= 1.1e-3
+
+
+def test_prep_and_aperture_mirrors_packing(monkeypatch):
+    """ChannelData.prep / zeropad / hilbert / downmix and kern.cohfac / dmas / pcf / slsc: the C x A x S view, lag lists, per-transmit
+    t0 indexing and column-major buffers the mirrors hand to qups_chd_prep / qups_aperture, interpreted on the CPU."""
+    import qups_b200
+    from tests.abi_emulator import emulated
+    from oracle import prep_np, aperture_np as apd
+    from qups_b200 import ultrasound as U
+    rng = np.random.default_rng(6)
+    with emulated(monkeypatch):
+        x = rng.integers(-500, 500, (40, 3, 2)).astype(np.int16)
+        t0 = np.array([1.0e-6, 1.4e-6])
+        chd = U.ChannelData(x, t0, 10e6)
+        y = chd.prep(B=3, A=21, hilbert=True, fmix=2e6)
+        ref, t0p = prep_np.prep(x.astype(np.float64), t0, 10e6, B=3, A=21, hilbert=True, fmix=2e6)
+        assert np.asarray(y.data).shape == ref.shape and rel_linf(np.asarray(y.data), ref) < 1e-6 and np.allclose(y.t0, t0p)
+        z = chd.zeropad(2, 5)
+        assert np.asarray(z.data).shape == (47, 3, 2) and np.array_equal(np.asarray(z.data)[2:42], x.astype(np.complex64))
+        b = (rng.standard_normal((4, 3, 7, 2)) + 1j * rng.standard_normal((4, 3, 7, 2))).astype(np.complex64)
+        for dim in (1, 3, 4):
+            assert rel_linf(qups_b200.cohfac(b, dim), apd.cohfac(b, dim)) < 1e-5
+            assert rel_linf(qups_b200.dmas(b, dim, 2), apd.dmas(b, dim, 2)) < 1e-5
+            w, sf = qups_b200.pcf(b, dim, 0.6)
+            wr, sfr = apd.pcf(b, dim, 0.6)
+            assert rel_linf(w, wr) < 1e-5 and rel_linf(sf, sfr) < 1e-5
+            assert rel_linf(qups_b200.slsc(b, dim, [1, 2], "ensemble"), apd.slsc(b, dim, [1, 2], "ensemble")) < 1e-5
+        assert qups_b200.cohfac(b).shape == (4, 3, 7, 1)          # default: last non-singleton dimension
