@@ -191,6 +191,11 @@ class UltrasoundSystem:
     tx_normal: np.ndarray = field(default_factory=lambda: np.array([[0.0], [0.0], [1.0]]))
     rx_normal: Optional[np.ndarray] = None   # 3 x N element normals (3rd output of Transducer.orientations); default +z
     rx_angle: Optional[np.ndarray] = None    # N element azimuth angles in degrees (1st output of orientations); default 0
+    # ScanPolar-style lateral coordinates for apScanline / apTranslatingAperture (src/UltrasoundSystem.m:4951-4953, 5103-5109):
+    # pixel angle per index along scan_lat_dim (scan.a), transmit angles (seq.angles); None -> Cartesian x coordinates
+    scan_lat: Optional[np.ndarray] = None
+    scan_lat_dim: int = 2
+    tx_lat: Optional[np.ndarray] = None
 
     # ---- apodization generators (src/UltrasoundSystem.m:4892-5429) --------------------------------
     # Each returns a kern.FusedApod: pass it to DAS as an apodization argument (evaluated inside the kernel), or call
@@ -198,6 +203,9 @@ class UltrasoundSystem:
     def _rx_normals(self):
         n = self.rx.shape[1]
         return np.broadcast_to(np.array([[0.0], [0.0], [1.0]]), (3, n)) if self.rx_normal is None else np.asarray(self.rx_normal, np.float64)
+
+    def _tx_lateral(self):
+        return np.asarray(self.tx_lat, np.float64).reshape(-1) if self.tx_lat is not None else np.asarray(self.seq.focus, np.float64)[0]
 
     def apAcceptanceAngle(self, theta=45.0):
         """apod = (n . (Pi - Pn)/|Pi - Pn|) >= cosd(theta)   (:5303-5375)."""
@@ -222,15 +230,18 @@ class UltrasoundSystem:
     def apScanline(self, tol):
         """apod = |x_i - x_focus(m)| < tol   (:4892-4968)."""
         if not tol > 0: raise ValueError("tol must be positive")
-        return kern.FusedApod(tx_kind=_lib.AP_TX_SCANLINE, tx_p=(np.float32(tol),), tx_aux=np.asarray(self.seq.focus, np.float64)[0], name="apScanline")
+        return kern.FusedApod(tx_kind=_lib.AP_TX_SCANLINE, tx_p=(np.float32(tol),), tx_aux=self._tx_lateral(), lat=self.scan_lat,
+                              lat_dim=self.scan_lat_dim, name="apScanline")
 
     def apTranslatingAperture(self, tol):
         """apod = |x_i - x_focus(m)| <= tol(1) & |x_i - x_n| <= tol(end)   (:5074-5163)."""
         tol = np.atleast_1d(np.asarray(tol, np.float64))
         if not np.all(tol > 0): raise ValueError("tol must be positive")
-        return kern.FusedApod(rx_kind=_lib.AP_RX_TRANSLATING, rx_p=(np.float32(tol[-1]),), rx_aux=np.asarray(self.rx, np.float64)[0],
-                              tx_kind=_lib.AP_TX_TRANSLATING, tx_p=(np.float32(tol[0]),), tx_aux=np.asarray(self.seq.focus, np.float64)[0],
-                              name="apTranslatingAperture")
+        polar = self.scan_lat is not None  # ScanPolar: receivers are compared by their orientation angle (:5108)
+        rx_lat = np.asarray(self.rx_angle, np.float64).reshape(-1) if polar and self.rx_angle is not None else np.asarray(self.rx, np.float64)[0]
+        return kern.FusedApod(rx_kind=_lib.AP_RX_TRANSLATING, rx_p=(np.float32(tol[-1]),), rx_aux=rx_lat,
+                              tx_kind=_lib.AP_TX_TRANSLATING, tx_p=(np.float32(tol[0]),), tx_aux=self._tx_lateral(),
+                              lat=self.scan_lat, lat_dim=self.scan_lat_dim, name="apTranslatingAperture")
 
     def apTxParallelogram(self, theta=None, phi=0.0, bounds=None):
         """Pixels whose projection along the (tilted) transmit direction lands on the aperture   (:5269-5301)."""

@@ -172,3 +172,31 @@ def test_prep_and_aperture_mirrors_packing(monkeypatch):
             assert rel_linf(w, wr) < 1e-5 and rel_linf(sf, sfr) < 1e-5
             assert rel_linf(qups_b200.slsc(b, dim, [1, 2], "ensemble"), apd.slsc(b, dim, [1, 2], "ensemble")) < 1e-5
         assert qups_b200.cohfac(b).shape == (4, 3, 7, 1)          # default: last non-singleton dimension
+
+
+def test_polar_lateral_coordinates_reach_the_abi(monkeypatch, oracle_c):
+    """ScanPolar-style apScanline / apTranslatingAperture: pixel angles per index along the lateral dimension (scan.a), transmit
+    angles (seq.angles) and receiver orientations travel as lat / tx_aux / rx_aux (src/UltrasoundSystem.m:4951-4953, 5103-5109)."""
+    from tests.abi_emulator import emulated
+    from qups_b200 import ultrasound as U
+    P = small_problem("FC", nz=10, nx=9, N=6, M=4, T=160, zlim=(2e-3, 9e-3))
+    ang_px = np.linspace(-20, 20, 9)            # degrees, one per image column (dim 2)
+    ang_tx = np.array([-12.0, -4.0, 4.0, 12.0])
+    ang_rx = np.linspace(-15, 15, 6)
+    us = U.UltrasoundSystem(tx=P["Pr"], rx=P["Pr"], seq=U.Sequence("FC", P["Pv"]), scan=P["Pi"], fs=P["fs"], rx_angle=ang_rx,
+                            scan_lat=ang_px, scan_lat_dim=2, tx_lat=ang_tx)
+    Isz = P["Pi"].shape[1:]
+    xi = np.broadcast_to(ang_px.astype(f32).reshape(1, -1, 1), Isz)[..., None, None]
+    a_tx = (np.abs(xi - ang_tx.astype(f32).reshape(1, 1, 1, 1, -1)) <= f32(4.5)).astype(f32)
+    a_rx = (np.abs(xi - ang_rx.astype(f32).reshape(1, 1, 1, -1, 1)) <= f32(11.0)).astype(f32)
+    a_sc = (np.abs(xi - ang_tx.astype(f32).reshape(1, 1, 1, 1, -1)) < f32(4.5)).astype(f32)
+    okw = oracle_kwargs(P["opts"])
+    with emulated(monkeypatch):
+        got = _call("DAS", P, "linear", "apod", us.apTranslatingAperture((4.5, 11.0)))
+        ref = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp="linear",
+                                apod=[a_tx, a_rx], **okw)[..., 0]
+        assert np.any(ref != 0) and rel_linf(got, ref) < 1e-5
+        got = _call("DAS", P, "linear", "apod", us.apScanline(4.5))
+        ref = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp="linear",
+                                apod=[a_sc], **okw)[..., 0]
+        assert rel_linf(got, ref) < 1e-5
