@@ -22,6 +22,7 @@ void count_launch(uint64_t n) { g_launches += n; }
 
 static std::mutex g_pool_mu;
 static cudaMemPool_t g_pools[64] = {};
+static bool g_pool_failed[64] = {};
 cudaError_t ws_alloc(void **p, size_t bytes, cudaStream_t st) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -30,13 +31,18 @@ cudaError_t ws_alloc(void **p, size_t bytes, cudaStream_t st) {
     cudaMemPool_t pool;
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool_failed[dev]) return cudaMallocAsync(p, bytes, st);
         if (!g_pools[dev]) {
             cudaMemPoolProps props = {};
             props.allocType = cudaMemAllocationTypePinned;
             props.handleTypes = cudaMemHandleTypeNone;
             props.location.type = cudaMemLocationTypeDevice;
             props.location.id = dev;
-            if ((e = cudaMemPoolCreate(&g_pools[dev], &props)) != cudaSuccess) { g_pools[dev] = nullptr; return cudaMallocAsync(p, bytes, st); }
+            if ((e = cudaMemPoolCreate(&g_pools[dev], &props)) != cudaSuccess) { // no pool on this device: default pool from now on
+                (void)cudaGetLastError();
+                g_pools[dev] = nullptr; g_pool_failed[dev] = true;
+                return cudaMallocAsync(p, bytes, st);
+            }
             uint64_t keep = UINT64_MAX;
             cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
         }
