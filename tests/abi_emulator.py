@@ -301,3 +301,70 @@ def emulated(monkeypatch):  # noqa: F811  (adds the pre-processing and aperture 
     with _emulated_greens(monkeypatch) as fake:
         _install_misc(fake)
         yield fake
+
+
+# ---- qups_apod_generate ----------------------------------------------------------------------------------------------------------
+def _install_apodgen(fake):
+    def qups_apod_generate(f_ref, which, out, as_complex, Pi, Pr, I1, I2, I3, NM, stream):
+        """Dense image of a closed-form apodization, from the canonical-fp32 oracle (same reconstruction as _das_emulated)."""
+        fa = f_ref._obj
+        fake.calls += 1
+        I1, I2, I3, NM = int(I1), int(I2), int(I3), int(NM)
+        I = I1 * I2 * I3
+        f32 = np.float32
+        Pi_ = _buf(_val(Pi), 3 * I, f32).reshape((3, I1, I2, I3), order="F")
+        from oracle import apod_np
+        Pi64 = Pi_.astype(np.float64)
+        lat = None if not fa.lat else _buf(fa.lat, (I1, I2, I3)[fa.lat_dim - 1], f32).astype(np.float64)
+        if int(which) == 0:
+            Pn = _buf(_val(Pr), 3 * NM, f32).reshape((3, NM), order="F").astype(np.float64)
+            if fa.rx_kind in (1, 2):
+                nn = _buf(fa.rx_aux, 3 * NM, f32).reshape((3, NM), order="F").astype(np.float64)
+                if fa.rx_kind == 1:
+                    a = (apod_np._dircos(Pi64, Pn, nn, False) >= f32(fa.rx_p[0])).astype(f32)
+                else:
+                    a = apod_np.apCosineAngle(Pi64, Pn, nn, 90.0 / np.float64(fa.rx_p[0]), literal=False)
+            elif fa.rx_kind == 3:
+                ae = None
+                if fa.rx_p[2]:
+                    cs = _buf(fa.rx_aux, 2 * NM, f32).reshape((2, NM), order="F")
+                    ae = np.rad2deg(np.arctan2(cs[1].astype(np.float64), cs[0].astype(np.float64)))
+                a = apod_np.apApertureGrowth(Pi64, Pn, ae=ae, f=fa.rx_p[0], Dmax=fa.rx_p[1], literal=False)
+            elif fa.rx_kind == 4:
+                xn = _buf(fa.rx_aux, NM, f32)
+                xi = apod_np._lateral(Pi64, lat, fa.lat_dim, f32)[..., None]
+                a = (np.abs(xi - xn.reshape(1, 1, 1, -1)) <= f32(fa.rx_p[0]))
+            else:
+                a = np.ones((I1, I2, I3, NM))
+        else:
+            if fa.tx_kind in (1, 2):
+                xv = _buf(fa.tx_aux, NM, f32)
+                xi = apod_np._lateral(Pi64, lat, fa.lat_dim, f32)[..., None]
+                d = np.abs(xi - xv.reshape(1, 1, 1, -1))
+                a = (d < f32(fa.tx_p[0])) if fa.tx_kind == 1 else (d <= f32(fa.tx_p[0]))
+            elif fa.tx_kind == 3:
+                q = _buf(fa.tx_aux, 4 * NM, f32).reshape((4, NM), order="F")
+                P_ = Pi_[..., None]
+                x0, x1 = P_[0] - q[0] * (P_[2] / q[1]), P_[0] - q[2] * (P_[2] / q[3])
+                lo, hi = f32(fa.tx_p[0]), f32(fa.tx_p[1])
+                a = ((lo < x0) | (lo < x1)) & ((x0 <= hi) | (x1 <= hi))
+            else:
+                a = np.ones((I1, I2, I3, NM))
+        a = np.asarray(a, f32).reshape(-1, order="F")
+        if as_complex:
+            _buf(_val(out), I * NM, np.complex64)[:] = a
+        else:
+            _buf(_val(out), I * NM, f32)[:] = a
+        return 0
+
+    fake.qups_apod_generate = qups_apod_generate
+
+
+_emulated_misc = emulated
+
+
+@contextlib.contextmanager
+def emulated(monkeypatch):  # noqa: F811  (adds the dense apodization generator)
+    with _emulated_misc(monkeypatch) as fake:
+        _install_apodgen(fake)
+        yield fake

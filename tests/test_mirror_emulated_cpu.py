@@ -200,3 +200,24 @@ def test_polar_lateral_coordinates_reach_the_abi(monkeypatch, oracle_c):
         ref = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp="linear",
                                 apod=[a_sc], **okw)[..., 0]
         assert rel_linf(got, ref) < 1e-5
+
+
+def test_fusedapod_dense_shapes_and_values(monkeypatch):
+    """FusedApod.dense: the MATLAB-shaped arrays the reference's generators return (I1 x I2 x I3 x N, I1 x I2 x I3 x 1 x M), real or
+    complex, from the qups_apod_generate call."""
+    from tests.abi_emulator import emulated
+    from oracle import apod_np
+    from qups_b200 import ultrasound as U
+    P = small_problem("FC", nz=9, nx=7, N=5, M=3, T=100, zlim=(2e-3, 8e-3))
+    us = U.UltrasoundSystem(tx=P["Pr"], rx=P["Pr"], seq=U.Sequence("FC", P["Pv"]), scan=P["Pi"], fs=P["fs"])
+    Pi, Pr = P["Pi"].astype(f32), P["Pr"].astype(f32)
+    with emulated(monkeypatch):
+        a = us.apApertureGrowth(1.2).dense(Pi, Pr, which="rx")
+        assert a.shape == Pi.shape[1:] + (5,) and a.dtype == f32
+        assert np.array_equal(a, apod_np.apApertureGrowth(P["Pi"], P["Pr"], f=1.2, literal=False).astype(f32))
+        s = us.apScanline(0.5e-3)
+        t = s.dense(Pi, M=3, which="tx")
+        assert t.shape == Pi.shape[1:] + (1, 3)
+        assert np.array_equal(t, apod_np.apScanline(P["Pi"], P["Pv"][0], 0.5e-3, literal=False).astype(f32))
+        c = s.dense(Pi, M=3, which="tx", complex_=True)
+        assert c.dtype == np.complex64 and np.array_equal(c.real, t) and not c.imag.any()
