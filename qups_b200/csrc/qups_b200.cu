@@ -17,7 +17,6 @@ namespace qups {
 static thread_local char g_err[512] = "";
 static thread_local uint64_t g_launches = 0;
 static thread_local const char *g_last_das = "none";
-static thread_local const qups_apod_fused *g_fused = nullptr; // set by qups_das_fused around das_impl
 void count_launch(uint64_t n) { g_launches += n; }
 
 static std::mutex g_pool_mu;
@@ -70,7 +69,8 @@ static int cuda_fail(int e, const char *what) {
 
 template <typename R>
 static int fill_args(DasArgs<R> &a, const qups_das_params *p, const void *Pi, const void *Pr, const void *Pv4,
-                     const void *Nv, const void *apod, const void *cinv, const uint64_t *acstride, int need_astride) {
+                     const void *Nv, const void *apod, const void *cinv, const uint64_t *acstride, int need_astride,
+                     const qups_apod_fused *fz = nullptr) {
     a.I1 = p->I1; a.I2 = p->I2; a.I3 = p->I3;
     a.I = p->I1 * p->I2 * p->I3;
     a.N = p->N; a.M = p->M; a.T = p->T;
@@ -92,12 +92,12 @@ static int fill_args(DasArgs<R> &a, const qups_das_params *p, const void *Pi, co
         for (int d = 0; d < 6; ++d) a.astride[s][d] = (need_astride && s < a.S) ? acstride[6 + 6 * s + d] : 0;
     a.fused = 0;
     a.fa = FusedApod{};
-    if (g_fused && need_astride) {
+    if (fz && need_astride) {
         a.fused = 1;
-        a.fa.rx_kind = g_fused->rx_kind; a.fa.tx_kind = g_fused->tx_kind;
-        for (int k = 0; k < 4; ++k) { a.fa.rx_p[k] = g_fused->rx_p[k]; a.fa.tx_p[k] = g_fused->tx_p[k]; }
-        a.fa.rx_aux = (const float *)g_fused->rx_aux; a.fa.tx_aux = (const float *)g_fused->tx_aux;
-        a.fa.lat = (const float *)g_fused->lat; a.fa.lat_dim = g_fused->lat_dim;
+        a.fa.rx_kind = fz->rx_kind; a.fa.tx_kind = fz->tx_kind;
+        for (int k = 0; k < 4; ++k) { a.fa.rx_p[k] = fz->rx_p[k]; a.fa.tx_p[k] = fz->tx_p[k]; }
+        a.fa.rx_aux = (const float *)fz->rx_aux; a.fa.tx_aux = (const float *)fz->tx_aux;
+        a.fa.lat = (const float *)fz->lat; a.fa.lat_dim = fz->lat_dim;
     }
     return 0;
 }
@@ -139,9 +139,9 @@ static int validate(const qups_das_params *p, bool is_delays) {
 template <typename DIN, typename DA, typename DOUT, typename R>
 static int run_das_typed(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4,
                          const void *Nv, const void *apod, const void *cinv, const uint64_t *acstride, const void *x,
-                         cudaStream_t st, int dtype_in, int dtype_out) {
+                         cudaStream_t st, int dtype_in, int dtype_out, const qups_apod_fused *fz) {
     DasArgs<R> a;
-    fill_args<R>(a, p, Pi, Pr, Pv4, Nv, apod, cinv, acstride, 1);
+    fill_args<R>(a, p, Pi, Pr, Pv4, Nv, apod, cinv, acstride, 1, fz);
     const uint64_t F = p->F ? p->F : 1;
     const uint64_t On = a.keep_rx ? a.N : 1, Om = a.keep_tx ? a.M : 1;
     const uint64_t xfs = p->x_frame_stride ? p->x_frame_stride : a.T * a.N * a.M;
@@ -230,14 +230,65 @@ static int run_das_typed(const qups_das_params *p, void *y, const void *Pi, cons
     return 0;
 }
 
+// fp16 data on the staged kernel: the cube is widened to fp32 ONCE per frame — exactly, and with the re-modulation of
+// kern/das_spec.m:413-417 folded into the same pass when fmod != 0 (1 read of the half2 cube + 1 write of the fp32 scratch) —
+// and takes the fp32 staged kernel; geometry / accumulation are fp32 either way.  Doing the widening inside the
+// kernel instead (a converter warp behind the bulk copies) would repeat it once per pixel tile, ~80x at the headline size.
+// Returns 1 when the call was not eligible (caller falls back to the generic mixed-type kernel), else a status <= 0.
+static int das_half_tiled(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
+                          const void *cinv, const uint64_t *acstride, const void *x, cudaStream_t st, const qups_apod_fused *fz) {
+    if (p->path == QUPS_PATH_GENERIC || p->S != 0) return 1;
+    DasArgs<float> a;
+    fill_args<float>(a, p, Pi, Pr, Pv4, Nv, nullptr, cinv, acstride, 1, fz);
+    a.x = (const void *)16; // alignment probe only: the scratch cube is 256-byte aligned
+    if (!das_tiled_plan(a, 0, 0).eligible) return 1;
+    const uint64_t F = p->F ? p->F : 1, nel = p->T * p->N * p->M, I = p->I1 * p->I2 * p->I3;
+    const uint64_t On = a.keep_rx ? p->N : 1, Om = a.keep_tx ? p->M : 1, ny = I * On * Om;
+    const uint64_t xfs = p->x_frame_stride ? p->x_frame_stride : nel, yfs = p->y_frame_stride ? p->y_frame_stride : ny;
+    if (nel == 0 || ny == 0) return 1;
+    float2 *xs = nullptr, *ys = nullptr;
+    const size_t need = sizeof(float2) * nel;
+    const bool own_x = !(p->workspace && p->workspace_bytes >= need);
+    cudaError_t e = cudaSuccess;
+    if (own_x) e = ws_alloc((void **)&xs, need, st); else xs = (float2 *)p->workspace;
+    if (e == cudaSuccess && !p->y_f32) e = ws_alloc((void **)&ys, sizeof(float2) * ny, st);
+    if (e != cudaSuccess) { if (xs && own_x) ws_free(xs, st); return fail(QUPS_ERR_ALLOC, "ws_alloc(fp32 staging of the fp16 cube): %s", cudaGetErrorString(e)); }
+    qups_das_params q = *p;
+    q.dtype = QUPS_F32; q.F = 1; q.path = QUPS_PATH_TILED; q.fmod = 0.0; q.workspace = nullptr; q.workspace_bytes = 0;
+    int rc = 0;
+    for (uint64_t f = 0; f < F && rc == 0; ++f) {
+        const __half2 *xf = (const __half2 *)x + f * xfs;
+        int ce = (p->fmod != 0.0)
+                     ? launch_modulate<__half2, float2, float>(xs, xf, (const float *)Pv4 + 3, 4, p->T, p->N, p->M, a.tpose, (float)p->fs, p->fmod, st)
+                     : launch_half2_to_float2(xs, xf, nel, st);
+        if (ce) { rc = cuda_fail(ce, "half2 -> float2 staging"); break; }
+        void *yo = p->y_f32 ? (void *)((float2 *)y + f * yfs) : (void *)ys;
+        if (!p->y_f32 && p->accumulate) // running sum kept by the caller in half precision: widen, add in fp32, narrow
+            if ((ce = launch_half2_to_float2(ys, (const __half2 *)y + f * yfs, ny, st))) { rc = cuda_fail(ce, "half2 -> float2"); break; }
+        rc = run_das_typed<float2, float2, float2, float>(&q, yo, Pi, Pr, Pv4, Nv, nullptr, cinv, acstride, xs, st, 0, 0, fz);
+        if (rc == 0 && !p->y_f32)
+            if ((ce = launch_float2_to_half2((__half2 *)y + f * yfs, ys, ny, st))) rc = cuda_fail(ce, "float2 -> half2");
+    }
+    if (own_x) ws_free(xs, st);
+    if (ys) ws_free(ys, st);
+    return rc;
+}
+
 static int das_impl(const qups_das_params *p, void *y, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
-                    const void *apod, const void *cinv, const uint64_t *acstride, const void *x, cudaStream_t st) {
+                    const void *apod, const void *cinv, const uint64_t *acstride, const void *x, cudaStream_t st,
+                    const qups_apod_fused *fz = nullptr) {
     if (int rc = validate(p, false)) return rc;
     if (!y || !Pi || !Pr || !Pv4 || !Nv || !cinv || !x) {
         const uint64_t I = p->I1 * p->I2 * p->I3;
         if (I != 0 && p->N != 0 && p->M != 0) return fail(QUPS_ERR_INVALID, "NULL array argument");
     }
     if (p->S > 0 && (!apod || !acstride)) return fail(QUPS_ERR_INVALID, "S > 0 but apod/acstride is NULL");
+
+    if (p->dtype == QUPS_F16) {
+        const int rc = das_half_tiled(p, y, Pi, Pr, Pv4, Nv, cinv, acstride, x, st, fz);
+        if (rc <= 0) return rc;
+        if (p->path == QUPS_PATH_TILED) return fail(QUPS_ERR_UNSUPPORTED, "tiled DAS path not applicable to this fp16 call");
+    }
 
     // (de)modulation pre-pass — the CPU-branch convention (kern/das_spec.m:413-417): the DATA are
     // re-modulated at absolute time before interpolation.  One frame of scratch.
@@ -266,19 +317,19 @@ static int das_impl(const qups_das_params *p, void *y, const void *Pi, const voi
                 e = launch_modulate<float2, float2, float>((float2 *)scratch, (const float2 *)x + f * xfs,
                                                            (const float *)Pv4 + 3, 4, p->T, p->N, p->M, tpose, (float)p->fs, p->fmod, st);
                 if (e) { rc = cuda_fail(e, "modulate"); break; }
-                rc = run_das_typed<float2, float2, float2, float>(&q, (float2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 0, 0);
+                rc = run_das_typed<float2, float2, float2, float>(&q, (float2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 0, 0, fz);
             } else if (p->dtype == QUPS_F16) {
                 e = launch_modulate<__half2, float2, float>((float2 *)scratch, (const __half2 *)x + f * xfs,
                                                             (const float *)Pv4 + 3, 4, p->T, p->N, p->M, tpose, (float)p->fs, p->fmod, st);
                 if (e) { rc = cuda_fail(e, "modulate"); break; }
                 q.path = QUPS_PATH_GENERIC; // apod stays half: generic mixed-type kernel
-                if (p->y_f32) rc = run_das_typed<float2, __half2, float2, float>(&q, (float2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 0, 0);
-                else rc = run_das_typed<float2, __half2, __half2, float>(&q, (__half2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 0, 1);
+                if (p->y_f32) rc = run_das_typed<float2, __half2, float2, float>(&q, (float2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 0, 0, fz);
+                else rc = run_das_typed<float2, __half2, __half2, float>(&q, (__half2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 0, 1, fz);
             } else {
                 e = launch_modulate<double2, double2, double>((double2 *)scratch, (const double2 *)x + f * xfs,
                                                               (const double *)Pv4 + 3, 4, p->T, p->N, p->M, tpose, p->fs, p->fmod, st);
                 if (e) { rc = cuda_fail(e, "modulate"); break; }
-                rc = run_das_typed<double2, double2, double2, double>(&q, (double2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 2, 2);
+                rc = run_das_typed<double2, double2, double2, double>(&q, (double2 *)y + f * yfs, Pi, Pr, Pv4, Nv, apod, cinv, acstride, scratch, st, 2, 2, fz);
             }
         }
         if (own) ws_free(scratch, st);
@@ -287,42 +338,12 @@ static int das_impl(const qups_das_params *p, void *y, const void *Pi, const voi
 
     switch (p->dtype) {
         case QUPS_F32:
-            return run_das_typed<float2, float2, float2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 0, 0);
-        case QUPS_F16: {
-            // fp16 data on the hot configuration: widen the cube to fp32 once (exact) and run the staged kernel;
-            // fp32 geometry / accumulation either way, half2 output narrowed at the end.
-            if (p->path != QUPS_PATH_GENERIC && p->S == 0 && !(p->flag & (QUPS_FLAG_KEEP_RX | QUPS_FLAG_KEEP_TX)) && !p->accumulate) {
-                DasArgs<float> a;
-                fill_args<float>(a, p, Pi, Pr, Pv4, Nv, apod, cinv, acstride, 1);
-                a.x = (const void *)16; // alignment probe only: the scratch cube is 256-byte aligned
-                if (das_tiled_plan(a, 0, 0).eligible) {
-                    const uint64_t F = p->F ? p->F : 1, nel = p->T * p->N * p->M, I = p->I1 * p->I2 * p->I3;
-                    const uint64_t xfs = p->x_frame_stride ? p->x_frame_stride : nel, yfs = p->y_frame_stride ? p->y_frame_stride : I;
-                    float2 *xs = nullptr, *ys = nullptr;
-                    cudaError_t e = ws_alloc((void **)&xs, sizeof(float2) * nel, st);
-                    if (e == cudaSuccess && !p->y_f32) e = ws_alloc((void **)&ys, sizeof(float2) * I, st);
-                    if (e != cudaSuccess) { if (xs) ws_free(xs, st); return fail(QUPS_ERR_ALLOC, "cudaMallocAsync: %s", cudaGetErrorString(e)); }
-                    qups_das_params q = *p;
-                    q.dtype = QUPS_F32; q.F = 1; q.path = QUPS_PATH_TILED;
-                    int rc = 0;
-                    for (uint64_t f = 0; f < F && rc == 0; ++f) {
-                        if (int ce = launch_half2_to_float2(xs, (const __half2 *)x + f * xfs, nel, st)) { rc = cuda_fail(ce, "half2->float2"); break; }
-                        void *yo = p->y_f32 ? (void *)((float2 *)y + f * yfs) : (void *)ys;
-                        rc = run_das_typed<float2, float2, float2, float>(&q, yo, Pi, Pr, Pv4, Nv, nullptr, cinv, acstride, xs, st, 0, 0);
-                        if (rc == 0 && !p->y_f32)
-                            if (int ce = launch_float2_to_half2((__half2 *)y + f * yfs, ys, I, st)) rc = cuda_fail(ce, "float2->half2");
-                    }
-                    ws_free(xs, st);
-                    if (ys) ws_free(ys, st);
-                    return rc;
-                }
-            }
-            if (p->path == QUPS_PATH_TILED) return fail(QUPS_ERR_UNSUPPORTED, "tiled DAS path not applicable to this fp16 call");
-            if (p->y_f32) return run_das_typed<__half2, __half2, float2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 1, 0);
-            return run_das_typed<__half2, __half2, __half2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 1, 1);
-        }
+            return run_das_typed<float2, float2, float2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 0, 0, fz);
+        case QUPS_F16:
+            if (p->y_f32) return run_das_typed<__half2, __half2, float2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 1, 0, fz);
+            return run_das_typed<__half2, __half2, __half2, float>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 1, 1, fz);
         default:
-            return run_das_typed<double2, double2, double2, double>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 2, 2);
+            return run_das_typed<double2, double2, double2, double>(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, st, 2, 2, fz);
     }
 }
 
@@ -354,12 +375,9 @@ int qups_das_fused(const qups_das_params *p, const qups_apod_fused *fz, void *y,
     if (int rc = validate_fused(fz, p)) return rc;
     if (fz->rx_kind == QUPS_AP_RX_NONE && fz->tx_kind == QUPS_AP_TX_NONE)
         return das_impl(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, (cudaStream_t)stream);
-    if (p->dtype == QUPS_F16 && (p->S != 0 || (p->flag & (QUPS_FLAG_KEEP_RX | QUPS_FLAG_KEEP_TX)) || p->accumulate || p->fmod != 0.0))
-        return fail(QUPS_ERR_UNSUPPORTED, "closed-form apodization with fp16 data: plain DAS only (no arrays / kept apertures / modulation)");
-    g_fused = fz;
-    const int rc = das_impl(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, (cudaStream_t)stream);
-    g_fused = nullptr;
-    return rc;
+    if (p->dtype == QUPS_F16 && (p->S != 0 || (p->flag & (QUPS_FLAG_KEEP_RX | QUPS_FLAG_KEEP_TX))))
+        return fail(QUPS_ERR_UNSUPPORTED, "closed-form apodization with fp16 data: no apodization arrays / kept apertures");
+    return das_impl(p, y, Pi, Pr, Pv4, Nv, apod, cinv, acstride, x, (cudaStream_t)stream, fz);
 }
 
 int qups_apod_generate(const qups_apod_fused *fz, int32_t which, void *out, int32_t as_complex, const void *Pi, const void *Pr,
@@ -450,7 +468,7 @@ int qups_modulate(int32_t dtype, void *xout, const void *x, const void *t0, uint
 namespace qups {
 // per-host-thread staging state, kept between calls (see qups_host_release)
 struct HostWs {
-    static constexpr int NB = 8, NEV = 32;
+    static constexpr int NB = 9, NEV = 32;
     int dev = -1;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev[NEV] = {};
@@ -530,7 +548,7 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
     QUPS_UP(dC, cinv, rsz * cinv_elems)
     // transmit-chunked pipeline: DAS is a plain sum over transmits (kern/das_spec.m:480), so chunk c+1 is copied
     // while chunk c is beamformed and accumulated.  Only for the contiguous-in-m layout and summed transmits.
-    const bool chunkable = rc == 0 && F == 1 && !(p->flag & (QUPS_FLAG_TRANSPOSE | QUPS_FLAG_KEEP_TX)) && p->fmod == 0.0 &&
+    const bool chunkable = rc == 0 && F == 1 && !(p->flag & (QUPS_FLAG_TRANSPOSE | QUPS_FLAG_KEEP_TX)) &&
                            p->S == 0 && !p->accumulate &&
                            ((p->M >= 16 && p->T * p->N * p->M * csz >= (64u << 20)) || (p->host_chunks > 1 && p->M >= (uint64_t)p->host_chunks));
     if (chunkable) {
@@ -561,6 +579,11 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
                 }
                 bounds[nb] = p->M;
             }
+            // fp16 with half2 output: the running sum over the chunks lives in an fp32 image and is narrowed ONCE at the end
+            // (accumulating in y itself would round the image to half precision after every chunk)
+            void *dYacc = dY;
+            const bool widen_y = p->dtype == QUPS_F16 && !p->y_f32;
+            if (widen_y && (rc = g_ws.get(8, sizeof(float2) * I * On * Om, &dYacc))) return rc;
             for (uint64_t c = 0; c < nb && rc == 0; ++c) {
                 const uint64_t m0 = bounds[c], m1 = bounds[c + 1];
                 const size_t off = csz * p->T * p->N * m0, len = csz * p->T * p->N * (m1 - m0);
@@ -570,9 +593,12 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
                 qups_das_params q = *p;
                 q.M = m1 - m0;
                 q.accumulate = c > 0;
-                rc = das_impl(&q, dY, dPi, dPr, (char *)dPv + rsz * 4 * m0, (char *)dNv + rsz * 3 * m0, dA, dC, acstride,
+                if (widen_y) q.y_f32 = 1;
+                rc = das_impl(&q, dYacc, dPi, dPr, (char *)dPv + rsz * 4 * m0, (char *)dNv + rsz * 3 * m0, dA, dC, acstride,
                               (char *)dX + off, sx);
             }
+            if (rc == 0 && widen_y)
+                if (int ce = launch_float2_to_half2((__half2 *)dY, (const float2 *)dYacc, I * On * Om, sx)) rc = cuda_fail(ce, "float2 -> half2");
             if (rc == 0 && yb && (e = cudaMemcpyAsync(y, dY, yb, cudaMemcpyDeviceToHost, sx)) != cudaSuccess) rc = cuda_fail(e, "D2H copy");
             if ((e = cudaStreamSynchronize(sx)) != cudaSuccess && rc == 0) rc = cuda_fail(e, "cudaStreamSynchronize");
             cudaStreamSynchronize(sc);

@@ -314,7 +314,12 @@ def das_spec(fun, Pi, Pr, Pv, Nv, x, t0, fs=None, c=1540.0, *varargin, _path=_li
                                      acs_c, st))
             y = _from_colmajor(tau, Isz + (N, M))
         else:
-            dX = _cplx_buf(xt.reshape(xs[:3] + (F,)), prec, dev)
+            # frames collapse in COLUMN-major order (f = f1 + F1*f2 + ..., as MATLAB's x(:,:,:,:) does): the output is
+            # unfolded column-major below, so a row-major collapse would hand the frames back permuted
+            xf = xt.reshape(xs)
+            if len(xs) > 4:
+                xf = xf.permute(0, 1, 2, *reversed(range(3, len(xs))))
+            dX = _cplx_buf(xf.reshape(xs[:3] + (F,)), prec, dev)
             On, Om = (N if keep_rx else 1), (M if keep_tx else 1)
             if prec == "halfT" and not _y_f32:
                 yb = torch.empty((F * Om * On * I, 2), dtype=torch.float16, device=dev)

@@ -221,3 +221,20 @@ def test_fusedapod_dense_shapes_and_values(monkeypatch):
         assert np.array_equal(t, apod_np.apScanline(P["Pi"], P["Pv"][0], 0.5e-3, literal=False).astype(f32))
         c = s.dense(Pi, M=3, which="tx", complex_=True)
         assert c.dtype == np.complex64 and np.array_equal(c.real, t) and not c.imag.any()
+
+
+def test_multiple_frame_dims_collapse_column_major(monkeypatch, oracle_c):
+    """x of size T x N x M x F1 x F2: frames must come back in the reference's (column-major) order
+    (kern/das_spec.m:173 fsz = size(x, 4:ndims(x)); the output is reshaped to [Isz, 1, 1, fsz])."""
+    from tests.abi_emulator import emulated
+    P = small_problem("FC", nz=6, nx=5, N=4, M=3, T=120, F=6)
+    x6 = P["x"]                                            # T x N x M x 6
+    x23 = np.asfortranarray(x6.reshape(x6.shape[:3] + (2, 3), order="F"))
+    with emulated(monkeypatch):
+        a = _call("DAS", P, "cubic", x=x6)
+        b = _call("DAS", P, "cubic", x=x23)
+    assert b.shape == a.shape[:5] + (2, 3)
+    assert np.array_equal(b.reshape(a.shape, order="F"), a)
+    ref = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], x6, P["t0"], P["fs"], P["c"], interp="cubic",
+                            **oracle_kwargs(P["opts"]))
+    assert rel_linf(a, ref) < 1e-5

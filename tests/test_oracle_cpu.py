@@ -200,3 +200,33 @@ def test_greens_c_equals_numpy(oracle_np, oracle_c):
         assert rel_linf(a, b) < 1e-6
     d = oracle_c.greens(ps, amp, pn, pn, kern, n0, T, fs, 1500.0, wt0, 1.0, 3e-4, "cubic", dtype=np.float64)
     assert rel_linf(b, d) < 1e-3
+
+
+def test_interp1_cubic_equals_independent_keys_convolution_incl_ends(oracle_c):
+    """Second, independent statement of interp1(..., 'cubic') (R2020b+: cubic convolution, Keys 1981, a = -1/2): the sample
+    sequence extended by the Keys boundary condition v(0) = 3v(1) - 3v(2) + v(3), v(T+1) = 3v(T) - 3v(T-1) + v(T-2),
+    convolved with the piecewise-cubic KERNEL W(s) (no per-interval polynomial, no floor) in fp64.  Covers the first and last
+    intervals, the grid points and out-of-range queries.  Also checks the polynomials the reference GPU kernel states in its
+    comment (src/interpd.cu:108-111), evaluated literally, against the same kernel form."""
+    rng = np.random.default_rng(11)
+    T = 37
+    v = rng.standard_normal(T) + 1j * rng.standard_normal(T)
+    vp = np.concatenate([[3 * v[0] - 3 * v[1] + v[2]], v, [3 * v[-1] - 3 * v[-2] + v[-3]]])   # positions 0 .. T+1
+    a = -0.5
+
+    def W(s):
+        s = np.abs(s)
+        return np.where(s <= 1, (a + 2) * s**3 - (a + 3) * s**2 + 1, np.where(s < 2, a * s**3 - 5 * a * s**2 + 8 * a * s - 4 * a, 0.0))
+
+    xq = np.concatenate([np.linspace(1, T, 1441), np.arange(1, T + 1), [0.999, T + 0.001, -3.0, np.nan]])
+    pos = np.arange(0, T + 2)
+    with np.errstate(invalid="ignore"):
+        indep = (vp[None, :] * W(xq[:, None] - pos[None, :])).sum(1)
+    indep = np.where((xq >= 1) & (xq <= T), indep, 0)
+    got = oracle_c.interp1(v, xq, "cubic", dtype=np.float64)
+    assert np.max(np.abs(got - indep)) < 1e-12 * np.max(np.abs(v))
+    # the commented Catmull-Rom polynomials of the reference GPU kernel == the Keys kernel on an interior interval
+    u = np.linspace(0, 1, 33)
+    cr = np.stack([-u**3 + 2 * u**2 - u, 3 * u**3 - 5 * u**2 + 2, -3 * u**3 + 4 * u**2 + u, u**3 - u**2]) * 0.5
+    kw = np.stack([W(u + 1), W(u), W(u - 1), W(u - 2)])
+    assert np.max(np.abs(cr - kw)) < 1e-14
