@@ -28,7 +28,11 @@
  *     qups_last_error() returns a thread-local message
  *   - `stream` is a cudaStream_t (NULL = legacy default stream); calls are
  *     asynchronous w.r.t. the host unless stated
- *   - re-entrant; no global mutable state besides the thread-local error text
+ *   - re-entrant.  State the library keeps between calls, all of it invisible in results: the thread-local error text,
+ *     launch counter and last-kernel name; one stream-ordered memory pool per device for scratch (created on first use,
+ *     memory is returned to it, not to the driver, at synchronisation points); and, for the *_host entry points only,
+ *     per-host-thread device staging buffers + two streams (the ~1 GB cube buffer is kept between calls on purpose;
+ *     qups_host_release() frees them).  No result depends on previous calls (see pitch_hint for the one perf-only cache).
  *   - results follow the reference's CPU semantics (kern/das_spec.m CPU branch +
  *     MATLAB interp1(…, extrapval=0)), not the edge quirks of src/interpd.cu
  */
@@ -42,7 +46,7 @@
 extern "C" {
 #endif
 
-#define QUPS_B200_VERSION 100
+#define QUPS_B200_VERSION 200
 
 #if defined(__GNUC__)
 #define QUPS_API __attribute__((visibility("default")))
@@ -89,12 +93,22 @@ typedef struct {
     int32_t path;         /* qups_path; AUTO picks the tiled kernel when eligible */
     int32_t accumulate;   /* extension: y += result instead of y = result (transmit-chunked pipelines) */
     int32_t host_chunks;  /* qups_das_host only: transmit chunks of the copy/compute pipeline (0 = automatic) */
+    int32_t y_device;     /* qups_das_host only: y is a DEVICE pointer on `device` and the image stays there (no read-back):
+                             multi-GPU transmit partitions reduce the partial images with NCCL before one rank reads the sum */
+    int32_t reserved_;    /* 0 */
     double fs;            /* sampling frequency */
     double fmod;          /* modulation frequency (data re-modulated at absolute time, kern/das_spec.m:413-417) */
     uint64_t x_frame_stride; /* complex elements between frames of x; 0 -> T*N*M */
     uint64_t y_frame_stride; /* complex elements between frames of y; 0 -> I*[N]*[M] */
     void *workspace;         /* optional device scratch for the modulated cube (fmod != 0); NULL -> stream-ordered alloc */
     uint64_t workspace_bytes;
+    /* Optional tuning hints for the staged kernel (never affect results): distance in metres between neighbouring pixels along
+     * I1 and I2 (scan.dz / scan.dx of a ScanCartesian) and the scalar sound speed.  With all three set the launcher picks the
+     * tile shape and ring geometry from them and never touches device memory from the host; with any of them 0 it reads three
+     * pixel positions and 1/c back once per (pixel pointer, grid size) — a host synchronisation on the first call with a new
+     * grid, cached for later calls (the one cache keyed on a caller pointer; a stale entry only costs speed). */
+    double pitch_hint[2];
+    double c_hint;
 } qups_das_params;
 
 /* y      : out, complex, I x [N if keep_rx] x [M if keep_tx] (x F)

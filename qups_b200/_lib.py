@@ -39,10 +39,11 @@ class DasParams(C.Structure):
         ("F", C.c_uint64), ("S", C.c_uint64),
         ("flag", C.c_int32), ("vs", C.c_int32), ("dv", C.c_int32),
         ("apod_real", C.c_int32), ("y_f32", C.c_int32), ("path", C.c_int32),
-        ("accumulate", C.c_int32), ("host_chunks", C.c_int32),
+        ("accumulate", C.c_int32), ("host_chunks", C.c_int32), ("y_device", C.c_int32), ("reserved_", C.c_int32),
         ("fs", C.c_double), ("fmod", C.c_double),
         ("x_frame_stride", C.c_uint64), ("y_frame_stride", C.c_uint64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
+        ("pitch_hint", C.c_double * 2), ("c_hint", C.c_double),
     ]
 
 

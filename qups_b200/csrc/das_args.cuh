@@ -25,6 +25,7 @@ template <typename R> struct DasArgs {
     void *y;
     uint64_t cstride[6];
     uint64_t astride[MAX_APOD][6];
+    double pitch_hint[2], c_hint; // optional launcher hints (pixel pitch along I1 / I2, sound speed); 0 = unknown
     int fused;      // 0 = no closed-form apodization; otherwise `fa` is valid (fp32 paths only)
     FusedApod fa;
 };

@@ -943,13 +943,33 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     // tile (~ pixel spacing x extent) is smallest: square-ish on isotropic grids (32 x 16, patch 8 x 4 x 2 — measured best on the
     // headline grid), narrow along a coarsely sampled axis (e.g. one image column per element pitch).  The spacing is read
     // from three pixel positions; the decision is cached per (Pi, grid) so only the first call with a new grid synchronises.
+    const bool hinted = a.pitch_hint[0] > 0.0 && a.pitch_hint[1] > 0.0 && a.c_hint > 0.0; // caller supplied the grid pitch: no probe, no cache
     {
         struct ShapeCache { const void *Pi; uint64_t I1, I2, I3; int lane_axis; uint32_t tA, lpa; double span; };
         static thread_local ShapeCache sc = {nullptr, 0, 0, 0, 0, 0, 0, 0.0};
         uint32_t tA = 32, lpa = QUPS_LPA;
+        // tile shape from the pixel pitch along the lane (dA) and row (dB) axes
+        auto choose = [&](double dA, double dB, bool okA, bool okB) {
+            if (!(dA > 0) || !(dB > 0) || !(dA == dA) || !(dB == dB)) dA = dB = 1.0;
+            if (!okA) dA = dB * 1e3;   // degenerate axis: make the tile as thin as possible along it
+            if (!okB) dB = dA * 1e3;
+            double best = 1e300;
+            for (uint32_t l = 1; l <= 32; l <<= 1)
+                for (uint32_t w = 1; w <= (uint32_t)kCW; w <<= 1) {
+                    const uint32_t ta_ = l * w, tb_ = kTilePix / ta_;
+                    const double tile = dA * ta_ + dB * tb_, warpspan = dA * l + dB * (2.0 * (32 / l));
+                    // prefer the measured-best isotropic shape on ties (32 x 16, patch 8): tiny bias
+                    const double cost = tile + 0.25 * warpspan + ((ta_ == 32 && l == (uint32_t)QUPS_LPA) ? -1e-9 * tile : 0.0);
+                    if (cost < best) { best = cost; tA = ta_; lpa = l; span_m = tile; }
+                }
+            if (!okA || !okB || dA == 1.0) span_m = 0.0; // unknown spacing: keep the default ring
+        };
         // the probe synchronises the stream once per new grid: not allowed while the stream is being captured into a CUDA
         // graph (and skippable with QUPS_B200_NOPROBE=1) — the default shape / ring are then used, results are unaffected
-        if (sc.Pi == a.Pi && sc.I1 == a.I1 && sc.I2 == a.I2 && sc.I3 == a.I3 && sc.lane_axis == lane_axis) {
+        if (hinted) {
+            const double d1 = a.pitch_hint[0], d2 = a.pitch_hint[1];
+            choose(lane_axis == 2 ? d2 : d1, lane_axis == 2 ? d1 : d2, t.IA > 1, t.IB > 1);
+        } else if (sc.Pi == a.Pi && sc.I1 == a.I1 && sc.I2 == a.I2 && sc.I3 == a.I3 && sc.lane_axis == lane_axis) {
             tA = sc.tA; lpa = sc.lpa; span_m = sc.span;
         } else if (noprobe) {
             span_m = 0.0;
@@ -965,19 +985,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
             auto dist = [&](const float *q) { double s2 = 0; for (int k = 0; k < 3; ++k) s2 += ((double)q[k] - P0[k]) * ((double)q[k] - P0[k]); return sqrt(s2); };
             if (okA) dA = dist(PA);
             if (okB) dB = dist(PB);
-            if (!(dA > 0) || !(dB > 0) || !(dA == dA) || !(dB == dB)) dA = dB = 1.0;
-            if (!okA) dA = dB * 1e3;   // degenerate axis: make the tile as thin as possible along it
-            if (!okB) dB = dA * 1e3;
-            double best = 1e300;
-            for (uint32_t l = 1; l <= 32; l <<= 1)
-                for (uint32_t w = 1; w <= (uint32_t)kCW; w <<= 1) {
-                    const uint32_t ta_ = l * w, tb_ = kTilePix / ta_;
-                    const double tile = dA * ta_ + dB * tb_, warpspan = dA * l + dB * (2.0 * (32 / l));
-                    // prefer the measured-best isotropic shape on ties (32 x 16, patch 8): tiny bias
-                    const double cost = tile + 0.25 * warpspan + ((ta_ == 32 && l == (uint32_t)QUPS_LPA) ? -1e-9 * tile : 0.0);
-                    if (cost < best) { best = cost; tA = ta_; lpa = l; span_m = tile; }
-                }
-            if (!okA || !okB || dA == 1.0) span_m = 0.0; // unknown spacing: keep the default ring
+            choose(dA, dB, okA, okB);
             sc = {a.Pi, a.I1, a.I2, a.I3, lane_axis, tA, lpa, span_m};
         }
         if (const char *e = getenv("QUPS_B200_TILE")) { // "tA,lpa" override for experiments
@@ -1000,7 +1008,8 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
         float cinv_h = 0.f;
         static thread_local const void *c_ptr = nullptr;
         static thread_local float c_val = 0.f;
-        if (span_m > 0.0) { // (span_m stays 0 when the probe was skipped)
+        if (span_m > 0.0 && hinted) cinv_h = (float)(1.0 / a.c_hint);
+        else if (span_m > 0.0) { // (span_m stays 0 when the probe was skipped)
             if (c_ptr == a.cinv && c_val > 0.f) cinv_h = c_val;
             else if (!noprobe && cudaMemcpyAsync(&cinv_h, a.cinv, sizeof(float), cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) { c_ptr = a.cinv; c_val = cinv_h; }
         }
@@ -1042,10 +1051,21 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint64_t want = 4ull * QUPS_MINBLOCKS * (uint64_t)sms;
+    // Candidate splits are scored by a makespan model: CTAs are scheduled dynamically onto sms * MINBLOCKS slots, so with
+    // w = grid / slots "waves" the launch takes between ceil(w) (equal CTAs) and w + 1/2 (unequal CTAs, small tail) CTA times;
+    // every extra split repeats the per-CTA setup (phase 0 over all M transmits ~ 9 % of one receive tile's work).
     uint32_t nsplit = 1;
-    if (tiles < want) nsplit = (uint32_t)((want + tiles - 1) / tiles);
-    if (nsplit > t.numNT / 2) nsplit = t.numNT / 2;   // at least two receive tiles per CTA
+    {
+        const double slots = (double)(wmax > 256 ? 1 : QUPS_MINBLOCKS) * sms; // long-slot rings run one CTA per SM
+        const uint32_t max_split = t.numNT >= 4 ? t.numNT / 2 : 1;   // at least two receive tiles per CTA
+        double best = 1e300;
+        for (uint32_t ns = 1; ns <= max_split; ++ns) {
+            const double w = (double)tiles * ns / slots;
+            const double span = 0.5 * ceil(w) + 0.5 * (w + 0.5);
+            const double cost = span / w * (1.0 + 0.09 * ns / t.numNT);
+            if (cost < best * 0.995) { best = cost; nsplit = ns; }     // prefer fewer splits on near-ties
+        }
+    }
     if (keep) nsplit = 1;                             // kept apertures: each CTA is the only writer of its pixels
     if (nsplit < 1) nsplit = 1;
     if (const char *e2 = getenv("QUPS_B200_NSPLIT")) { int v = atoi(e2); if (v >= 1 && (uint32_t)v <= t.numNT) nsplit = (uint32_t)v; }

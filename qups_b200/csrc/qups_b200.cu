@@ -3,6 +3,7 @@
 // modulation pre-pass (kern/das_spec.m:413-417) and the host-buffer variants.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -90,6 +91,7 @@ static int fill_args(DasArgs<R> &a, const qups_das_params *p, const void *Pi, co
     a.cstride[5] = 0; // entry 6 of cstride is unused padding in the reference (kern/das_spec.m:259)
     for (int s = 0; s < MAX_APOD; ++s)
         for (int d = 0; d < 6; ++d) a.astride[s][d] = (need_astride && s < a.S) ? acstride[6 + 6 * s + d] : 0;
+    a.pitch_hint[0] = p->pitch_hint[0]; a.pitch_hint[1] = p->pitch_hint[1]; a.c_hint = p->c_hint;
     a.fused = 0;
     a.fa = FusedApod{};
     if (fz && need_astride) {
@@ -522,6 +524,24 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
     if (int rc = validate(p, false)) return rc;
     if (int rc = g_ws.ensure(device)) return rc;
     cudaError_t e;
+    // the geometry is in host memory here: derive the launcher hints from it so the staged kernel never probes the device
+    qups_das_params hinted = *p;
+    if (Pi && cinv && cinv_elems == 1 && !(p->pitch_hint[0] > 0 && p->pitch_hint[1] > 0 && p->c_hint > 0)) {
+        auto pitch = [&](uint64_t j) -> double {
+            double s2 = 0;
+            for (int k = 0; k < 3; ++k) {
+                const double d = (p->dtype == QUPS_F64) ? ((const double *)Pi)[3 * j + k] - ((const double *)Pi)[k]
+                                                        : (double)((const float *)Pi)[3 * j + k] - (double)((const float *)Pi)[k];
+                s2 += d * d;
+            }
+            return sqrt(s2);
+        };
+        const double ci = (p->dtype == QUPS_F64) ? *(const double *)cinv : (double)*(const float *)cinv;
+        if (p->I1 > 1 && p->I2 > 1 && ci > 0) {
+            hinted.pitch_hint[0] = pitch(1); hinted.pitch_hint[1] = pitch(p->I1); hinted.c_hint = 1.0 / ci;
+        }
+    }
+    p = &hinted;
     const size_t rsz = (p->dtype == QUPS_F64) ? 8 : 4;                       // geometry element
     const size_t csz = (p->dtype == QUPS_F64) ? 16 : (p->dtype == QUPS_F16 ? 4 : 8); // complex data element
     const size_t ysz = (p->dtype == QUPS_F16 && p->y_f32) ? 8 : csz;
@@ -535,8 +555,10 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
     int rc = 0;
     if ((rc = g_ws.get(0, xb, &dX)) || (rc = g_ws.get(1, rsz * 3 * I, &dPi)) || (rc = g_ws.get(2, rsz * 3 * p->N, &dPr)) ||
         (rc = g_ws.get(3, rsz * 4 * p->M, &dPv)) || (rc = g_ws.get(4, rsz * 3 * p->M, &dNv)) ||
-        (rc = g_ws.get(5, asz * apod_elems, &dA)) || (rc = g_ws.get(6, rsz * cinv_elems, &dC)) || (rc = g_ws.get(7, yb, &dY)))
+        (rc = g_ws.get(5, asz * apod_elems, &dA)) || (rc = g_ws.get(6, rsz * cinv_elems, &dC)) ||
+        (rc = p->y_device ? 0 : g_ws.get(7, yb, &dY)))
         return rc;
+    if (p->y_device) dY = y;
     cudaStream_t sc = g_ws.s_copy, sx = g_ws.s_comp;
 #define QUPS_UP(dst, src, bytes) \
     if (rc == 0 && (bytes) && (e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sc)) != cudaSuccess) rc = cuda_fail(e, "H2D copy");
@@ -599,7 +621,7 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
             }
             if (rc == 0 && widen_y)
                 if (int ce = launch_float2_to_half2((__half2 *)dY, (const float2 *)dYacc, I * On * Om, sx)) rc = cuda_fail(ce, "float2 -> half2");
-            if (rc == 0 && yb && (e = cudaMemcpyAsync(y, dY, yb, cudaMemcpyDeviceToHost, sx)) != cudaSuccess) rc = cuda_fail(e, "D2H copy");
+            if (rc == 0 && yb && !p->y_device && (e = cudaMemcpyAsync(y, dY, yb, cudaMemcpyDeviceToHost, sx)) != cudaSuccess) rc = cuda_fail(e, "D2H copy");
             if ((e = cudaStreamSynchronize(sx)) != cudaSuccess && rc == 0) rc = cuda_fail(e, "cudaStreamSynchronize");
             cudaStreamSynchronize(sc);
             return rc;
@@ -610,7 +632,7 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
     if (rc == 0 && (e = cudaEventRecord(g_ws.ev[0], sc)) != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord");
     if (rc == 0 && (e = cudaStreamWaitEvent(sx, g_ws.ev[0], 0)) != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent");
     if (rc == 0) rc = das_impl(p, dY, dPi, dPr, dPv, dNv, dA, dC, acstride, dX, sx);
-    if (rc == 0 && yb && (e = cudaMemcpyAsync(y, dY, yb, cudaMemcpyDeviceToHost, sx)) != cudaSuccess) rc = cuda_fail(e, "D2H copy");
+    if (rc == 0 && yb && !p->y_device && (e = cudaMemcpyAsync(y, dY, yb, cudaMemcpyDeviceToHost, sx)) != cudaSuccess) rc = cuda_fail(e, "D2H copy");
     if ((e = cudaStreamSynchronize(sx)) != cudaSuccess && rc == 0) rc = cuda_fail(e, "cudaStreamSynchronize");
     cudaStreamSynchronize(sc);
     return rc;

@@ -305,6 +305,12 @@ def das_spec(fun, Pi, Pr, Pv, Nv, x, t0, fs=None, c=1540.0, *varargin, _path=_li
     p.vs, p.dv = int(VS), int(DV)
     p.apod_real, p.y_f32, p.path = int(apod_real), int(_y_f32), int(_path)
     p.fs, p.fmod = float(fs), float(fmod)
+    if not Pi_t.is_cuda and cinv_t.numel() == 1 and Isz[0] > 1 and Isz[1] > 1 and Pi_t.shape[0] == 3:
+        # geometry still on the host: hand the launcher the pixel pitch / sound speed so it never reads them back from the device
+        P0 = Pi_t[:, 0, 0, 0].double()
+        p.pitch_hint[0] = float(torch.linalg.norm(Pi_t[:, 1, 0, 0].double() - P0))
+        p.pitch_hint[1] = float(torch.linalg.norm(Pi_t[:, 0, 1, 0].double() - P0))
+        p.c_hint = float(1.0 / cinv_t.reshape(-1)[0])
     st = _stream(dev)
 
     with torch.cuda.device(dev):

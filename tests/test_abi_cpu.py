@@ -45,7 +45,7 @@ def test_struct_sizes_match_the_header(lib, tmp_path):
 
 def test_validation_errors_without_a_gpu(lib):
     from qups_b200 import _lib
-    assert lib.qups_version() == 100
+    assert lib.qups_version() == 200
     p = _lib.DasParams()
     p.struct_size = 7  # header/library mismatch
     assert lib.qups_das(C.byref(p), None, None, None, None, None, None, None, None, None, None) == -1

@@ -97,8 +97,11 @@ def test_generic_fp64_and_fp16(oracle_c):
     for path in ("auto", "generic"):
         got16 = _gpu("DAS", P, "cubic", path, ("input-precision", "halfT"))
         assert rel_linf(got16, ref) < 2e-3  # half2 output rounding (reference DASh writes half2)
-    gsyn = _gpu("SYN", P, "cubic", "auto", ("input-precision", "halfT"), _y_f32=True)           # generic mixed types
-    assert np.array_equal(gsyn, _ora(oracle_c, "SYN", P, "cubic", x=xh))
+    rsyn = _ora(oracle_c, "SYN", P, "cubic", x=xh)
+    gsyn = _gpu("SYN", P, "cubic", "generic", ("input-precision", "halfT"), _y_f32=True)        # generic mixed types
+    assert np.array_equal(gsyn, rsyn)
+    gsyn = _gpu("SYN", P, "cubic", "auto", ("input-precision", "halfT"), _y_f32=True)           # fp16 data on the staged kernel
+    assert qb.last_das_kernel() == "das_tiled" and rel_linf(gsyn, rsyn) < TOL
 
 
 def test_generic_modulation(oracle_c):
