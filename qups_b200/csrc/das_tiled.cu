@@ -75,7 +75,20 @@ constexpr int threads_of(int interp) { return (kCW + (interp == 0 ? kPW : 1)) * 
 #ifndef QUPS_LPA
 #define QUPS_LPA 8
 #endif
+#ifndef QUPS_WAITHINT
+#define QUPS_WAITHINT 0   // mbarrier.try_wait with a suspend-time hint (measured on C2: 68.05 vs 67.69 ms without — no gain, off)
+#endif
+#ifndef QUPS_SOFF4
+#define QUPS_SOFF4 1      // all-fast stages: slot offsets of 4 traces per LDS.128 from a compact table (12 fewer LDS per stage)
+#endif
+#ifndef QUPS_HDRGEO
+#define QUPS_HDRGEO 1     // the producer puts the stage's transmit geometry (Pv, t0, Nv, uniform sign of dv) into the stage header
+#endif
 constexpr int kBarBytes = ((2 * kStages * 8 + 63) / 64) * 64;  // full[] + empty[] mbarriers
+// per-stage header block: [0] int4 (kind, outer index, inner tile, uniform sign of dv: +1 / -1 / 0 = mixed) | [1] float4 geometry A
+// (Pv.xyz, t0 of transmit `outer`; Pr.xyz when the inner traces are transmits) | [2] float4 geometry B (Nv.xyz) | [3] pad |
+// then the compact slot-offset table of all-fast stages (kNT x uint32)
+constexpr int kHdrBytes = 64 + 4 * kNT;
 constexpr int kTilePix = kCW * 32 * kR; // pixels per tile; its SHAPE (tA x tB, lane patch lpa) is chosen per call from the pixel spacing
 
 // QUPS_MAGIC: the cubic fast path derives the tap address from the bits of 2^23 + floor(xq); the constant
@@ -83,7 +96,7 @@ constexpr int kTilePix = kCW * 32 * kR; // pixels per tile; its SHAPE (tA x tB, 
 template <int INTERP> struct magic_off { static constexpr uint32_t value = QUPS_MAGIC ? (0x4B000000u << 3) : 0u; };
 
 #if QUPS_STATS
-__device__ unsigned long long g_stats[8]; // [0..3] traces by flag, [4] split traces, [5] all-fast stages, [6] general stages
+__device__ unsigned long long g_stats[12]; // [0..3] traces by flag, [4] split traces, [5] all-fast stages, [6] general stages, [7] empty, [8] general stages made of single-window FAST + SKIP traces only, [9] general stages with a dual-window trace, [10] with an EDGE trace, [11] with a SLOW trace
 #endif
 enum { TR_FAST = 0, TR_SKIP = 1, TR_SLOW = 2, TR_EDGE = 3 };   // per (n,m) trace
 enum { ST_MIXED = 0, ST_ALL_FAST = 1, ST_END = 2 };             // per published stage of kNT traces
@@ -138,7 +151,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if QUPS_WAITHINT
+    // potentially-blocking wait with a suspend-time hint: the warp is parked by the hardware until the phase completes (or the
+    // hint expires) instead of re-issuing try_wait (ncu, round 1: 1.5e9 SYNCS + as many BRA = 6 % of all issued instructions)
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "QUPS_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra QUPS_DONE_%=;\n\t"
+        "bra QUPS_WAIT_%=;\n\t"
+        "QUPS_DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+#else
     while (!mbar_try_wait(bar, parity)) {}
+#endif
 }
 // global -> shared bulk async copy (TMA engine, SASS UBLKCP), completes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -401,11 +427,12 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
     static_assert(kR == 2, "the packed fp32x2 inner loop assumes two pixel rows per thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [0,64) full/empty mbarriers | stage_hdr[kStages] int4 | desc[kStages][kNT] int4 |
-    //         dv cluster bounds: nmin[M] nmax[M] pmin[M] pmax[M] | drmin[N] drmax[N] (ordered ints) | 128B-aligned ring
+    //         (stage header blocks: see kHdrBytes)  dv cluster bounds: nmin[M] nmax[M] pmin[M] pmax[M] | drmin[N] drmax[N] (ordered ints) | 128B-aligned ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-    int4 *stage_hdr = reinterpret_cast<int4 *>(smem_raw + kBarBytes);
-    int4 *desc = reinterpret_cast<int4 *>(smem_raw + kBarBytes + sizeof(int4) * kStages);
-    int *s_dvnmin = reinterpret_cast<int *>(smem_raw + kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT);
+    unsigned char *stage_blk = smem_raw + kBarBytes;   // kStages blocks of kHdrBytes
+    auto stage_hdr = [&](uint32_t st_) -> int4 * { return reinterpret_cast<int4 *>(stage_blk + st_ * kHdrBytes); };
+    int4 *desc = reinterpret_cast<int4 *>(smem_raw + kBarBytes + kHdrBytes * kStages);
+    int *s_dvnmin = reinterpret_cast<int *>(smem_raw + kBarBytes + kHdrBytes * kStages + sizeof(int4) * kStages * kNT);
     int *s_dvnmax = s_dvnmin + a.M;
     int *s_dvpmin = s_dvnmax + a.M;
     int *s_dvpmax = s_dvpmin + a.M;
@@ -413,7 +440,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
     int *s_drmax = s_drmin + a.N;
     int *s_txany = s_drmax + a.N;   // FUSED: does any pixel of the tile have a non-zero transmit / receive weight?
     int *s_rxany = s_txany + (FUSED ? a.M : 0);
-    const uint32_t ring_off = (uint32_t)((kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * ((FUSED ? 5 : 4) * a.M + (FUSED ? 3 : 2) * a.N) + 127) & ~127u);
+    const uint32_t ring_off = (uint32_t)((kBarBytes + kHdrBytes * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * ((FUSED ? 5 : 4) * a.M + (FUSED ? 3 : 2) * a.N) + 127) & ~127u);
     const uint32_t ring = smem_u32(smem_raw) + ring_off;
     // FUSED == 2: receive-weight table [kNT][kCW*32] float2 (.x/.y = the thread's two pixel rows) behind the ring
     const uint32_t wtab = ring + a.stages * kNT * a.wmax * 8u;
@@ -550,7 +577,8 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
         for (uint32_t it = 0;; ++it) {
             const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
             mbar_wait(bar_full + 8 * s, ph);
-            const int4 hdr = stage_hdr[s]; // kind, m, nt
+            const int4 *hblk = stage_hdr(s);
+            const int4 hdr = hblk[0]; // kind, m, nt, uniform sign of dv
             if (hdr.x == ST_END) break;
             // hdr.y = outer index of the stage (transmit m; receive n when kInnerTx), hdr.z = inner tile (16 receives; 16 transmits)
             const uint32_t outer = (uint32_t)hdr.y, nt = (uint32_t)hdr.z;
@@ -580,14 +608,34 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                 }
             }
             if constexpr (kInnerTx) { // stage scalar = receive path length; t0 is per trace (fetched in the loop, warp-uniform)
+#if QUPS_HDRGEO
+                const float4 prv = reinterpret_cast<const float4 *>(hblk)[1];
+                const float rx = prv.x, ry = prv.y, rz = prv.z;
+#else
                 const float rx = __ldg(a.Pr + 3 * outer), ry = __ldg(a.Pr + 3 * outer + 1), rz = __ldg(a.Pr + 3 * outer + 2);
+#endif
                 pk.dv.x = rx_dist(px[0], py[0], pz[0], rx, ry, rz);
                 pk.dv.y = rx_dist(px[1], py[1], pz[1], rx, ry, rz);
             } else {
+#if QUPS_HDRGEO
+                const float4 pv = reinterpret_cast<const float4 *>(hblk)[1];
+                if (VS && !DV && hdr.w != 0) {
+                    // every pixel of the tile lies strictly on one side of the transmit's focal plane: dv = +-|Pi - Pv| exactly
+                    // (d * (+-1) is exact), no dot product with the normal
+                    const float d0 = rx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z), d1 = rx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z);
+                    pk.dv.x = hdr.w > 0 ? d0 : -d0;
+                    pk.dv.y = hdr.w > 0 ? d1 : -d1;
+                } else {
+                    const float4 nv = reinterpret_cast<const float4 *>(hblk)[2];
+                    pk.dv.x = tx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z, nv.x, nv.y, nv.z, VS, DV);
+                    pk.dv.y = tx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z, nv.x, nv.y, nv.z, VS, DV);
+                }
+#else
                 const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
                 const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
                 pk.dv.x = tx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
                 pk.dv.y = tx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+#endif
                 t0m = pv.w;
             }
             pk.t0 = t0m;
@@ -636,9 +684,18 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
             if (live) {
             if (hdr.x == ST_ALL_FAST) {
                 // every trace FAST with a single window: fully unrolled, branch-free
+#if QUPS_SOFF4
+                const uint4 *so4p = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(hblk) + 64);
+                uint4 so4 = make_uint4(0u, 0u, 0u, 0u);
+#endif
 #pragma unroll
                 for (int j = 0; j < kNT; ++j) {
+#if QUPS_SOFF4
+                    if ((j & 3) == 0) so4 = so4p[j >> 2];
+                    const uint32_t so = (j & 3) == 0 ? so4.x : ((j & 3) == 1 ? so4.y : ((j & 3) == 2 ? so4.z : so4.w));
+#else
                     const uint32_t so = (uint32_t)dsc[j].x;
+#endif
                     if constexpr (kInnerTx) pk.t0 = t0_of(j);
                     if constexpr (!kWeighted) {
                         fast_pair2<INTERP>(pk, dr[j], so, so, sa0, sa1);
@@ -848,10 +905,40 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                     if (lane == 0 && total == 0) atomicAdd(&g_stats[7], 1ull);
                     if (lane < kNT) { atomicAdd(&g_stats[flag], 1ull); if (bytes[1]) atomicAdd(&g_stats[4], 1ull); }
                     if (lane == 0) atomicAdd(&g_stats[all_fast ? 5 : 6], 1ull);
+                    {
+                        const bool fs_only = __all_sync(0xffffffffu, ((flag == TR_FAST && bytes[1] == 0u) || flag == TR_SKIP) || lane >= kNT);
+                        const bool any_dual = __any_sync(0xffffffffu, bytes[1] != 0u && lane < kNT);
+                        const bool any_edge = __any_sync(0xffffffffu, flag == TR_EDGE && lane < kNT);
+                        const bool any_slow = __any_sync(0xffffffffu, flag == TR_SLOW && lane < kNT);
+                        if (lane == 0 && !all_fast) { if (fs_only) atomicAdd(&g_stats[8], 1ull); if (any_dual) atomicAdd(&g_stats[9], 1ull); if (any_edge) atomicAdd(&g_stats[10], 1ull); if (any_slow) atomicAdd(&g_stats[11], 1ull); }
+                    }
+#endif
+                    // stage header payload (warp-uniform loads, issued before the wait so their latency overlaps it)
+                    int sgn = 0;
+#if QUPS_HDRGEO
+                    float4 gA = make_float4(0.f, 0.f, 0.f, 0.f), gB = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (kInnerTx) {
+                        gA = make_float4(__ldg(a.Pr + 3 * outer), __ldg(a.Pr + 3 * outer + 1), __ldg(a.Pr + 3 * outer + 2), 0.f);
+                    } else {
+                        gA = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + outer);
+                        gB = make_float4(__ldg(a.Nv + 3 * outer), __ldg(a.Nv + 3 * outer + 1), __ldg(a.Nv + 3 * outer + 2), 0.f);
+                        // uniform sign of dv over the tile: the positive cluster also holds dv == 0 (sign(0) = 0, where dv = 0 and
+                        // not |Pi - Pv|), so "+1" needs its minimum strictly positive
+                        const int nmin_ = s_dvnmin[outer], nmax_ = s_dvnmax[outer], pmin_ = s_dvpmin[outer], pmax_ = s_dvpmax[outer];
+                        if (nmin_ > nmax_ && pmin_ <= pmax_ && o2f(pmin_) > 0.f) sgn = 1;
+                        else if (pmin_ > pmax_ && nmin_ <= nmax_) sgn = -1;
+                    }
 #endif
                     mbar_wait(bar_empty + 8 * s, ph ^ 1); // slot free (first lap passes immediately)
                     if (lane < kNT) desc[s * kNT + lane] = make_int4((int)soff[0], flag, (int)soff[1], 0);
-                    if (lane == 0) stage_hdr[s] = make_int4(all_fast ? ST_ALL_FAST : ST_MIXED, (int)outer, (int)nt, 0);
+                    if (lane < kNT) reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(stage_hdr(s)) + 64)[lane] = soff[0];
+                    if (lane == 0) {
+#if QUPS_HDRGEO
+                        reinterpret_cast<float4 *>(stage_hdr(s))[1] = gA;
+                        reinterpret_cast<float4 *>(stage_hdr(s))[2] = gB;
+#endif
+                        stage_hdr(s)[0] = make_int4(all_fast ? ST_ALL_FAST : ST_MIXED, (int)outer, (int)nt, sgn);
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * s, total);
                     __syncwarp();
@@ -866,7 +953,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
             const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
             if ((it % nprod) == pw) mbar_wait(bar_empty + 8 * s, ph ^ 1);
             if ((it % nprod) == pw && lane == 0) {
-                stage_hdr[s] = make_int4(ST_END, 0, 0, 0);
+                stage_hdr(s)[0] = make_int4(ST_END, 0, 0, 0);
                 mbar_arrive(bar_full + 8 * s);
             }
         }
@@ -888,7 +975,7 @@ __global__ void __launch_bounds__(256) das_reduce_kernel(float2 *y, const float2
 
 // ---- host side ------------------------------------------------------------------------
 static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax, int fused = 0, uint32_t stages = kStages) {
-    size_t head = kBarBytes + sizeof(int4) * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * ((fused ? 5 : 4) * (size_t)M + (fused ? 3 : 2) * (size_t)N);
+    size_t head = kBarBytes + (size_t)kHdrBytes * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * ((fused ? 5 : 4) * (size_t)M + (fused ? 3 : 2) * (size_t)N);
     head = (head + 127) & ~(size_t)127;
     return head + (size_t)stages * kNT * wmax * 8 + (fused == 2 ? (size_t)kNT * kCW * 32 * 8 : 0);
 }
@@ -1063,7 +1150,9 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
             const double w = (double)tiles * ns / slots;
             const double span = 0.5 * ceil(w) + 0.5 * (w + 0.5);
             const double cost = span / w * (1.0 + 0.09 * ns / t.numNT);
-            if (cost < best * 0.995) { best = cost; nsplit = ns; }     // prefer fewer splits on near-ties
+            // a further split must win by 3 %: measured on the headline grid (2048 tiles, 6.9 waves) two splits ran 1 % slower
+            // than one although the model gives them 1.2 % (second pass of phase 0, two receive working sets in L2, the reduce)
+            if (cost < best * 0.97) { best = cost; nsplit = ns; }
         }
     }
     if (keep) nsplit = 1;                             // kept apertures: each CTA is the only writer of its pixels
@@ -1089,13 +1178,14 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     e = cudaGetLastError();
 #if QUPS_STATS
     {
-        unsigned long long h[8] = {0};
+        unsigned long long h[12] = {0};
         cudaStreamSynchronize(st);
         cudaMemcpyFromSymbol(h, g_stats, sizeof(h));
         fprintf(stderr, "[das_tiled stats] tile %u x %u lpa %u wmax %u stages %u nsplit %u grid %llu\n", t.tA, t.tB, t.lpa, t.wmax, t.stages, t.nsplit, (unsigned long long)(tiles * nsplit));
         fprintf(stderr, "[das_tiled stats] traces FAST %llu SKIP %llu SLOW %llu EDGE %llu split %llu | stages all-fast %llu general %llu (empty %llu)\n",
                 h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
-        unsigned long long z[8] = {0};
+        fprintf(stderr, "[das_tiled stats] general stages: FAST+SKIP only %llu, with dual-window %llu, with EDGE %llu, with SLOW %llu\n", h[8], h[9], h[10], h[11]);
+        unsigned long long z[12] = {0};
         cudaMemcpyToSymbol(g_stats, z, sizeof(z));
     }
 #endif
