@@ -227,7 +227,12 @@ QUPS_API int qups_aperture(const qups_aperture_params *p, void *out, void *out2,
 /* y(l) = sum over dims with ystride==0 of  exp(1i*omega*t) * w(k) * interp1(x(:,v), 1+t, interp, 0),  t = t1(r)+t2(u)
  * Image of the reference argument list (src/interpd.cu:344-349): D broadcast dims of size sizes[d]; dstride is
  * uint64[5*D], column d = element strides of {w, y, t1, t2, x-trace} along dim d (kern/wsinterpd2.m:193-219).
- * The reference reduces with global atomics; this library reduces deterministically inside one thread. */
+ * The reference reduces with global atomics; this library reduces deterministically inside one thread.
+ * dtype F16 = wsinterpd2h / wsinterpdh (src/interpd.cu:422-429,451-458): x, w half2 (w half when w_real), t1 / t2 HALF, y half2
+ * (float2 with y_f32); positions, interpolation and sums in fp32.
+ * Fast path: the canonical look-up-table delay-and-sum (bfDAS -> bfDASLUT -> sample2sep: dense I x N and I x M tables, both
+ * apertures summed, scalar weight, omega = 0, nearest|linear|cubic, fp32 or fp16) runs on the staged DAS kernel in table mode
+ * (qups_last_ws2_kernel() == "ws2_tiled"); everything else takes the generic strided kernel. */
 typedef struct {
     uint32_t struct_size;
     int32_t dtype;
@@ -279,7 +284,7 @@ QUPS_API int qups_greens(const qups_greens_params *p, void *y, const void *Pi, c
  * shape 0 'full' (Lz = Lx+Ly-1), 1 'same' (Lz = Lx, centred as MATLAB conv), 2 'valid' (Lz = max(Lx-Ly+1, 0)). */
 typedef struct {
     uint32_t struct_size;
-    int32_t dtype;      /* QUPS_F32 | QUPS_F64 */
+    int32_t dtype;      /* QUPS_F32 | QUPS_F64 | QUPS_F16 (half / half2 storage, fp32 accumulation: convh / convch) */
     int32_t is_complex; /* interleaved complex data */
     int32_t shape;
     uint64_t C, S, Lx, Ly, yC, yS;
@@ -293,6 +298,9 @@ QUPS_API int qups_version(void);
 QUPS_API uint64_t qups_launch_count(int reset);
 /* name of the DAS kernel variant the last qups_das call on this thread dispatched to */
 QUPS_API const char *qups_last_das_kernel(void);
+/* "ws2_tiled" (canonical look-up-table delay-and-sum on the staged kernel) or "wsinterpd2" (generic strided kernel) for the
+ * last qups_wsinterpd2 / qups_wsinterpd call of the process */
+QUPS_API const char *qups_last_ws2_kernel(void);
 
 #ifdef __cplusplus
 }

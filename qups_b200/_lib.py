@@ -19,7 +19,7 @@ INTERP = {"nearest": NEAREST, "linear": LINEAR, "cubic": CUBIC, "lanczos3": LANC
 
 EXPORTS = (
     "qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
-    "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_greens", "qups_convd", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel",
+    "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_greens", "qups_convd", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel", "qups_last_ws2_kernel",
 )
 
 
@@ -144,6 +144,7 @@ def lib() -> C.CDLL:
         getattr(L, f).restype = C.c_int
     L.qups_last_error.restype = C.c_char_p
     L.qups_last_das_kernel.restype = C.c_char_p
+    L.qups_last_ws2_kernel.restype = C.c_char_p
     L.qups_launch_count.restype = C.c_uint64
     L.qups_launch_count.argtypes = [C.c_int]
     _lib = L
@@ -161,3 +162,7 @@ def launch_count(reset: bool = False) -> int:
 
 def last_das_kernel() -> str:
     return lib().qups_last_das_kernel().decode()
+
+
+def last_ws2_kernel() -> str:
+    return lib().qups_last_ws2_kernel().decode()

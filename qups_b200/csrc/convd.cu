@@ -31,6 +31,20 @@ template <> struct cv<double2> {
     static __device__ double2 zero() { return make_double2(0.0, 0.0); }
 };
 
+// storage type -> accumulation type: half data (convh / convch, src/convd.cu:141,153) is widened per element — exactly — and
+// accumulated in fp32 (the reference accumulates in half), rounded to half once per output element
+template <typename T> struct io { using acc = T; static __device__ T ld(const T *p, uint64_t i) { return p[i]; } static __device__ void st(T *p, uint64_t i, T v) { p[i] = v; } };
+template <> struct io<__half> {
+    using acc = float;
+    static __device__ float ld(const __half *p, uint64_t i) { return __half2float(p[i]); }
+    static __device__ void st(__half *p, uint64_t i, float v) { p[i] = __float2half_rn(v); }
+};
+template <> struct io<__half2> {
+    using acc = float2;
+    static __device__ float2 ld(const __half2 *p, uint64_t i) { return __half22float2(p[i]); }
+    static __device__ void st(__half2 *p, uint64_t i, float2 v) { p[i] = __floats2half2_rn(v.x, v.y); }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) convd_kernel(T *z, const T *x, const T *y, uint64_t C, uint64_t S, long long Lx, long long Ly,
                                                     long long Lz, long long l0, uint64_t yC, uint64_t yS) {
@@ -42,9 +56,10 @@ __global__ void __launch_bounds__(256) convd_kernel(T *z, const T *x, const T *y
         const long long k = (long long)l + l0;               // full-convolution index
         long long i0 = k - (Ly - 1); if (i0 < 0) i0 = 0;
         long long i1 = k; if (i1 > Lx - 1) i1 = Lx - 1;
-        T acc = cv<T>::zero();
-        for (long long i = i0; i <= i1; ++i) acc = cv<T>::mac(acc, xp[(uint64_t)i * C], yp[(uint64_t)(k - i) * yC]);
-        z[o] = acc;
+        using A = typename io<T>::acc;
+        A acc = cv<A>::zero();
+        for (long long i = i0; i <= i1; ++i) acc = cv<A>::mac(acc, io<T>::ld(xp, (uint64_t)i * C), io<T>::ld(yp, (uint64_t)(k - i) * yC));
+        io<T>::st(z, o, acc);
     }
 }
 
@@ -62,6 +77,7 @@ int launch_convd(const qups_convd_params &p, void *z, const void *x, const void 
 #define QUPS_CV(T) convd_kernel<T><<<grid, 256, 0, st>>>((T *)z, (const T *)x, (const T *)y, p.C, p.S, Lx, Ly, Lz, l0, p.yC, p.yS)
     if (p.dtype == QUPS_F32) { if (p.is_complex) QUPS_CV(float2); else QUPS_CV(float); }
     else if (p.dtype == QUPS_F64) { if (p.is_complex) QUPS_CV(double2); else QUPS_CV(double); }
+    else if (p.dtype == QUPS_F16) { if (p.is_complex) QUPS_CV(__half2); else QUPS_CV(__half); }
     else return -3;
 #undef QUPS_CV
     count_launch(1);

@@ -28,6 +28,10 @@ template <typename R> struct DasArgs {
     double pitch_hint[2], c_hint; // optional launcher hints (pixel pitch along I1 / I2, sound speed); 0 = unknown
     int fused;      // 0 = no closed-form apodization; otherwise `fa` is valid (fp32 paths only)
     FusedApod fa;
+    // table-driven delays (staged kernel only; set by launch_wsinterpd2 for the canonical bfDAS form, else nullptr):
+    // xq = 1 + (lut_tm[m * I + i] + lut_tn[n * I + i]), y = w * sum; Pi / Pr / Pv4 / Nv / cinv are then unused
+    const float *lut_tn = nullptr, *lut_tm = nullptr, *lut_w = nullptr;
+    int lut_wcplx = 0;
 };
 
 // launch entry points implemented in das_generic.cu / das_tiled.cu
@@ -42,6 +46,8 @@ int launch_modulate(DOUT *xo, const DIN *x, const R *t0, int t0_stride, uint64_t
 // element-wise precision conversion of a complex array (n complex elements)
 int launch_half2_to_float2(float2 *dst, const __half2 *src, uint64_t n, cudaStream_t st);
 int launch_float2_to_half2(__half2 *dst, const float2 *src, uint64_t n, cudaStream_t st);
+int launch_half_to_float(float *dst, const __half *src, uint64_t n, cudaStream_t st);   // n real elements
+int launch_float_to_half(__half *dst, const float *src, uint64_t n, cudaStream_t st);
 
 // tiled fast path (fp32 data, sum over both apertures, scalar cinv, no apodization arrays)
 struct TiledPlan {

@@ -227,6 +227,14 @@ __global__ void __launch_bounds__(256) f2h_kernel(__half2 *dst, const float2 *sr
         dst[i] = __floats2half2_rn(v.x, v.y);
     }
 }
+__global__ void __launch_bounds__(256) h2f1_kernel(float *dst, const __half *src, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = __half2float(__ldg(src + i));
+}
+__global__ void __launch_bounds__(256) f2h1_kernel(__half *dst, const float *src, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = __float2half_rn(__ldg(src + i));
+}
 static unsigned conv_grid(uint64_t n) {
     const uint64_t g = (n + 255) / 256;
     return (unsigned)(g < 148ull * 16 ? (g ? g : 1) : 148ull * 16);
@@ -234,6 +242,18 @@ static unsigned conv_grid(uint64_t n) {
 int launch_half2_to_float2(float2 *dst, const __half2 *src, uint64_t n, cudaStream_t st) {
     if (n == 0) return 0;
     h2f_kernel<<<conv_grid(n), 256, 0, st>>>(dst, src, n);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+int launch_half_to_float(float *dst, const __half *src, uint64_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    h2f1_kernel<<<conv_grid(n), 256, 0, st>>>(dst, src, n);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+int launch_float_to_half(__half *dst, const float *src, uint64_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    f2h1_kernel<<<conv_grid(n), 256, 0, st>>>(dst, src, n);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -126,6 +126,11 @@ struct TiledArgs {
     uint64_t total_elems;   // T*N*M
     FusedApod fa;           // closed-form apodization evaluated in-kernel (FUSED > 0)
     uint32_t I3;
+    // LUT mode (bfDAS / bfDASLUT / sample2sep -> wsinterpd2 with separable delay tables, src/interpd.cu:344-396): the path
+    // lengths come from tables in SAMPLES instead of geometry, xq = 1 + (tm(i,m) + tn(i,n))   (kern/wsinterpd2.m:290)
+    const float *tn, *tm;   // tn[n * I + i] (the aperture whose traces are contiguous in x), tm[m * I + i]
+    const float *wscal;     // scalar weight applied to the sum (real, or complex when wcplx)
+    int wcplx;
 };
 
 // ---- small PTX wrappers -----------------------------------------------------
@@ -232,11 +237,17 @@ struct Pack2 {
     float2 dv;
     float cinv, t0, fs;
 };
-template <int INTERP>
+template <int INTERP, int LUT = 0>
 __device__ __forceinline__ void fast_pair2(const Pack2 &c, float2 dr, uint32_t soff, uint32_t soff1, float2 &acc0, float2 &acc1) {
     float2 xq;
-    xq.x = sample_pos(c.dv.x, dr.x, c.cinv, c.t0, c.fs);
-    xq.y = sample_pos(c.dv.y, dr.y, c.cinv, c.t0, c.fs);
+    if (LUT) { // tables already in samples: 1 + (t_m + t_n), two individually rounded adds (identical to the general form
+               // with cinv = 1, t0 = 0, fs = 1, whose extra operations are exact)
+        xq.x = __fadd_rn(1.0f, __fadd_rn(c.dv.x, dr.x));
+        xq.y = __fadd_rn(1.0f, __fadd_rn(c.dv.y, dr.y));
+    } else {
+        xq.x = sample_pos(c.dv.x, dr.x, c.cinv, c.t0, c.fs);
+        xq.y = sample_pos(c.dv.y, dr.y, c.cinv, c.t0, c.fs);
+    }
     if (INTERP == 2) {
 #if QUPS_MAGIC
         // floor + float->int + address in one go: for 0 <= xq < 2^23, add.rm(xq, 2^23) = 2^23 + floor(xq) exactly
@@ -419,11 +430,12 @@ __device__ __forceinline__ int tap_window(float xlo, float xhi, float Tf, int T,
 //        traces of a stage are 16 transmits of ONE receive, the registers hold dv(i, m) of a transmit tile and the stage
 //        scalar is dr(i, n) — so every stage adds to y(:,n).  (sample_pos only adds dv + dr: the swap is bit-neutral.)
 //        y is pre-zeroed by the launcher; a CTA owns its pixels (nsplit = 1), so the read-modify-write needs no atomics.
-template <int INTERP, int NAP, int FUSED, int KEEP>
+template <int INTERP, int NAP, int FUSED, int KEEP, int LUT = 0>
 __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_kernel(const TiledArgs a) {
     constexpr int kThreads = threads_of(INTERP);
     constexpr bool kInnerTx = (KEEP == 2); // the 16 traces of a stage run over transmits instead of receives
     static_assert(KEEP == 0 || (NAP == 0 && FUSED == 0), "kept apertures: plain weights only");
+    static_assert(LUT == 0 || (NAP == 0 && FUSED == 0 && KEEP == 0), "table-driven delays: plain sum over both apertures");
     static_assert(kR == 2, "the packed fp32x2 inner loop assumes two pixel rows per thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [0,64) full/empty mbarriers | stage_hdr[kStages] int4 | desc[kStages][kNT] int4 |
@@ -476,8 +488,9 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
     }
     __syncthreads();
 
-    const float cinv = __ldg(a.cinv);
-    const float fs = a.fs;
+    // LUT: the tables are sample indices; the general position formula with cinv = 1, t0 = 0, fs = 1 is then exactly 1 + (tm + tn)
+    const float cinv = LUT ? 1.0f : __ldg(a.cinv);
+    const float fs = LUT ? 1.0f : a.fs;
     const float Tf = (float)a.T;
     const bool VS = a.VS, DV = a.DV;
 
@@ -493,9 +506,12 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
             // out-of-image lanes shadow a valid pixel so they never widen the windows
             const uint32_t ca = ia < a.IA ? ia : a.IA - 1, cb = ib < a.IB ? ib : a.IB - 1;
             pix[r] = (uint64_t)ca * a.sA + (uint64_t)cb * a.sB + (uint64_t)tc * a.sC;
-            px[r] = __ldg(a.Pi + 3 * pix[r]);
-            py[r] = __ldg(a.Pi + 3 * pix[r] + 1);
-            pz[r] = __ldg(a.Pi + 3 * pix[r] + 2);
+            if constexpr (LUT) { px[r] = py[r] = pz[r] = 0.f; }
+            else {
+                px[r] = __ldg(a.Pi + 3 * pix[r]);
+                py[r] = __ldg(a.Pi + 3 * pix[r] + 1);
+                pz[r] = __ldg(a.Pi + 3 * pix[r] + 2);
+            }
         }
         // per-pixel part of the apodization index (NAP arrays, real weights)
         uint32_t aoff[NAP > 0 ? NAP : 1][kR];
@@ -519,15 +535,19 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
         // dv is tracked in two clusters, dv < 0 and dv >= 0: a focused transmit flips the sign of dv at the focal
         // plane (kern/das_spec.m:429), so a tile crossing it touches two disjoint windows of each trace
         for (uint32_t m = 0; m < a.M; ++m) {
-            const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
-            const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
+            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+            if constexpr (!LUT) {
+                pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
+                nx = __ldg(a.Nv + 3 * m); ny = __ldg(a.Nv + 3 * m + 1); nz = __ldg(a.Nv + 3 * m + 2);
+            }
             int nlo = INT_MAX, nhi = INT_MIN, plo = INT_MAX, phi = INT_MIN;
 #pragma unroll
             for (int r = 0; r < kR; ++r) {
-                const float d = tx_dist(px[r], py[r], pz[r], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+                const float d = LUT ? __ldg(a.tm + (uint64_t)m * a.I + pix[r]) : tx_dist(px[r], py[r], pz[r], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
                 const int o = f2o(d);
-                if (d < 0.f) { nlo = min(nlo, o); nhi = max(nhi, o); }
-                else         { plo = min(plo, o); phi = max(phi, o); }
+                if (!LUT && d < 0.f) { nlo = min(nlo, o); nhi = max(nhi, o); }   // (table delays: one cluster)
+                else                 { plo = min(plo, o); phi = max(phi, o); }
             }
             nlo = __reduce_min_sync(0xffffffffu, nlo);
             nhi = __reduce_max_sync(0xffffffffu, nhi);
@@ -545,11 +565,12 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
             }
         }
         for (uint32_t n = kInnerTx ? 0u : nt0 * kNT; n < (kInnerTx ? a.N : min(nt1 * kNT, a.N)); ++n) {
-            const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
+            float rx = 0.f, ry = 0.f, rz = 0.f;
+            if constexpr (!LUT) { rx = __ldg(a.Pr + 3 * n); ry = __ldg(a.Pr + 3 * n + 1); rz = __ldg(a.Pr + 3 * n + 2); }
             int lo = INT_MAX, hi = INT_MIN;
 #pragma unroll
             for (int r = 0; r < kR; ++r) {
-                const int o = f2o(rx_dist(px[r], py[r], pz[r], rx, ry, rz));
+                const int o = f2o(LUT ? __ldg(a.tn + (uint64_t)n * a.I + pix[r]) : rx_dist(px[r], py[r], pz[r], rx, ry, rz));
                 lo = min(lo, o);
                 hi = max(hi, o);
             }
@@ -594,6 +615,10 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                         const float nxj = __ldg(a.Nv + 3 * mj), nyj = __ldg(a.Nv + 3 * mj + 1), nzj = __ldg(a.Nv + 3 * mj + 2);
                         dr[j].x = tx_dist(px[0], py[0], pz[0], pvj.x, pvj.y, pvj.z, nxj, nyj, nzj, VS, DV);
                         dr[j].y = tx_dist(px[1], py[1], pz[1], pvj.x, pvj.y, pvj.z, nxj, nyj, nzj, VS, DV);
+                    } else if constexpr (LUT) {
+                        const uint32_t n = min(nt * kNT + j, a.N - 1);
+                        dr[j].x = __ldg(a.tn + (uint64_t)n * a.I + pix[0]);
+                        dr[j].y = __ldg(a.tn + (uint64_t)n * a.I + pix[1]);
                     } else {
                         const uint32_t n = min(nt * kNT + j, a.N - 1);
                         const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
@@ -616,6 +641,9 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
 #endif
                 pk.dv.x = rx_dist(px[0], py[0], pz[0], rx, ry, rz);
                 pk.dv.y = rx_dist(px[1], py[1], pz[1], rx, ry, rz);
+            } else if constexpr (LUT) {
+                pk.dv.x = __ldg(a.tm + (uint64_t)m * a.I + pix[0]);
+                pk.dv.y = __ldg(a.tm + (uint64_t)m * a.I + pix[1]);
             } else {
 #if QUPS_HDRGEO
                 const float4 pv = reinterpret_cast<const float4 *>(hblk)[1];
@@ -698,10 +726,10 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
 #endif
                     if constexpr (kInnerTx) pk.t0 = t0_of(j);
                     if constexpr (!kWeighted) {
-                        fast_pair2<INTERP>(pk, dr[j], so, so, sa0, sa1);
+                        fast_pair2<INTERP, LUT>(pk, dr[j], so, so, sa0, sa1);
                     } else { // a .* interp1(...): sample into temporaries, then one weighted accumulate per pixel
                         float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
-                        fast_pair2<INTERP>(pk, dr[j], so, so, t0, t1);
+                        fast_pair2<INTERP, LUT>(pk, dr[j], so, so, t0, t1);
                         const float2 w = apw2(j);
                         sa0.x = fmaf(w.x, t0.x, sa0.x); sa0.y = fmaf(w.x, t0.y, sa0.y);
                         sa1.x = fmaf(w.y, t1.x, sa1.x); sa1.y = fmaf(w.y, t1.y, sa1.y);
@@ -725,7 +753,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                     const uint32_t so0 = (uint32_t)(neg0 ? d.x : d.z), so1 = (uint32_t)(neg1 ? d.x : d.z);
                     float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
                     if (d.y == TR_FAST) {
-                        fast_pair2<INTERP>(pk, drj, so0, so1, t0, t1);
+                        fast_pair2<INTERP, LUT>(pk, drj, so0, so1, t0, t1);
                     } else {
                         const uint32_t n = kInnerTx ? outer : nt * kNT + j, mm = kInnerTx ? nt * kNT + j : outer;
                         const uint64_t nm = a.tpose ? ((uint64_t)mm + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)mm * a.N);
@@ -736,7 +764,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                         const bool in2 = interior<INTERP>(xq0, Tf) && interior<INTERP>(xq1, Tf);
                         const bool out2 = !(xq0 >= 1.0f && xq0 <= Tf) && !(xq1 >= 1.0f && xq1 <= Tf);
                         if (d.y == TR_EDGE && __all_sync(0xffffffffu, in2)) {
-                            fast_pair2<INTERP>(pk, drj, so0, so1, t0, t1);
+                            fast_pair2<INTERP, LUT>(pk, drj, so0, so1, t0, t1);
                         } else if (d.y == TR_EDGE && __all_sync(0xffffffffu, out2)) {
                             continue;
                         } else {
@@ -764,6 +792,15 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+        }
+        if constexpr (LUT) { // y = w * sum (scalar weight; w = 1 leaves the sum untouched)
+            const float wr = __ldg(a.wscal), wi = a.wcplx ? __ldg(a.wscal + 1) : 0.f;
+            if (a.wcplx) {
+                acc0 = make_float2(wr * acc0.x - wi * acc0.y, wr * acc0.y + wi * acc0.x);
+                acc1 = make_float2(wr * acc1.x - wi * acc1.y, wr * acc1.y + wi * acc1.x);
+            } else if (wr != 1.0f) {
+                acc0.x *= wr; acc0.y *= wr; acc1.x *= wr; acc1.y *= wr;
+            }
         }
         if constexpr (KEEP != 0) {
             // nothing left to write: every stage updated y in place
@@ -820,7 +857,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                         xl = sample_pos(rlo_t, o2f(s_drmin[ml]), cinv, t0hi_t, fs);
                         xh = sample_pos(rhi_t, o2f(s_drmax[ml]), cinv, t0lo_t, fs);
                     } else {
-                        const float t0l = __ldg(a.Pv4 + 4 * ml + 3);
+                        const float t0l = LUT ? 0.f : __ldg(a.Pv4 + 4 * ml + 3);
                         xl = sample_pos(o2f(min(s_dvnmin[ml], s_dvpmin[ml])), rlo_t, cinv, t0l, fs);
                         xh = sample_pos(o2f(max(s_dvnmax[ml], s_dvpmax[ml])), rhi_t, cinv, t0l, fs);
                     }
@@ -840,7 +877,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                     uint32_t bytes[2] = {0u, 0u}, soff[2] = {0u, 0u}, dst[2] = {0u, 0u};
                     const float2 *src[2] = {nullptr, nullptr};
                     if (has) {
-                        const float t0m = __ldg(a.Pv4 + 4 * m + 3);
+                        const float t0m = LUT ? 0.f : __ldg(a.Pv4 + 4 * m + 3);
                         const int nmin = s_dvnmin[m], nmax = s_dvnmax[m], pmin = s_dvpmin[m], pmax = s_dvpmax[m];
                         const float rlo = o2f(s_drmin[n]), rhi = o2f(s_drmax[n]); // receive path-length bounds of this trace
                         const float xlo = sample_pos(o2f(min(nmin, pmin)), rlo, cinv, t0m, fs);
@@ -917,7 +954,9 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                     int sgn = 0;
 #if QUPS_HDRGEO
                     float4 gA = make_float4(0.f, 0.f, 0.f, 0.f), gB = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if constexpr (kInnerTx) {
+                    if constexpr (LUT) {
+                        // nothing: the consumers read their delays from the tables
+                    } else if constexpr (kInnerTx) {
                         gA = make_float4(__ldg(a.Pr + 3 * outer), __ldg(a.Pr + 3 * outer + 1), __ldg(a.Pr + 3 * outer + 2), 0.f);
                     } else {
                         gA = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + outer);
@@ -1014,6 +1053,8 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     t.N = (uint32_t)a.N; t.M = (uint32_t)a.M; t.T = (uint32_t)a.T;
     t.fs = a.fs; t.VS = a.VS; t.DV = a.DV; t.tpose = a.tpose; t.accumulate = a.accumulate;
     t.total_elems = a.T * a.N * a.M;
+    const bool lut = a.lut_tn != nullptr;   // table-driven delays (wsinterpd2 canonical form): no geometry arrays at all
+    t.tn = a.lut_tn; t.tm = a.lut_tm; t.wscal = a.lut_w; t.wcplx = a.lut_wcplx;
     const int keep = a.keep_tx ? 1 : (a.keep_rx ? 2 : 0);
     t.numNT = ((keep == 2 ? t.M : t.N) + kNT - 1) / kNT; // inner tiles: receives, or transmits when the receive dimension is kept
     // axis assignment: lanes along I2 (the slow axis of a ZXY ScanCartesian, src/ScanCartesian.m:11) when
@@ -1025,7 +1066,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     t.IC = (uint32_t)a.I3; t.sC = a.I1 * a.I2;
     double span_m = 0.0; // path-length spread across one tile (metres, sum of the two tile extents)
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    const bool noprobe = (cudaStreamIsCapturing(st, &cap) != cudaSuccess) || cap != cudaStreamCaptureStatusNone || getenv("QUPS_B200_NOPROBE");
+    const bool noprobe = lut || (cudaStreamIsCapturing(st, &cap) != cudaSuccess) || cap != cudaStreamCaptureStatusNone || getenv("QUPS_B200_NOPROBE");
     // ---- tile shape: 512 pixels as tA x tB with a lpa x (32/lpa) x 2 warp patch, chosen so that the delay spread across the
     // tile (~ pixel spacing x extent) is smallest: square-ish on isotropic grids (32 x 16, patch 8 x 4 x 2 — measured best on the
     // headline grid), narrow along a coarsely sampled axis (e.g. one image column per element pitch).  The spacing is read
@@ -1130,6 +1171,11 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     QUPS_PICK_I(0) QUPS_PICK_I(1) QUPS_PICK_I(2)
 #undef QUPS_PICK_I
 #undef QUPS_PICK
+    if (lut) {
+        kern = nullptr;
+        if (a.S == 0 && fused == 0 && keep == 0)
+            kern = ip == 0 ? das_tiled_kernel<0, 0, 0, 0, 1> : (ip == 1 ? das_tiled_kernel<1, 0, 0, 0, 1> : das_tiled_kernel<2, 0, 0, 0, 1>);
+    }
     if (!kern) return (int)cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
+#include "das_args.cuh"
 #include "other_kernels.cuh"
 
 namespace qups {
@@ -458,6 +459,26 @@ int launch_greens(const qups_greens_params &p, void *y, const void *Pi, const vo
                   const void *kern, cudaStream_t st) {
     if (p.S == 0 || p.N == 0 || p.M == 0) return 0;
     if (p.N > 0x7fffffffull || p.M > 65535) return -3;
+    if (p.dtype == QUPS_F16) {
+        // greensh (src/greens.cu:113-122): half2 waveform in, half2 traces out, fp32 geometry.  The waveform (T samples) is widened
+        // once — exactly — and the fp32 kernels run as they are: fp32 delays and fp32 accumulation over the scatterers (the
+        // reference accumulates in half2), one rounding to half2 per output sample at the end (or none with y_f32).
+        float2 *k32 = nullptr, *y32 = nullptr;
+        const uint64_t ny = p.S * p.N * p.M;
+        cudaError_t e = ws_alloc((void **)&k32, sizeof(float2) * (p.T ? p.T : 1), st);
+        if (e == cudaSuccess && !p.y_f32) e = ws_alloc((void **)&y32, sizeof(float2) * ny, st);
+        int rc = e == cudaSuccess ? 0 : -4;
+        if (rc == 0) rc = launch_half2_to_float2(k32, (const __half2 *)kern, p.T, st);
+        if (rc == 0) {
+            qups_greens_params q = p;
+            q.dtype = QUPS_F32;
+            rc = launch_greens(q, p.y_f32 ? y : (void *)y32, Pi, a, Pr, Pv, k32, st);
+        }
+        if (rc == 0 && !p.y_f32) rc = launch_float2_to_half2((__half2 *)y, y32, ny, st);
+        if (k32) ws_free(k32, st);
+        if (y32) ws_free(y32, st);
+        return rc;
+    }
     const uint64_t E = p.E ? p.E : 1;
     dim3 grid((unsigned)p.N, (unsigned)p.M), block(kGThreads);
     // bucketed kernel unless the waveform is so long that its reach exceeds the bucket table, or the exact

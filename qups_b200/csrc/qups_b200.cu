@@ -358,6 +358,7 @@ extern "C" {
 int qups_version(void) { return QUPS_B200_VERSION; }
 const char *qups_last_error(void) { return g_err; }
 const char *qups_last_das_kernel(void) { return g_last_das; }
+const char *qups_last_ws2_kernel(void) { return qups::last_ws2_kernel_name(); }
 uint64_t qups_launch_count(int reset) {
     const uint64_t v = g_launches;
     if (reset) g_launches = 0;

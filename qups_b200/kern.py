@@ -357,12 +357,14 @@ def _swapdim(t, a, b):
     return t.transpose(a, b) if a != b else t
 
 
-def wsinterpd2(x, t1, t2, dim=1, w=1, sdim=(), interp="linear", extrapval=0, omega=0):
+def wsinterpd2(x, t1, t2, dim=1, w=1, sdim=(), interp="linear", extrapval=0, omega=0, _prec=None, _y_f32=False):
     """Weighted-sum interpolation with separable delays — mirror of ``kern/wsinterpd2.m:1``.
 
     y = sum_{sdim} w .* exp(omega .* (t1+t2)) .* interp1(x, 1 + t1 + t2, interp, 0)
     `dim`/`sdim` are 1-based as in MATLAB.  Only extrapval = 0 (what every hot-path caller passes:
     src/ChannelData.m:1445, src/UltrasoundSystem.m:843) is implemented.
+    _prec='halfT' selects the half kernels (wsinterpd2h, src/interpd.cu:451-458): data, weights AND delay tables are passed as
+    fp16 (torch has no complex-half type, so the mirror narrows here); the result comes back widened to complex64.
     """
     if interp not in _lib.INTERP:
         raise ValueError("Interp option not recognized: " + str(interp))
@@ -378,6 +380,7 @@ def wsinterpd2(x, t1, t2, dim=1, w=1, sdim=(), interp="linear", extrapval=0, ome
     numpy_out = not any(isinstance(v, torch.Tensor) and v.is_cuda for v in (x, t1, t2, w))
     dev = torch.device("cuda", torch.cuda.current_device())
     prec = "double" if xt.dtype in (torch.float64, torch.complex128) else "single"
+    half = _prec == "halfT"
     rt, ct = _RT[prec], _CT[prec]
     d0 = dim - 1
     sd = [s - 1 for s in (sdim if np.ndim(sdim) else [sdim])]
@@ -403,7 +406,8 @@ def wsinterpd2(x, t1, t2, dim=1, w=1, sdim=(), interp="linear", extrapval=0, ome
     strides = [_stride5(ws), _stride5(osz), _stride5(s1), _stride5(s2), _stride5((1,) + tuple(xs[1:]))]
     p = Ws2Params()
     p.struct_size = C.sizeof(Ws2Params)
-    p.dtype = _DT[prec]
+    p.dtype = _DT["halfT"] if half else _DT[prec]
+    p.y_f32 = int(bool(_y_f32))
     p.T, p.D, p.interp = T, nd, _lib.INTERP[interp]
     w_real = not wt.is_complex()
     p.w_real = int(w_real)
@@ -412,23 +416,29 @@ def wsinterpd2(x, t1, t2, dim=1, w=1, sdim=(), interp="linear", extrapval=0, ome
         p.sizes[k] = dsz[k]
         for r in range(5):
             p.dstride[r + 5 * k] = strides[r][k]
-    dX = _cplx_buf(xt.reshape(xs), prec, dev)
-    d1 = _colmajor(t1t.reshape(s1), rt, dev)
-    d2 = _colmajor(t2t.reshape(s2), rt, dev) if t2t is not None else None
-    dW = _colmajor(wt.reshape(ws), rt, dev) if w_real else _cplx_buf(wt.reshape(ws), prec, dev)
-    yb = torch.zeros(int(np.prod(osz)), dtype=ct, device=dev)
+    tt = torch.float16 if half else rt
+    dX = _cplx_buf(xt.reshape(xs), "halfT" if half else prec, dev)
+    d1 = _colmajor(t1t.reshape(s1), tt, dev)
+    d2 = _colmajor(t2t.reshape(s2), tt, dev) if t2t is not None else None
+    dW = _colmajor(wt.reshape(ws), tt, dev) if w_real else _cplx_buf(wt.reshape(ws), "halfT" if half else prec, dev)
+    if half and not _y_f32:
+        yb = torch.zeros((int(np.prod(osz)), 2), dtype=torch.float16, device=dev)
+    else:
+        yb = torch.zeros(int(np.prod(osz)), dtype=ct, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().qups_wsinterpd2(C.byref(p), _ptr(yb), _ptr(dW), _ptr(dX), _ptr(d1), _ptr(d2), _stream(dev)))
+    if yb.dtype == torch.float16:
+        yb = torch.view_as_complex(yb.float())
     y = _swapdim(_from_colmajor(yb, osz), 0, d0)
     return np.asfortranarray(y.cpu().numpy()) if numpy_out else y
 
 
-def wsinterpd(x, t, dim=1, w=1, sdim=(), interp="linear", extrapval=0, omega=0):
+def wsinterpd(x, t, dim=1, w=1, sdim=(), interp="linear", extrapval=0, omega=0, _prec=None, _y_f32=False):
     """Mirror of ``kern/wsinterpd.m:1`` (single delay table)."""
-    return wsinterpd2(x, t, None, dim, w, sdim, interp, extrapval, omega)
+    return wsinterpd2(x, t, None, dim, w, sdim, interp, extrapval, omega, _prec=_prec, _y_f32=_y_f32)
 
 
-def convd(x, y=None, dim=None, shape="full"):
+def convd(x, y=None, dim=None, shape="full", _half=False):
     """Batched 1-D convolution along one dimension — mirror of ``kern/convd.m:1`` (GPU branch :135-201).
 
     C = convd(A, B, dim, shape); B defaults to conj(flip(A)) (auto-correlation); dim (1-based) defaults to the
@@ -465,13 +475,20 @@ def convd(x, y=None, dim=None, shape="full"):
     dX, dY = _colmajor(xt.reshape(xs), dt, dev), _colmajor(yt.reshape(ys), dt, dev)
     osz = tuple(xs[:d0]) + (Lz,) + tuple(xs[d0 + 1:])
     z = torch.zeros(int(np.prod(osz)), dtype=dt, device=dev)
+    if _half:  # convh / convch (src/convd.cu:141,153): half storage; the mirror narrows / widens around the call
+        if dbl: raise QupsError(-3, "half convolution of double data")
+        nar = lambda t: (torch.view_as_real(t).to(torch.float16).contiguous() if t.is_complex() else t.to(torch.float16).contiguous())
+        dX, dY = nar(dX), nar(dY)
+        z = torch.zeros((z.numel(), 2) if cplx else (z.numel(),), dtype=torch.float16, device=dev)
     p = _lib.ConvdParams()
     p.struct_size = C.sizeof(_lib.ConvdParams)
-    p.dtype, p.is_complex = (_lib.F64 if dbl else _lib.F32), int(cplx)
+    p.dtype, p.is_complex = (_lib.F16 if _half else (_lib.F64 if dbl else _lib.F32)), int(cplx)
     p.shape = {"full": 0, "same": 1, "valid": 2}[shape]
     p.C, p.S, p.Lx, p.Ly, p.yC, p.yS = C_, S_, Lx, Ly, yC, yS
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().qups_convd(C.byref(p), _ptr(z), _ptr(dX), _ptr(dY), _stream(dev)))
+    if _half:
+        z = torch.view_as_complex(z.float()) if cplx else z.float()
     out = _from_colmajor(z, osz)
     lag_shape = [1] * nd
     lag_shape[d0] = -1

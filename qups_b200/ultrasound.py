@@ -504,9 +504,12 @@ def focusTx(chd: "ChannelData", seq: "Sequence", tx: np.ndarray, interp="cubic",
 
 def greens_raw(ps, amp, pn, pv, kern_s, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, interp="cubic", device=None,
                dtype=np.float32):
-    """Direct call of the qups_greens C ABI; returns a CUDA tensor of logical shape (T, N, M)."""
+    """Direct call of the qups_greens C ABI; returns a CUDA tensor of logical shape (T, N, M).
+    dtype=np.float16 selects the half variant (greensh, src/greens.cu:113-122): half2 waveform in, half2 traces out
+    (returned widened to complex64), fp32 geometry."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    rt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    half = np.dtype(dtype) == np.float16
+    rt = torch.float32 if np.dtype(dtype) in (np.float32, np.float16) else torch.float64
     ct = torch.complex64 if rt == torch.float32 else torch.complex128
     col = lambda a_: torch.from_numpy(np.ascontiguousarray(np.asarray(a_, np.float64).T)).to(dev, rt).contiguous()
     dPs, dPn, dPv = col(ps), col(pn), col(pv)
@@ -514,9 +517,12 @@ def greens_raw(ps, amp, pn, pv, kern_s, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, i
     dK = torch.from_numpy(np.asarray(kern_s, np.complex128)).to(dev, ct).contiguous()
     N, M = dPn.shape[0], dPv.shape[0]
     y = torch.empty((M, N, T), dtype=ct, device=dev)
+    if half:
+        dK = torch.view_as_real(dK).to(torch.float16).contiguous()
+        y = torch.empty((M, N, T, 2), dtype=torch.float16, device=dev)
     p = GreensParams()
     p.struct_size = C.sizeof(GreensParams)
-    p.dtype = _lib.F32 if rt == torch.float32 else _lib.F64
+    p.dtype = _lib.F16 if half else (_lib.F32 if rt == torch.float32 else _lib.F64)
     p.I, p.S, p.T, p.N, p.M, p.E = dPs.shape[0], T, dK.shape[0], N, M, 1
     p.n0, p.interp = int(n0), _lib.INTERP[interp]
     p.t0x, p.fs, p.fsr, p.c0, p.R0 = float(wv_t0), float(fs), float(fsr), float(c0), float(R0)
@@ -524,4 +530,6 @@ def greens_raw(ps, amp, pn, pv, kern_s, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, i
     with torch.cuda.device(dev):
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(_lib.lib().qups_greens(C.byref(p), vp(y), vp(dPs), vp(dA), vp(dPn), vp(dPv), vp(dK), st))
+    if half:
+        y = torch.view_as_complex(y.float())
     return y.permute(2, 1, 0)
