@@ -347,11 +347,14 @@ class LutRunner:
         self.w = torch.ones(1, dtype=f32, device=dev)
         p = _lib.Ws2Params()
         p.struct_size = C.sizeof(_lib.Ws2Params)
-        p.dtype, p.T, p.D, p.interp, p.w_real, p.omega = _lib.F32, T, 4, _lib.INTERP[P.interp], 1, 0.0
-        sizes = [1, I, N, M]
+        p.dtype, p.T, p.D, p.interp, p.w_real, p.omega = _lib.F32, T, 5, _lib.INTERP[P.interp], 1, 0.0
+        # the MATLAB shapes of sample2sep with apdim = [4, 5]: tables I1 x I2 x I3 x N x 1 and I1 x I2 x I3 x 1 x M, x is T x 1 x 1 x N x M
+        I1, I2, I3 = P.Isz
+        sizes = [I1, I2, I3, N, M]
         #          w  y  t1 t2 x      t1 = transmit table (I x 1 x M), t2 = receive table (I x N)
-        strides = [[0, 0, 0, 0, 0], [0, 1, 1, 1, 0], [0, 0, 0, I, 1], [0, 0, I, 0, N]]
-        for k in range(4):
+        strides = [[0, 1, 1, 1, 0], [0, I1, I1, I1, 0], [0, I1 * I2, I1 * I2, I1 * I2, 0], [0, 0, 0, I, 1], [0, 0, I, 0, N]]
+        strides = [st if sizes[k] > 1 else [0] * 5 for k, st in enumerate(strides)]
+        for k in range(5):
             p.sizes[k] = sizes[k]
             for r in range(5):
                 p.dstride[r + 5 * k] = strides[k][r]
@@ -428,7 +431,7 @@ def also_legs(dev, peak, log):
         out["bfdas"] = {"workload": workload_label(P, "bfdas", o) + " via qups_wsinterpd2 (tau_rx I x N, tau_tx I x M)",
                         "ms_per_step": ms, "value": P.I / ms / 1e3, "unit": UNIT, "compulsory_bytes": comp,
                         "compulsory_GBps": comp / ms / 1e6, "frac_of_hbm_peak": comp / ms / 1e6 / peak,
-                        "kernel": qups_b200.last_ws2_kernel() if hasattr(qups_b200, "last_ws2_kernel") else "wsinterpd2"}
+                        "kernel": qups_b200.last_ws2_kernel()}
         # same problem through qups_das on the same device data: the two paths must agree to tolerance
         d = DasRunner(P, {"dtype": "f32", "fmod": 0.0, "kind": "das"}, dev, x_dev=x)
         d.step()
@@ -613,7 +616,7 @@ def main():
     W = max(3, a.warmup)
     for _ in range(W):
         y = run_step()
-    kern_name = qups_b200.last_das_kernel() if o["kind"] in ("das", "c5") else ("greens" if o["kind"] == "greens" else "wsinterpd2")
+    kern_name = qups_b200.last_das_kernel() if o["kind"] in ("das", "c5") else ("greens" if o["kind"] == "greens" else qups_b200.last_ws2_kernel())
     barrier()
     sampler = ClockSampler(local).start()  # every rank samples ITS GPU: a clock-locked / throttled peer must show up in the line
     time.sleep(0.25)
