@@ -291,6 +291,48 @@ typedef struct {
 } qups_convd_params;
 QUPS_API int qups_convd(const qups_convd_params *p, void *z, const void *x, const void *y, qups_stream_t stream);
 
+/* ---- pwznxcorr -------------------------------------------------------------------------- */
+/* Pair-wise windowed zero-normalised cross-correlation: replaces the whole-array expressions of kern/pwznxcorr.m:142-266
+ * (native branch `iflt = false`; integer lags; U = 1; multi = false).  x is T x N x F (time, channels, frames; real or
+ * interleaved complex), y is T x N' x F x L complex (N' = N - stride for ref NEIGHBOR, else N):
+ *   y(t,n,f,l) = kernfun(xlz .* xrz_l) ./ (sqrt(kernfun(|xlz|^2)) .* sqrt(kernfun(|xrz_l|^2)))          (norm)
+ *   xlz = xl - kernfun(xl),  xrz_l = conj(circshift(xr, -lag_l)) - kernfun(...)                           (zero)
+ *   kernfun(z) = convn(z, w, 'same') along time; with `pad` ceil(max|lag|) zeros are appended before the circular shift
+ * ref: NEIGHBOR channel n vs n + stride | CENTER mean of the median channel(s) | X0 a given signal x0 (T x {1|N} x {1|F},
+ * complex).  lags: HOST int32[L]; w: DEVICE real[W] window weights (the reference's scalar W is ones(W), unscaled). */
+typedef enum { QUPS_XC_NEIGHBOR = 0, QUPS_XC_CENTER = 1, QUPS_XC_X0 = 2 } qups_xcorr_ref;
+typedef struct {
+    uint32_t struct_size;
+    int32_t dtype;      /* QUPS_F32 | QUPS_F64 */
+    int32_t is_complex; /* x is interleaved complex (y and x0 always are) */
+    int32_t ref;        /* qups_xcorr_ref */
+    int32_t zero, norm, pad;
+    uint32_t stride;
+    uint32_t L, W;
+    uint64_t T, N, F;
+    uint64_t x0N, x0F;  /* extents of x0 along channels / frames (1 = broadcast); ignored unless ref == X0 */
+} qups_xcorr_params;
+QUPS_API int qups_pwznxcorr(const qups_xcorr_params *p, void *y, const void *x, const void *x0, const void *w, const int32_t *lags,
+                            qups_stream_t stream);
+
+/* ---- refocus (REFoCUS transmit decoding) -------------------------------------------------------- */
+/* Applies a per-frequency decoding matrix to channel data: replaces src/UltrasoundSystem.m:3729-3757
+ *   x = fft(x, T, tdim) .* exp(-2i*pi*f.*t0);  y(:,:,e) = sum_v Hi(e,v,:) .* x(:,:,v);  y = ifft(y .* exp(+2i*pi*f.*min(t0)))
+ * with f = (0:T-1)*fs/T (src/ChannelData.m:1491).  x: T x N x V complex (time, receives, pulses), Hi: E x V x T complex
+ * (elements x pulses x frequency, the reference's `Hi` output), y: T x N x E complex.  t0: HOST array of n_t0 (1 or V)
+ * start times; *t0_out (HOST, may be NULL) receives min(t0), the start time of the decoded data (:3762).
+ * The decoder itself (tikhonov / adjoint / pinv, :3690-3727) depends only on the sequence and stays host code.
+ * T must be a power of two <= 8192 (QUPS_ERR_UNSUPPORTED otherwise: zero-pad, as the reference's help recommends). */
+typedef struct {
+    uint32_t struct_size;
+    int32_t dtype;      /* QUPS_F32 */
+    uint64_t T, N, V, E;
+    uint32_t n_t0, reserved_;
+    double fs;
+} qups_refocus_params;
+QUPS_API int qups_refocus(const qups_refocus_params *p, void *y, const void *x, const void *Hi, const double *t0, double *t0_out,
+                          qups_stream_t stream);
+
 /* ---- misc --------------------------------------------------------------- */
 QUPS_API const char *qups_last_error(void);
 QUPS_API int qups_version(void);

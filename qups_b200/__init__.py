@@ -7,6 +7,6 @@ include/qups_b200.h); this package is the thin host-side mirror of the
 reference's operator interface used by tests and bench.  No CPU fallback.
 """
 from ._lib import QupsError, lib, launch_count, last_das_kernel, last_ws2_kernel, LIB_PATH  # noqa: F401
-from .kern import das_spec, wsinterpd2, wsinterpd, convd, cohfac, dmas, pcf, slsc, FusedApod  # noqa: F401
+from .kern import das_spec, wsinterpd2, wsinterpd, convd, cohfac, dmas, pcf, slsc, pwznxcorr, FusedApod  # noqa: F401
 
-__all__ = ["das_spec", "wsinterpd2", "wsinterpd", "convd", "cohfac", "dmas", "pcf", "slsc", "FusedApod", "QupsError", "lib", "launch_count", "last_das_kernel", "last_ws2_kernel"]
+__all__ = ["das_spec", "wsinterpd2", "wsinterpd", "convd", "cohfac", "dmas", "pcf", "slsc", "pwznxcorr", "FusedApod", "QupsError", "lib", "launch_count", "last_das_kernel", "last_ws2_kernel"]

@@ -19,7 +19,7 @@ INTERP = {"nearest": NEAREST, "linear": LINEAR, "cubic": CUBIC, "lanczos3": LANC
 
 EXPORTS = (
     "qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
-    "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_greens", "qups_convd", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel", "qups_last_ws2_kernel",
+    "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_greens", "qups_convd", "qups_pwznxcorr", "qups_refocus", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel", "qups_last_ws2_kernel",
 )
 
 
@@ -98,6 +98,28 @@ class PrepParams(C.Structure):
 IN_REAL_F32, IN_CPLX_F32, IN_REAL_I16, IN_REAL_F64 = range(4)
 
 
+class XcorrParams(C.Structure):
+    """qups_xcorr_params: pair-wise windowed zero-normalised cross-correlation (kern/pwznxcorr.m)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("dtype", C.c_int32), ("is_complex", C.c_int32), ("ref", C.c_int32),
+        ("zero", C.c_int32), ("norm", C.c_int32), ("pad", C.c_int32), ("stride", C.c_uint32),
+        ("L", C.c_uint32), ("W", C.c_uint32),
+        ("T", C.c_uint64), ("N", C.c_uint64), ("F", C.c_uint64), ("x0N", C.c_uint64), ("x0F", C.c_uint64),
+    ]
+
+
+XC_NEIGHBOR, XC_CENTER, XC_X0 = range(3)
+
+
+class RefocusParams(C.Structure):
+    """qups_refocus_params: REFoCUS decode (src/UltrasoundSystem.m:3729-3757)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("dtype", C.c_int32),
+        ("T", C.c_uint64), ("N", C.c_uint64), ("V", C.c_uint64), ("E", C.c_uint64),
+        ("n_t0", C.c_uint32), ("reserved_", C.c_uint32), ("fs", C.c_double),
+    ]
+
+
 class ApertureParams(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("dtype", C.c_int32), ("op", C.c_int32), ("nlags", C.c_uint32),
@@ -139,6 +161,10 @@ def lib() -> C.CDLL:
     L.qups_greens.argtypes = [C.POINTER(GreensParams), vp, vp, vp, vp, vp, vp, vp]
     L.qups_convd.argtypes = [C.POINTER(ConvdParams), vp, vp, vp, vp]
     L.qups_convd.restype = C.c_int
+    L.qups_pwznxcorr.argtypes = [C.POINTER(XcorrParams), vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
+    L.qups_pwznxcorr.restype = C.c_int
+    L.qups_refocus.argtypes = [C.POINTER(RefocusParams), vp, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
+    L.qups_refocus.restype = C.c_int
     for f in ("qups_das", "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
               "qups_greens", "qups_version"):
         getattr(L, f).restype = C.c_int

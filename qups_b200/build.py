@@ -31,6 +31,8 @@ UNITS = {
     "apod_gen.cu": ["-fmad=false"],
     "chd_prep.cu": [],
     "aperture.cu": [],
+    "xcorr.cu": [],
+    "refocus.cu": [],
     "das_tiled.cu": [],
     "qups_b200.cu": [],
 }

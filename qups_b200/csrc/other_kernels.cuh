@@ -32,4 +32,14 @@ int launch_chd_prep(PrepArgs a, cudaStream_t st);
 
 // aperture-domain post-processing (aperture.cu); lags is a HOST array of p.nlags entries
 int launch_aperture(const qups_aperture_params &p, void *out, void *out2, const void *b, const uint32_t *lags, cudaStream_t st);
+
+// pair-wise windowed cross-correlation (xcorr.cu); lags_dev is a DEVICE int32[L]
+size_t xcorr_smem_bytes(uint32_t W, int dbl);
+int launch_pwznxcorr(int dbl, void *y, const void *x, const void *x0, const void *w, const int32_t *lags_dev, uint32_t T, uint32_t P,
+                     uint32_t N, uint32_t F, uint32_t L, uint32_t W, int ref, int zero, int norm, int x_complex, uint32_t S,
+                     uint32_t x0N, uint32_t x0F, cudaStream_t st);
+
+// REFoCUS decode (refocus.cu); dt_host: V doubles t0(v) - min(t0).  returns 0, a cudaError_t (> 0) or -3 (T not a power of two <= 8192)
+int launch_refocus(void *y, const void *x, const void *Hi, const double *dt_host, uint64_t T, uint64_t N, uint64_t V, uint64_t E,
+                   double fs, cudaStream_t st);
 } // namespace qups

@@ -1,6 +1,7 @@
 // qups_b200.cu — the extern "C" boundary of libqups_b200.so (see include/qups_b200.h).
 // Argument validation, dtype dispatch, frame loop (kern/das_spec.m:371-373),
 // modulation pre-pass (kern/das_spec.m:413-417) and the host-buffer variants.
+#include <vector>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -678,6 +679,52 @@ int qups_convd(const qups_convd_params *p, void *z, const void *x, const void *y
     if (int e = launch_convd(*p, z, x, y, (cudaStream_t)stream)) {
         if (e == -3) return fail(QUPS_ERR_UNSUPPORTED, "unsupported dtype for convd");
         return cuda_fail(e, "convd kernel");
+    }
+    return 0;
+}
+
+int qups_pwznxcorr(const qups_xcorr_params *p, void *y, const void *x, const void *x0, const void *w, const int32_t *lags,
+                   qups_stream_t stream) {
+    g_err[0] = 0;
+    if (!p || p->struct_size != sizeof(qups_xcorr_params)) return fail(QUPS_ERR_INVALID, "bad qups_xcorr_params");
+    if (p->dtype != QUPS_F32 && p->dtype != QUPS_F64) return fail(QUPS_ERR_UNSUPPORTED, "pwznxcorr: dtype must be F32 or F64");
+    if (p->ref < 0 || p->ref > 2) return fail(QUPS_ERR_INVALID, "pwznxcorr: ref must be neighbor(0), center(1) or x0(2)");
+    if (p->L == 0 || p->W == 0 || p->T == 0 || p->N == 0 || p->F == 0) return fail(QUPS_ERR_INVALID, "pwznxcorr: empty input");
+    if (p->ref == QUPS_XC_NEIGHBOR && (p->stride == 0 || p->stride >= p->N)) return fail(QUPS_ERR_INVALID, "pwznxcorr: stride must be in [1, N)");
+    if (p->ref == QUPS_XC_X0 && (!x0 || !((p->x0N == 1 || p->x0N == p->N) && (p->x0F == 1 || p->x0F == p->F))))
+        return fail(QUPS_ERR_INVALID, "pwznxcorr: x0 must be T x {1|N} x {1|F}");
+    if (p->T >= (1ull << 30) || p->N > 65535 || p->F > 65535) return fail(QUPS_ERR_UNSUPPORTED, "pwznxcorr: T < 2^30, N and F <= 65535");
+    if (xcorr_smem_bytes(p->W, p->dtype == QUPS_F64) > 200 * 1024) return fail(QUPS_ERR_UNSUPPORTED, "pwznxcorr: window too long for the shared-memory tile");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t amax = 0;
+    for (uint32_t l = 0; l < p->L; ++l) { const int64_t v = lags[l] < 0 ? -(int64_t)lags[l] : lags[l]; if (v > amax) amax = v; }
+    const uint32_t P = p->pad ? (uint32_t)amax : 0u; // kern/pwznxcorr.m:182
+    int32_t *dl = nullptr;
+    if (cudaError_t ce = ws_alloc((void **)&dl, sizeof(int32_t) * p->L, st)) return cuda_fail((int)ce, "pwznxcorr: lag table");
+    cudaError_t ce = cudaMemcpyAsync(dl, lags, sizeof(int32_t) * p->L, cudaMemcpyHostToDevice, st);
+    int e = ce ? (int)ce : launch_pwznxcorr(p->dtype == QUPS_F64, y, x, x0, w, dl, (uint32_t)p->T, P, (uint32_t)p->N, (uint32_t)p->F, p->L, p->W,
+                                             p->ref, p->zero != 0, p->norm != 0, p->is_complex != 0, p->stride, (uint32_t)p->x0N, (uint32_t)p->x0F, st);
+    // the lag table is pageable host memory: the copy above has been staged by the driver when cudaMemcpyAsync returns
+    ws_free(dl, st);
+    if (e) return cuda_fail(e, "pwznxcorr kernel");
+    return 0;
+}
+
+int qups_refocus(const qups_refocus_params *p, void *y, const void *x, const void *Hi, const double *t0, double *t0_out,
+                 qups_stream_t stream) {
+    g_err[0] = 0;
+    if (!p || p->struct_size != sizeof(qups_refocus_params)) return fail(QUPS_ERR_INVALID, "bad qups_refocus_params");
+    if (p->dtype != QUPS_F32) return fail(QUPS_ERR_UNSUPPORTED, "refocus: dtype must be F32");
+    if (!t0 || !(p->n_t0 == 1 || p->n_t0 == p->V)) return fail(QUPS_ERR_INVALID, "refocus: t0 must hold 1 or V start times");
+    if (!(p->fs > 0)) return fail(QUPS_ERR_INVALID, "refocus: fs must be positive");
+    double tmin = t0[0];
+    for (uint32_t v = 1; v < p->n_t0; ++v) tmin = t0[v] < tmin ? t0[v] : tmin;
+    std::vector<double> dt(p->V ? p->V : 1, 0.0);
+    for (uint64_t v = 0; v < p->V; ++v) dt[v] = t0[p->n_t0 == 1 ? 0 : v] - tmin;
+    if (t0_out) *t0_out = tmin;
+    if (int e = launch_refocus(y, x, Hi, dt.data(), p->T, p->N, p->V, p->E, p->fs, (cudaStream_t)stream)) {
+        if (e == -3) return fail(QUPS_ERR_UNSUPPORTED, "refocus: T must be a power of two <= 8192 (zero-pad the data)");
+        return cuda_fail(e, "refocus kernels");
     }
     return 0;
 }

@@ -559,3 +559,85 @@ def slsc(x, dim=None, L=None, method="average"):
     L = max(1, A // 4) if L is None else L
     lags = list(range(1, int(L) + 1)) if np.ndim(L) == 0 else [int(v) for v in np.ravel(L)]
     return _aperture(_lib.APD_SLSC_AVERAGE if method == "average" else _lib.APD_SLSC_ENSEMBLE, x, dim, lags)
+
+
+# ---- pair-wise windowed zero-normalised cross-correlation (kern/pwznxcorr.m) ------------------------------------------
+def pwznxcorr(x, lags, W=None, U=1, *, pad=True, zero=True, norm=True, ref="neighbor", stride=1, x0=None, tdim=1, ndim=2,
+              ldim=None, multi=False):
+    """y = pwznxcorr(x, lags, W, U, ...) — mirror of ``kern/pwznxcorr.m:1`` (argument block :113-131, native branch).
+
+    x: N-D data, time along `tdim`, channels along `ndim` (1-based).  lags: integer lags (a scalar L means -L:L, :142-143);
+    W: window length (ones(W), unscaled, :147-150) or a weight vector along time; default max(ceil(max|lags|/2), 1).
+    Returns the correlation with the channel dimension N - stride ('neighbor') or N ('center' / 'x0') long and the lags
+    along dimension `ldim` (default ndims(x) + 1).  Fractional lags, U > 1 and multi = true are the reference's
+    interpd / resample / convd branches and are not on this path (rejected).
+    """
+    if U != 1: raise _lib.QupsError(-3, "pwznxcorr: upsampling (U > 1) is not supported")
+    if multi: raise _lib.QupsError(-3, "pwznxcorr: multi = true is not supported")
+    if ref not in ("neighbor", "center", "x0"): raise ValueError("ref must be one of {'neighbor', 'center', 'x0'}")
+    lg = np.atleast_1d(np.asarray(lags, dtype=np.float64)).ravel()
+    if not np.all(np.isfinite(lg)): raise ValueError("lags must be finite")
+    if not np.all(lg == np.floor(lg)): raise _lib.QupsError(-3, "pwznxcorr: fractional lags are not supported")
+    if lg.size == 1: lg = np.arange(-lg[0], lg[0] + 1)
+    lg = lg.astype(np.int64)
+    if W is None: W = max(int(np.ceil(np.max(np.abs(lg)) / 2)), 1)
+    xt = _as_tensor(x)
+    numpy_out = not (isinstance(x, torch.Tensor) and x.is_cuda)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dbl = xt.dtype in (torch.float64, torch.complex128)
+    ct, rt = (torch.complex128, torch.float64) if dbl else (torch.complex64, torch.float32)
+    if np.ndim(W) == 0:
+        wv = torch.ones(int(W), dtype=rt)
+    else:
+        Wa = np.asarray(W)
+        wsz = list(Wa.shape) + [1] * max(0, max(tdim, ndim) - Wa.ndim)
+        if any(s != 1 for d, s in enumerate(wsz) if d != tdim - 1 and d != ndim - 1):
+            raise ValueError("The filter weights w must be scalar in all dimensions except time (%d) and channel (%d)." % (tdim, ndim))  # QUPS:pwznxcorr:incompatibleWeightSize
+        if wsz[ndim - 1] != 1 and Wa.ndim >= ndim: raise _lib.QupsError(-3, "pwznxcorr: channel-dimension weights (multi) are not supported")
+        wv = torch.as_tensor(Wa.reshape(-1), dtype=rt)
+    nd = max(xt.ndim, tdim, ndim)
+    xs = _sz(xt, nd)
+    xv = xt.reshape(xs)
+    order = [tdim - 1, ndim - 1] + [d for d in range(nd) if d not in (tdim - 1, ndim - 1)]
+    xp = xv.permute(order)
+    T, N = xp.shape[0], xp.shape[1]
+    rest = tuple(xp.shape[2:])
+    F = int(np.prod(rest)) if rest else 1
+    cplx = xt.is_complex()
+    dX = _colmajor(xp.reshape(T, N, F).to(ct if cplx else rt), ct if cplx else rt, dev)
+    dX0, x0N, x0F = None, 1, 1
+    if ref == "x0":
+        if x0 is None: raise ValueError("ref = 'x0' needs the reference data x0")
+        x0t = _as_tensor(x0)
+        x0s = _sz(x0t, nd)
+        x0p = x0t.reshape(x0s).permute(order)
+        if x0p.shape[0] != T: raise _lib.QupsError(-3, "pwznxcorr: x0 must have the time extent of x")
+        x0N, x0F = x0p.shape[1], int(np.prod(x0p.shape[2:])) if nd > 2 else 1
+        if x0N not in (1, N) or x0F not in (1, F): raise AssertionError("x and x0 must have compatible dimensions")
+        dX0 = _colmajor(x0p.reshape(T, x0N, x0F).to(ct), ct, dev)
+    Nout = N - int(stride) if ref == "neighbor" else N
+    L = int(lg.size)
+    y = torch.empty(T * Nout * F * L, dtype=ct, device=dev)
+    p = _lib.XcorrParams()
+    p.struct_size = C.sizeof(_lib.XcorrParams)
+    p.dtype, p.is_complex = (_lib.F64 if dbl else _lib.F32), int(cplx)
+    p.ref = {"neighbor": _lib.XC_NEIGHBOR, "center": _lib.XC_CENTER, "x0": _lib.XC_X0}[ref]
+    p.zero, p.norm, p.pad, p.stride = int(bool(zero)), int(bool(norm)), int(bool(pad)), int(stride)
+    p.L, p.W, p.T, p.N, p.F, p.x0N, p.x0F = L, int(wv.numel()), T, N, F, x0N, x0F
+    dW = wv.to(dev).contiguous()
+    lgc = (C.c_int32 * L)(*[int(v) for v in lg])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().qups_pwznxcorr(C.byref(p), _ptr(y), _ptr(dX), _ptr(dX0), _ptr(dW), lgc, _stream(dev)))
+    out = _from_colmajor(y, (T, Nout, F, L)).reshape((T, Nout) + rest + (L,))   # frames were flattened row-major above
+    # back to the caller's dimension order, lags along ldim
+    inv = [0] * nd
+    for i, d in enumerate(order): inv[d] = i
+    out = out.permute(inv + [nd])                                   # x's dims, then lags
+    ld = (nd + 1) if ldim is None else int(ldim)
+    if ld <= nd:
+        if out.shape[ld - 1] != 1: raise AssertionError("the lag dimension must be a singleton dimension of x")
+        out = out.squeeze(ld - 1).movedim(-1, ld - 1)
+    elif ld > nd + 1:
+        out = out.reshape(tuple(out.shape[:-1]) + (1,) * (ld - nd - 1) + (L,))
+    if not cplx and not norm: out = out.real
+    return np.asfortranarray(out.cpu().numpy()) if numpy_out else out

@@ -176,6 +176,7 @@ class Sequence:
     type: str = "FSA"
     focus: Optional[np.ndarray] = None
     c0: float = 1540.0
+    apd: Optional[np.ndarray] = None   # elements x pulses apodization matrix (Sequence.apodization_, e.g. hadamard(M)); None = default
 
 
 @dataclass
@@ -462,6 +463,8 @@ def seq_delays(seq: "Sequence", tx: np.ndarray) -> np.ndarray:
 def seq_apodization(seq: "Sequence", tx: np.ndarray) -> np.ndarray:
     """Sequence.apodization(tx) default (src/Sequence.m:951-960)."""
     M = np.asarray(tx).shape[1]
+    if getattr(seq, "apd", None) is not None:
+        return np.asarray(seq.apd)
     if seq.type == "FSA":
         return np.eye(M)
     return np.ones((M, np.asarray(seq.focus).shape[1]))
@@ -500,6 +503,62 @@ def focusTx(chd: "ChannelData", seq: "Sequence", tx: np.ndarray, interp="cubic",
     y = ws2(x4, t1, t2, 1, w, (3,), interp, 0, 0)         # T' x N x 1 x M'
     y = y[:, :, 0, :]
     return ChannelData(y, t0 if np.ndim(t0) else float(t0), fs)
+
+
+def refocus(chd: "ChannelData", seq: "Sequence", tx: np.ndarray, method="tikhonov", gamma=None):
+    """[chd, Hi] = refocus(us, chd, seq, 'method', method, 'gamma', gamma) — mirror of src/UltrasoundSystem.m:3505-3768.
+
+    Host logic as in the reference (:3690-3727, evaluated in float64): encoding matrix H = a.' .* exp(-2j*pi*f.*tau.')
+    per frequency, weights w = pagenorm(H,2)^-2, decoder Hi = (H'H + gamma w I) \ H.' | H.' w | w pinv(H), NaN -> 0.
+    The data path (:3729-3757: fft, time-alignment phase, tensor-times-matrix over the transmit dimension, ifft) is ONE
+    C-ABI call, qups_refocus.  Returns (ChannelData with t0 = min(t0), Hi as an E x V x T array)."""
+    if method not in ("tikhonov", "adjoint", "pinv"):
+        raise ValueError("method must be one of {'tikhonov', 'adjoint', 'pinv'}")
+    x = chd.data
+    xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.asarray(x))
+    if xt.ndim != 3: raise ValueError("refocus: data must be T x N x M")
+    T, N, V = (int(v) for v in xt.shape)
+    fs = float(chd.fs)
+    tau = np.asarray(seq_delays(seq, tx), np.float64)                     # E x V  (:3690)
+    a = seq_apodization(seq, tx) * np.ones(tau.shape)                     # E x V  (:3691)
+    E = tau.shape[0]
+    if tau.shape[1] != V: raise ValueError("refocus: the sequence has %d pulses, the data %d transmits" % (tau.shape[1], V))
+    if gamma is None: gamma = 10.0 * (N / 10.0) ** 2                       # (:3683)
+    f = np.arange(T) * fs / T                                              # chd.fftaxis (src/ChannelData.m:1491)
+    H = a.T[None] * np.exp(-2j * np.pi * f[:, None, None] * tau.T[None])   # pages first: T x V x E  (:3697)
+    with np.errstate(divide="ignore"):
+        w = np.linalg.norm(H, 2, axis=(1, 2)) ** -2.0                      # pagenorm(H, 2).^-2  (:3702)
+    if method == "tikhonov":
+        if N != E: raise ValueError("Arrays have incompatible sizes for this operation.")  # gamma .* w .* eye(chd.N) + H'H (:3709-3710)
+        A = np.conj(np.swapaxes(H, 1, 2)) @ H + (float(gamma) * w)[:, None, None] * np.eye(E)[None]
+        Hi = np.zeros((T, E, V), np.complex128)
+        for k in range(T):
+            if np.all(np.isfinite(A[k])):
+                try: Hi[k] = np.linalg.solve(A[k], H[k].T)                 # pagemldivide(A, pagetranspose(H))  (:3712)
+                except np.linalg.LinAlgError: Hi[k] = np.nan
+            else: Hi[k] = np.nan
+    elif method == "adjoint":
+        Hi = np.swapaxes(H, 1, 2) * w[:, None, None]                        # (:3715)
+    else:
+        Hi = w[:, None, None] * np.linalg.pinv(H)                          # (:3719)
+    Hi = np.where(np.isnan(Hi), 0, Hi)                                      # (:3727)
+    Hi = np.ascontiguousarray(np.transpose(Hi, (1, 2, 0)))                  # E x V x T
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dX = kern._colmajor(xt.to(torch.complex64), torch.complex64, dev)
+    dH = kern._colmajor(torch.from_numpy(Hi), torch.complex64, dev)
+    y = torch.empty(T * N * E, dtype=torch.complex64, device=dev)
+    t0 = np.atleast_1d(np.asarray(chd.t0, np.float64)).reshape(-1)
+    if t0.size not in (1, V): raise ValueError("refocus: t0 must be scalar or per transmit")
+    p = _lib.RefocusParams()
+    p.struct_size = C.sizeof(_lib.RefocusParams)
+    p.dtype, p.T, p.N, p.V, p.E, p.n_t0, p.fs = _lib.F32, T, N, V, E, int(t0.size), fs
+    t0c = (C.c_double * int(t0.size))(*[float(v) for v in t0])
+    t0o = C.c_double(0.0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().qups_refocus(C.byref(p), kern._ptr(y), kern._ptr(dX), kern._ptr(dH), t0c, C.byref(t0o), kern._stream(dev)))
+    out = kern._from_colmajor(y, (T, N, E))
+    if not (isinstance(x, torch.Tensor) and x.is_cuda): out = np.asfortranarray(out.cpu().numpy())
+    return ChannelData(out, float(t0o.value), fs), Hi
 
 
 def greens_raw(ps, amp, pn, pv, kern_s, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, interp="cubic", device=None,

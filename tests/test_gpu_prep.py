@@ -41,7 +41,7 @@ def test_casts(kind):
     assert np.allclose(H.astype(np.complex64), want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
 
 
-@pytest.mark.parametrize("T", [256, 2048, 100, 777, 1500, 4096])
+@pytest.mark.parametrize("T", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 100, 777, 1500, 4096, 8192])
 def test_hilbert_matches_float64_fft(T):
     from oracle import prep_np
     chd, x = _chd(T, 3, 2, "real", seed=T)
