@@ -127,27 +127,21 @@ __global__ void __launch_bounds__(1024) chd_prep_kernel(const PrepArgs a) {
             // power-of-two length: global -> [top forward group] -> shared ... -> [bottom group: forward stages, weights,
             // inverse stages in registers] -> ... shared -> [top inverse group] -> global.  The trace crosses shared memory
             // 2 * (groups - 1) times (n = 2048: 6 passes; the radix-2 version: 22 + load + weights + store)
-            auto lds = [&](uint32_t i) { return s[padi(i)]; };
-            auto sts = [&](uint32_t i, float2 v) { s[padi(i)] = v; };
             auto ldg = [&](uint32_t i) { return load_in(i); };
             auto stg = [&](uint32_t i, float2 v) { store_out(i, v); };
-            auto mid = [&](uint32_t i, float2 v) { // position i holds frequency bitrev(i)
-                const float w = hweight(log2n ? (uint64_t)(__brev(i) >> (32 - log2n)) : 0ull);
+            // analytic-signal weights in the bit-reversed layout: position i holds frequency bitrev(i), so the positive
+            // frequencies (k < n/2) are the EVEN positions, k = 0 is position 0 and k = n/2 is position 1
+            auto mid = [&](uint32_t i, float2 v) {
+                const float w = (i < 2 || L == 1) ? 1.f : ((i & 1) ? 0.f : 2.f);
                 return make_float2(v.x * w, v.y * w);
             };
-            if (log2n == 0) {
-                if (tid == 0) store_out(0, load_in(0));
-            } else if (log2n == rb) { // a single group: everything in registers
-                if (rb == 3) fft_bottom<3>(n, tw, ldg, stg, mid); else if (rb == 2) fft_bottom<2>(n, tw, ldg, stg, mid); else fft_bottom<1>(n, tw, ldg, stg, mid);
-            } else {
-                fft_group<3, false>(n, log2n, tw, ldg, sts);
-                __syncthreads();
-                for (uint32_t st = log2n - 3; st > rb; st -= 3) { fft_group<3, false>(n, st, tw, lds, sts); __syncthreads(); }
-                if (rb == 3) fft_bottom<3>(n, tw, lds, sts, mid); else if (rb == 2) fft_bottom<2>(n, tw, lds, sts, mid); else fft_bottom<1>(n, tw, lds, sts, mid);
-                __syncthreads();
-                for (uint32_t st = rb + 3; st < log2n; st += 3) { fft_group<3, true>(n, st, tw, lds, sts); __syncthreads(); }
-                fft_group<3, true>(n, log2n, tw, lds, stg);
-                __syncthreads(); // the next trace's first pass overwrites s
+            switch (log2n) {
+            case 0: if (tid == 0) store_out(0, load_in(0)); break;
+#define QUPS_FFT_CASE(LG_) case LG_: fft_roundtrip_c<LG_>(s, tw, ldg, stg, mid); break;
+            QUPS_FFT_CASE(1) QUPS_FFT_CASE(2) QUPS_FFT_CASE(3) QUPS_FFT_CASE(4) QUPS_FFT_CASE(5) QUPS_FFT_CASE(6) QUPS_FFT_CASE(7)
+            QUPS_FFT_CASE(8) QUPS_FFT_CASE(9) QUPS_FFT_CASE(10) QUPS_FFT_CASE(11) QUPS_FFT_CASE(12) QUPS_FFT_CASE(13)
+#undef QUPS_FFT_CASE
+            default: break; // longer traces do not fit shared memory: rejected by the launcher
             }
         }
     }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace qups {
 
@@ -145,6 +146,84 @@ __device__ inline void fft_inv_dit(float2 *s, const float2 *tw, uint32_t n, uint
     if (rb == 3) fft_group<3, true>(n, 3, tw, ld, stf); else if (rb == 2) fft_group<2, true>(n, 2, tw, ld, stf); else if (rb == 1) fft_group<1, true>(n, 1, tw, ld, stf);
     __syncthreads();
     for (uint32_t st = rb + 3; st <= log2n; st += 3) { fft_group<3, true>(n, st, tw, ld, stf); __syncthreads(); }
+}
+
+// ---- compile-time specialised passes (LG = log2 of the length) -------------------------------------------------------
+// With the length known at compile time every index of a pass is `padi(base) + constant`: for a group stride q the
+// padded offset of element j is j*q + 2*((j*q) >> 4) (k' < q never carries into the 16-element pad period), so the loads
+// and stores take immediate offsets and the integer work per element disappears (ncu on the run-time version: ALU pipe
+// 58 %, FMA 30 %, issue 74 % — index arithmetic, not butterflies, filled the issue slots).
+template <int I, int N, class F> __device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+__host__ __device__ constexpr uint32_t pad_off(uint32_t e) { return e + ((e >> 4) << 1); }
+
+// radix-8 pass with top stage ST of a 2^LG transform.  ld(i, p) / stf(i, p, v): i = logical index, p = padded index (a
+// global-memory functor ignores p, a shared-memory one ignores i)
+template <int LG, int ST, bool INV, class Ld, class St>
+__device__ __forceinline__ void fft_group_c(const float2 *tw, Ld ld, St stf) {
+    constexpr uint32_t q = 1u << (ST - 3), tasks = (1u << LG) >> 3;
+    for (uint32_t task = threadIdx.x; task < tasks; task += blockDim.x) {
+        const uint32_t kp = task & (q - 1), base = ((task >> (ST - 3)) << ST) + kp, pb = padi(base);
+        float2 e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = ld(base + j * q, pb + pad_off(j * q));
+        // twiddles W^m = exp(-i*pi*k'*m/(4q)): m = 1, 2, 4, 3 from the stage tables (no wrap: 3k' < 4q), 5..7 as products
+        float2 w[8];
+        w[1] = tw[4 * q - 1 + kp]; w[2] = tw[2 * q - 1 + kp]; w[4] = tw[q - 1 + kp]; w[3] = tw[4 * q - 1 + 3 * kp];
+        if (INV) { w[1].y = -w[1].y; w[2].y = -w[2].y; w[3].y = -w[3].y; w[4].y = -w[4].y; }
+        w[5] = cmulf(w[4], w[1]); w[6] = cmulf(w[4], w[2]); w[7] = cmulf(w[4], w[3]);
+        constexpr int br3[8] = {0, 4, 2, 6, 1, 5, 3, 7};
+        if (INV) {
+#pragma unroll
+            for (int j = 1; j < 8; ++j) e[j] = cmulf(e[j], w[br3[j]]);
+            dit_regs<3, true>(e, tw, q, kp);
+        } else {
+            dif_regs<3, true>(e, tw, q, kp);
+#pragma unroll
+            for (int j = 1; j < 8; ++j) e[j] = cmulf(e[j], w[br3[j]]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) stf(base + j * q, pb + pad_off(j * q), e[j]);
+    }
+}
+// bottom group of R stages: forward, element-wise `mid(position, value)`, inverse — on 2^R contiguous elements
+template <int LG, int R, class Ld, class St, class Mid>
+__device__ __forceinline__ void fft_bottom_c(const float2 *tw, Ld ld, St stf, Mid mid) {
+    for (uint32_t task = threadIdx.x; task < ((1u << LG) >> R); task += blockDim.x) {
+        const uint32_t base = task << R, pb = padi(base);
+        float2 e[1 << R];
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j) e[j] = ld(base + j, pb + j);
+        dif_regs<R, true>(e, tw, 1, 0);
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j) e[j] = mid(base + j, e[j]);
+        dit_regs<R, true>(e, tw, 1, 0);
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j) stf(base + j, pb + j, e[j]);
+    }
+}
+// forward transform, spectrum operation, inverse transform of one 2^LG trace: ldg / stg read and write the caller's
+// (global) data, s is the padded shared work array.  Passes over shared memory: 2 * (groups - 1).
+template <int LG, class LdG, class StG, class Mid>
+__device__ __forceinline__ void fft_roundtrip_c(float2 *s, const float2 *tw, LdG ldg, StG stg, Mid mid) {
+    constexpr int RB = (LG % 3) ? (LG % 3) : 3, NG = (LG - RB) / 3; // bottom stages, number of radix-8 groups above them
+    auto lds = [&](uint32_t, uint32_t p) { return s[p]; };
+    auto sts = [&](uint32_t, uint32_t p, float2 v) { s[p] = v; };
+    auto ldG = [&](uint32_t i, uint32_t) { return ldg(i); };
+    auto stG = [&](uint32_t i, uint32_t, float2 v) { stg(i, v); };
+    if constexpr (NG == 0) {
+        fft_bottom_c<LG, RB>(tw, ldG, stG, mid);
+    } else {
+        fft_group_c<LG, LG, false>(tw, ldG, sts);
+        __syncthreads();
+        static_for<1, NG>([&](auto I) { fft_group_c<LG, LG - 3 * decltype(I)::value, false>(tw, lds, sts); __syncthreads(); });
+        fft_bottom_c<LG, RB>(tw, lds, sts, mid);
+        __syncthreads();
+        static_for<1, NG>([&](auto I) { fft_group_c<LG, RB + 3 * decltype(I)::value, true>(tw, lds, sts); __syncthreads(); });
+        fft_group_c<LG, LG, true>(tw, lds, stG);
+        __syncthreads(); // the next trace's first pass overwrites s
+    }
 }
 
 // chirp c[n] = exp(-i*pi*n^2/L) with n^2 reduced mod 2L in integers

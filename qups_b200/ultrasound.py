@@ -506,7 +506,7 @@ def focusTx(chd: "ChannelData", seq: "Sequence", tx: np.ndarray, interp="cubic",
 
 
 def refocus(chd: "ChannelData", seq: "Sequence", tx: np.ndarray, method="tikhonov", gamma=None):
-    """[chd, Hi] = refocus(us, chd, seq, 'method', method, 'gamma', gamma) — mirror of src/UltrasoundSystem.m:3505-3768.
+    r"""[chd, Hi] = refocus(us, chd, seq, 'method', method, 'gamma', gamma) — mirror of src/UltrasoundSystem.m:3505-3768.
 
     Host logic as in the reference (:3690-3727, evaluated in float64): encoding matrix H = a.' .* exp(-2j*pi*f.*tau.')
     per frequency, weights w = pagenorm(H,2)^-2, decoder Hi = (H'H + gamma w I) \ H.' | H.' w | w pinv(H), NaN -> 0.
