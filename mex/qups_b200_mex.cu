@@ -18,6 +18,9 @@
 //   r = qups_b200_mex('aperture', C, r0, b)                                    cohfac / dmas / pcf / slsc along one dimension
 //                                                                               (C.op, C.C, C.A, C.S, C.lags (uint32), C.gamma)
 //   y = qups_b200_mex('prep',   C, y0, x, t0)                                 zeropad -> hilbert -> downmix -> cast (C.B, C.A, C.hilbert, C.fmix, C.fs, C.N)
+//   y = qups_b200_mex('xcorr',  C, y0, x, x0, w)                               pwznxcorr: C.ref, C.zero, C.norm, C.pad, C.stride, C.lags (int32, host),
+//                                                                               x is T x N x F, w the window weights (single/double gpuArray), x0 may be []
+//   y = qups_b200_mex('refocus',C, y0, x, Hi)                                  REFoCUS decode: C.fs, C.t0 (double, host, 1 or V values); y0 T x N x E prototype
 // where C is a scalar struct holding what the reference puts in __constant__ memory with k.setConstantMemory
 // (kern/das_spec.m:294-298): C.I1,C.I2,C.I3,C.N,C.M,C.T,C.S,C.VS,C.DV,C.flag  (+ ws2: C.T,C.interp,C.omega ;
 // greens: C.n0,C.t0x,C.fs,C.fsr,C.c0,C.R0,C.E,C.interp).  The output is a new gpuArray of the size/type of the
@@ -181,6 +184,43 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         p.fs = fld(C, "fs", 1); p.fmix = fld(C, "fmix", 0);
         check(qups_chd_prep(&p, y, RO(x), p.n_t0 ? RO(t0) : NULL, NULL));
         mxGPUDestroyGPUArray(x); mxGPUDestroyGPUArray(t0);
+    } else if (!strcmp(op, "xcorr")) {
+        if (nrhs != 6) mexErrMsgIdAndTxt("QUPS:b200:usage", "'xcorr' takes 6 arguments");
+        const mxGPUArray *x = IN(3), *x0 = IN(4), *w = IN(5);
+        qups_xcorr_params p;
+        memset(&p, 0, sizeof(p));
+        p.struct_size = sizeof(p);
+        p.dtype = dtype_of(x);
+        p.is_complex = mxGPUGetComplexity(x) == mxCOMPLEX;
+        p.ref = (int32_t)fld(C, "ref", 0); p.zero = (int32_t)fld(C, "zero", 1); p.norm = (int32_t)fld(C, "norm", 1);
+        p.pad = (int32_t)fld(C, "pad", 1); p.stride = (uint32_t)fld(C, "stride", 1);
+        const mxArray *lg = mxGetField(C, 0, "lags");          /* host int32 vector */
+        if (!lg || mxGetClassID(lg) != mxINT32_CLASS) mexErrMsgIdAndTxt("QUPS:b200:usage", "C.lags must be an int32 vector");
+        p.L = (uint32_t)mxGetNumberOfElements(lg); p.W = (uint32_t)mxGPUGetNumberOfElements(w);
+        const mwSize *xs = mxGPUGetDimensions(x);
+        const mwSize nd = mxGPUGetNumberOfDimensions(x);
+        p.T = xs[0]; p.N = nd > 1 ? xs[1] : 1; p.F = mxGPUGetNumberOfElements(x) / (p.T * p.N ? p.T * p.N : 1);
+        if (mxGPUGetNumberOfElements(x0)) {
+            const mwSize *zs = mxGPUGetDimensions(x0);
+            p.x0N = mxGPUGetNumberOfDimensions(x0) > 1 ? zs[1] : 1;
+            p.x0F = mxGPUGetNumberOfElements(x0) / (zs[0] * p.x0N ? zs[0] * p.x0N : 1);
+        }
+        check(qups_pwznxcorr(&p, y, RO(x), mxGPUGetNumberOfElements(x0) ? RO(x0) : NULL, RO(w), (const int32_t *)mxGetData(lg), NULL));
+        mxGPUDestroyGPUArray(x); mxGPUDestroyGPUArray(x0); mxGPUDestroyGPUArray(w);
+    } else if (!strcmp(op, "refocus")) {
+        if (nrhs != 5) mexErrMsgIdAndTxt("QUPS:b200:usage", "'refocus' takes 5 arguments");
+        const mxGPUArray *x = IN(3), *Hi = IN(4);             /* x: T x N x V, Hi: E x V x T, both complex single */
+        qups_refocus_params p;
+        memset(&p, 0, sizeof(p));
+        p.struct_size = sizeof(p);
+        p.dtype = dtype_of(x);
+        const mwSize *xs = mxGPUGetDimensions(x), *hs = mxGPUGetDimensions(Hi);
+        p.T = xs[0]; p.N = xs[1]; p.V = mxGPUGetNumberOfDimensions(x) > 2 ? xs[2] : 1; p.E = hs[0];
+        const mxArray *t0 = mxGetField(C, 0, "t0");            /* host double vector, 1 or V start times */
+        if (!t0 || !mxIsDouble(t0)) mexErrMsgIdAndTxt("QUPS:b200:usage", "C.t0 must be a double vector");
+        p.n_t0 = (uint32_t)mxGetNumberOfElements(t0); p.fs = fld(C, "fs", 1);
+        check(qups_refocus(&p, y, RO(x), RO(Hi), mxGetPr(t0), NULL, NULL));
+        mxGPUDestroyGPUArray(x); mxGPUDestroyGPUArray(Hi);
     } else {
         mexErrMsgIdAndTxt("QUPS:b200:usage", "unknown op '%s'", op);
     }

@@ -591,8 +591,12 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
                 for (uint64_t c = 0; c <= nch; ++c) bounds[c] = p->M * c / nch;
                 nb = nch;
             } else {
-                double sz = (double)p->M / 8.0; // launches below ~32 transmits lose >8 % to per-launch setup (measured)
-                if (sz < 32) sz = 32;
+                // launches below ~32 transmits lose >8 % to per-launch setup (measured), so large calls start at max(32, M/8).
+                // A transmit-partitioned rank of an 8-GPU job holds only M/8 = 32 transmits: there the un-overlapped copy is
+                // the larger loss (8 ranks share the host's memory bandwidth), so short calls start at max(8, M/4)
+                double sz = (p->M >= 64) ? (double)p->M / 8.0 : (double)p->M / 4.0;
+                const double szmin = (p->M >= 64) ? 32.0 : 8.0;
+                if (sz < szmin) sz = szmin;
                 bounds[0] = 0;
                 while (pos < p->M && nb < HostWs::NEV - 3) {
                     uint64_t step = (uint64_t)sz;
