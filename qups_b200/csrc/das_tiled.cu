@@ -131,6 +131,9 @@ struct TiledArgs {
     const float *tn, *tm;   // tn[n * I + i] (the aperture whose traces are contiguous in x), tm[m * I + i]
     const float *wscal;     // scalar weight applied to the sum (real, or complex when wcplx)
     int wcplx;
+    // receive-split launches: per-tile path-length bounds computed ONCE by das_bounds_kernel instead of once per (tile, split)
+    // CTA — [tile][4 M + 2 N] ordered ints: dv < 0 cluster min / max [M], dv >= 0 cluster min / max [M], dr min / max [N]
+    int *bounds;
 };
 
 // ---- small PTX wrappers -----------------------------------------------------
@@ -480,8 +483,14 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
     }
+    const bool have_bounds = (FUSED == 0 && KEEP == 0 && LUT == 0) && a.bounds != nullptr;
+    if (have_bounds) { // the six tables are contiguous in shared memory and in the pre-pass output
+        const int *src = a.bounds + (uint64_t)tile * (4 * a.M + 2 * a.N);
+        for (uint32_t i = tid; i < 4 * a.M + 2 * a.N; i += kThreads) s_dvnmin[i] = __ldg(src + i);
+    } else {
     for (uint32_t i = tid; i < a.M; i += kThreads) { s_dvnmin[i] = INT_MAX; s_dvnmax[i] = INT_MIN; s_dvpmin[i] = INT_MAX; s_dvpmax[i] = INT_MIN; }
     for (uint32_t i = tid; i < a.N; i += kThreads) { s_drmin[i] = INT_MAX; s_drmax[i] = INT_MIN; }
+    }
     if constexpr (FUSED != 0) {
         for (uint32_t i = tid; i < a.M; i += kThreads) s_txany[i] = (a.fa.tx_kind == AP_TX_NONE);
         for (uint32_t i = tid; i < a.N; i += kThreads) s_rxany[i] = (FUSED != 2);
@@ -534,7 +543,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
         // ---- phase 0: per-tile min/max of dv(.,m) and dr(.,n) -------------------------
         // dv is tracked in two clusters, dv < 0 and dv >= 0: a focused transmit flips the sign of dv at the focal
         // plane (kern/das_spec.m:429), so a tile crossing it touches two disjoint windows of each trace
-        for (uint32_t m = 0; m < a.M; ++m) {
+        for (uint32_t m = 0; m < (have_bounds ? 0u : a.M); ++m) {
             float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
             float nx = 0.f, ny = 0.f, nz = 0.f;
             if constexpr (!LUT) {
@@ -564,7 +573,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                 }
             }
         }
-        for (uint32_t n = kInnerTx ? 0u : nt0 * kNT; n < (kInnerTx ? a.N : min(nt1 * kNT, a.N)); ++n) {
+        for (uint32_t n = kInnerTx ? 0u : nt0 * kNT; n < (have_bounds ? 0u : (kInnerTx ? a.N : min(nt1 * kNT, a.N))); ++n) {
             float rx = 0.f, ry = 0.f, rz = 0.f;
             if constexpr (!LUT) { rx = __ldg(a.Pr + 3 * n); ry = __ldg(a.Pr + 3 * n + 1); rz = __ldg(a.Pr + 3 * n + 2); }
             int lo = INT_MAX, hi = INT_MIN;
@@ -999,6 +1008,61 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
     }
 }
 
+// per-tile path-length bounds for receive-split launches (plain geometric delays, no kept aperture): phase 0 of the main
+// kernel, run once per TILE.  A (tile, split) CTA then loads its 4 M + 2 N bounds instead of recomputing dv(.,m) for all M
+// transmits (ncu, 8-GPU slab: ~30 000 instructions per warp and CTA — 1.1 % of the launch per unit of nsplit)
+__global__ void __launch_bounds__(kCW * 32) das_bounds_kernel(const TiledArgs a) {
+    extern __shared__ int s_b[];
+    int *s_dvnmin = s_b, *s_dvnmax = s_dvnmin + a.M, *s_dvpmin = s_dvnmax + a.M, *s_dvpmax = s_dvpmin + a.M;
+    int *s_drmin = s_dvpmax + a.M, *s_drmax = s_drmin + a.N;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t ta = tile % a.tilesA, tb = (tile / a.tilesA) % a.tilesB, tc = tile / (a.tilesA * a.tilesB);
+    const uint32_t lpa = a.lpa, lpb = 32u / lpa, wA = a.tA / lpa;
+    const uint32_t ia = ta * a.tA + (warp % wA) * lpa + (lane % lpa);
+    for (uint32_t i = tid; i < a.M; i += kCW * 32) { s_dvnmin[i] = INT_MAX; s_dvnmax[i] = INT_MIN; s_dvpmin[i] = INT_MAX; s_dvpmax[i] = INT_MIN; }
+    for (uint32_t i = tid; i < a.N; i += kCW * 32) { s_drmin[i] = INT_MAX; s_drmax[i] = INT_MIN; }
+    __syncthreads();
+    float px[kR], py[kR], pz[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) { // the same pixels (incl. the shadowing of out-of-image lanes) as the main kernel's consumers
+        const uint32_t ib = tb * a.tB + ((warp / wA) * lpb + (lane / lpa)) * kR + r;
+        const uint32_t ca = ia < a.IA ? ia : a.IA - 1, cb = ib < a.IB ? ib : a.IB - 1;
+        const uint64_t pix = (uint64_t)ca * a.sA + (uint64_t)cb * a.sB + (uint64_t)tc * a.sC;
+        px[r] = __ldg(a.Pi + 3 * pix); py[r] = __ldg(a.Pi + 3 * pix + 1); pz[r] = __ldg(a.Pi + 3 * pix + 2);
+    }
+    const bool VS = a.VS, DV = a.DV;
+    for (uint32_t m = 0; m < a.M; ++m) {
+        const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
+        const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
+        int nlo = INT_MAX, nhi = INT_MIN, plo = INT_MAX, phi = INT_MIN;
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+            const float d = tx_dist(px[r], py[r], pz[r], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+            const int o = f2o(d);
+            if (d < 0.f) { nlo = min(nlo, o); nhi = max(nhi, o); }
+            else         { plo = min(plo, o); phi = max(phi, o); }
+        }
+        nlo = __reduce_min_sync(0xffffffffu, nlo); nhi = __reduce_max_sync(0xffffffffu, nhi);
+        plo = __reduce_min_sync(0xffffffffu, plo); phi = __reduce_max_sync(0xffffffffu, phi);
+        if (lane == 0) {
+            if (nlo <= nhi) { atomicMin(&s_dvnmin[m], nlo); atomicMax(&s_dvnmax[m], nhi); }
+            if (plo <= phi) { atomicMin(&s_dvpmin[m], plo); atomicMax(&s_dvpmax[m], phi); }
+        }
+    }
+    for (uint32_t n = 0; n < a.N; ++n) {
+        const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
+        int lo = INT_MAX, hi = INT_MIN;
+#pragma unroll
+        for (int r = 0; r < kR; ++r) { const int o = f2o(rx_dist(px[r], py[r], pz[r], rx, ry, rz)); lo = min(lo, o); hi = max(hi, o); }
+        lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { atomicMin(&s_drmin[n], lo); atomicMax(&s_drmax[n], hi); }
+    }
+    __syncthreads();
+    int *dst = a.bounds + (uint64_t)tile * (4 * a.M + 2 * a.N);
+    for (uint32_t i = tid; i < 4 * a.M + 2 * a.N; i += kCW * 32) dst[i] = s_b[i];
+}
+
 // sums the receive-split partial images in split order (deterministic) into y
 __global__ void __launch_bounds__(256) das_reduce_kernel(float2 *y, const float2 *part, uint64_t I, uint32_t nsplit, int accumulate) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < I; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -1201,6 +1265,22 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
             if (cost < best * 0.97) { best = cost; nsplit = ns; }
         }
     }
+    // Plain geometric delays: the per-tile bounds come from das_bounds_kernel (below), so a split costs a CTA almost nothing
+    // and finer is better — the tail of a launch is about half a CTA duration.  Measured on one rank's slab of an 8-GPU job
+    // (256 tiles): nsplit 4 / 8 / 16 = 9.66 / 9.77 / 9.32 ms (10.15 ms with the makespan model and in-kernel bounds); uneven
+    // receive ranges (nsplit 3, 5, 6 of 16 tiles) made stragglers.  So: the smallest DIVISOR of the receive-tile count that
+    // gives at least 12 waves of CTAs, else one receive tile per CTA.
+    // (with a handful of transmits phase 0 is cheap anyway and the extra launch is not: config C1, one plane wave, 39 -> 69 us)
+    const bool can_bounds = !lut && fused == 0 && keep == 0 && t.M >= 16 && !getenv("QUPS_B200_NOBOUNDS");
+    if (can_bounds) {
+        const double slots = (double)(wmax > 256 ? 1 : QUPS_MINBLOCKS) * sms;
+        nsplit = 1;
+        for (uint32_t d = 1; d <= t.numNT; ++d) {
+            if (t.numNT % d) continue;
+            nsplit = d;
+            if ((double)tiles * d >= 12.0 * slots) break;
+        }
+    }
     if (keep) nsplit = 1;                             // kept apertures: each CTA is the only writer of its pixels
     if (nsplit < 1) nsplit = 1;
     if (const char *e2 = getenv("QUPS_B200_NSPLIT")) { int v = atoi(e2); if (v >= 1 && (uint32_t)v <= t.numNT) nsplit = (uint32_t)v; }
@@ -1218,6 +1298,20 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     if (keep && !t.accumulate) { // every stage adds into y(:, n | m)
         e = cudaMemsetAsync(t.y, 0, sizeof(float2) * a.I * (keep == 1 ? a.M : a.N), st);
         if (e != cudaSuccess) return (int)e;
+    }
+    t.bounds = nullptr;
+    const bool use_bounds = nsplit > 1 && can_bounds;
+    if (use_bounds) {
+        const size_t per_tile = sizeof(int) * (4 * (size_t)t.M + 2 * (size_t)t.N);
+        e = ws_alloc((void **)&t.bounds, per_tile * tiles, st);
+        if (e != cudaSuccess) { if (t.part) ws_free(t.part, st); return (int)e; }
+        if (per_tile > 48 * 1024) e = cudaFuncSetAttribute(das_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_tile);
+        if (e == cudaSuccess) {
+            das_bounds_kernel<<<(unsigned)tiles, kCW * 32, per_tile, st>>>(t);
+            count_launch();
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) { ws_free(t.bounds, st); if (t.part) ws_free(t.part, st); return (int)e; }
     }
     kern<<<(unsigned)(tiles * nsplit), threads_of(ip), smem, st>>>(t);
     count_launch();
@@ -1244,6 +1338,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
         }
         ws_free(t.part, st);
     }
+    if (t.bounds) ws_free(t.bounds, st);
     return (int)e;
 }
 
