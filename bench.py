@@ -445,6 +445,97 @@ def also_legs(dev, peak, log):
     return out
 
 
+def next_row_legs(dev, peak, log):
+    """SURVEY.md §8f rows at the headline cube size, each through its C-ABI entry point on device-resident data (N = 1, after the
+    headline's timed region): ChannelData pre-processing, aperture-domain reductions of the keep_rx cube, pwznxcorr, refocus.
+    These ARE bound by HBM (one read + one write of the cube): frac = algorithmic bytes / time / measured HBM peak."""
+    import torch
+    from qups_b200 import _lib
+    L = _lib.lib()
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    out = {}
+    T, N, M = 2048, 256, 256
+    K = N * M
+
+    def rec(name, fn, gbytes, extra=None, warm=1, iters=3):
+        try:
+            ms, mn = time_device(fn, warm, iters)
+            out[name] = {"ms": mn, "algorithmic_GB": gbytes, "GBps": gbytes / mn * 1e3, "frac_of_hbm_peak": gbytes / mn * 1e3 / peak}
+            if extra: out[name].update(extra)
+        except Exception as e:
+            out[name] = {"error": repr(e)}
+        log(f"next-row {name}: {out[name]}")
+
+    # ---- qups_chd_prep (src/ChannelData.m zeropad / hilbert / downmix / cast) ----
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    rf = torch.randn((K, T), generator=g, device=dev, dtype=torch.float32)
+    yc = torch.empty((K, T), dtype=torch.complex64, device=dev)
+    def prep(hilbert, fmix, inp, in_dtype):
+        p = _lib.PrepParams()
+        p.struct_size = C.sizeof(_lib.PrepParams)
+        p.in_dtype, p.out_dtype, p.hilbert = in_dtype, _lib.F32, int(hilbert)
+        p.T, p.K, p.B, p.A, p.traces_per_t0, p.n_t0, p.fs, p.fmix = T, K, 0, 0, N, 0, 30e6, fmix
+        return lambda: _lib.check(L.qups_chd_prep(C.byref(p), vp(yc), vp(inp), None, st))
+    rec("prep_hilbert_f32", prep(True, 0.0, rf, _lib.IN_REAL_F32), (4 + 8) * K * T / 1e9)
+    rec("prep_hilbert_downmix_f32", prep(True, 7.5e6, rf, _lib.IN_REAL_F32), (4 + 8) * K * T / 1e9)
+    rec("prep_cast_f32_to_complex", prep(False, 0.0, rf, _lib.IN_REAL_F32), (4 + 8) * K * T / 1e9)
+    del rf
+    # ---- qups_pwznxcorr (kern/pwznxcorr.m) on the complex cube: neighbouring channels, 9 lags, window 16 ----
+    try:
+        lags = (C.c_int32 * 9)(*range(-4, 5))
+        w = torch.ones(16, dtype=torch.float32, device=dev)
+        F = 32
+        xin = yc[: N * F]                                        # T x N x F (time fastest)
+        yx = torch.empty((9, F, N - 1, T), dtype=torch.complex64, device=dev)
+        px = _lib.XcorrParams()
+        px.struct_size = C.sizeof(_lib.XcorrParams)
+        px.dtype, px.is_complex, px.ref, px.zero, px.norm, px.pad, px.stride = _lib.F32, 1, _lib.XC_NEIGHBOR, 1, 1, 1, 1
+        px.L, px.W, px.T, px.N, px.F, px.x0N, px.x0F = 9, 16, T, N, F, 1, 1
+        rec("pwznxcorr_9lags_w16", lambda: _lib.check(L.qups_pwznxcorr(C.byref(px), vp(yx), vp(xin), None, vp(w), lags, st)),
+            (xin.numel() + yx.numel()) * 8 / 1e9, {"shape": f"T={T} N={N} F={F} lags=9 W=16"})
+        del yx
+    except Exception as e:
+        out["pwznxcorr_9lags_w16"] = {"error": repr(e)}
+    # ---- qups_refocus (REFoCUS decode): T x 128 x 128 data, 128 x 128 x T decoder ----
+    try:
+        Nr = Er = Vr = 128
+        xr = yc[: Nr * Vr]
+        Hi = torch.randn((T, Vr, Er, 2), generator=g, device=dev, dtype=torch.float32)
+        yr = torch.empty((Er, Nr, T), dtype=torch.complex64, device=dev)
+        pr = _lib.RefocusParams()
+        pr.struct_size = C.sizeof(_lib.RefocusParams)
+        pr.dtype, pr.T, pr.N, pr.V, pr.E, pr.n_t0, pr.fs = _lib.F32, T, Nr, Vr, Er, 1, 30e6
+        t0c = (C.c_double * 1)(0.0)
+        flop = 8.0 * T * Nr * Vr * Er
+        rec("refocus_128x128x128", lambda: _lib.check(L.qups_refocus(C.byref(pr), vp(yr), vp(xr), vp(Hi), t0c, None, st)),
+            (xr.numel() + yr.numel() + Hi.numel() // 2) * 8 / 1e9, {"decode_GFLOP": flop / 1e9})
+        if "ms" in out["refocus_128x128x128"]:
+            out["refocus_128x128x128"]["TFLOPs_fp32"] = flop / out["refocus_128x128x128"]["ms"] / 1e9
+        del Hi, yr
+    except Exception as e:
+        out["refocus_128x128x128"] = {"error": repr(e)}
+    del yc
+    torch.cuda.empty_cache()
+    # ---- qups_aperture on a keep_rx-sized cube: 1024^2 pixels x 256 receives (2.15 GB) ----
+    try:
+        Cn, A = 1024 * 1024, 256
+        b = torch.randn((A, Cn, 2), generator=g, device=dev, dtype=torch.float32)
+        o1 = torch.empty(Cn, dtype=torch.complex64, device=dev)
+        for name, op, lagv in (("aperture_cohfac", _lib.APD_COHFAC, []), ("aperture_dmas_L16", _lib.APD_DMAS, list(range(1, 17))),
+                               ("aperture_slsc_average_L16", _lib.APD_SLSC_AVERAGE, list(range(1, 17)))):
+            pa = _lib.ApertureParams()
+            pa.struct_size = C.sizeof(_lib.ApertureParams)
+            pa.dtype, pa.op, pa.nlags, pa.C, pa.A, pa.S, pa.gamma = _lib.F32, op, len(lagv), Cn, A, 1, 1.0
+            lg = (C.c_uint32 * max(1, len(lagv)))(*lagv)
+            rec(name, (lambda pa=pa, lg=lg: _lib.check(L.qups_aperture(C.byref(pa), vp(o1), None, vp(b), lg, st))), Cn * A * 8 / 1e9)
+        del b, o1
+    except Exception as e:
+        out["aperture"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    return out
+
+
 def ref_kernel_leg(P, o, dev, x_dev, log):
     """The reference's own GPU kernel on this box (test infrastructure, oracle/ref_ptx.py): DASf from the unmodified
     src/bf.cu, compiled with the reference's flags, launched with the reference's geometry (kern/das_spec.m:301-306)."""
@@ -779,6 +870,7 @@ def main():
         del run
         torch.cuda.empty_cache()
         line["also"] = also_legs(dev, peak, log)
+        line["next_rows"] = next_row_legs(dev, peak, log)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
