@@ -122,7 +122,7 @@ def test_mex_gateway_compiles_against_a_stub_mex_h(tmp_path):
     (tmp_path / "mex.h").write_text("""
 #include <stddef.h>
 typedef struct mxArray_tag mxArray; typedef size_t mwSize;
-typedef enum { mxDOUBLE_CLASS, mxSINGLE_CLASS, mxUINT16_CLASS, mxINT16_CLASS, mxUINT64_CLASS } mxClassID;
+typedef enum { mxDOUBLE_CLASS, mxSINGLE_CLASS, mxUINT16_CLASS, mxINT16_CLASS, mxINT32_CLASS, mxUINT64_CLASS } mxClassID;
 typedef enum { mxREAL, mxCOMPLEX } mxComplexity;
 #ifdef __cplusplus
 extern "C" {
@@ -131,6 +131,7 @@ const mxArray *mxGetField(const mxArray *, size_t, const char *); double mxGetSc
 void mexErrMsgIdAndTxt(const char *, const char *, ...); bool mxIsChar(const mxArray *); bool mxIsStruct(const mxArray *);
 int mxGetString(const mxArray *, char *, size_t); double *mxGetPr(const mxArray *); bool mxIsUint64(const mxArray *);
 void *mxGetData(const mxArray *); size_t mxGetNumberOfElements(const mxArray *);
+mxClassID mxGetClassID(const mxArray *); bool mxIsDouble(const mxArray *);
 #ifdef __cplusplus
 }
 #endif
