@@ -1269,16 +1269,18 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     // and finer is better — the tail of a launch is about half a CTA duration.  Measured on one rank's slab of an 8-GPU job
     // (256 tiles): nsplit 4 / 8 / 16 = 9.66 / 9.77 / 9.32 ms (10.15 ms with the makespan model and in-kernel bounds); uneven
     // receive ranges (nsplit 3, 5, 6 of 16 tiles) made stragglers.  So: the smallest DIVISOR of the receive-tile count that
-    // gives at least 12 waves of CTAs, else one receive tile per CTA.
+    // gives at least `waves_target` waves of CTAs, else one receive tile per CTA.
     // (with a handful of transmits phase 0 is cheap anyway and the extra launch is not: config C1, one plane wave, 39 -> 69 us)
     const bool can_bounds = !lut && fused == 0 && keep == 0 && t.M >= 16 && !getenv("QUPS_B200_NOBOUNDS");
     if (can_bounds) {
         const double slots = (double)(wmax > 256 ? 1 : QUPS_MINBLOCKS) * sms;
+        double waves_target = 48.0; // C2 on one GPU, same box: 12 / 24 / 48 waves = 65.12 / 64.82 / 64.40 ms (end to end 71.98 / 71.98 / 71.25)
+        if (const char *ew = getenv("QUPS_B200_WAVES")) { const double v = atof(ew); if (v >= 1.0) waves_target = v; }
         nsplit = 1;
         for (uint32_t d = 1; d <= t.numNT; ++d) {
             if (t.numNT % d) continue;
             nsplit = d;
-            if ((double)tiles * d >= 12.0 * slots) break;
+            if ((double)tiles * d >= waves_target * slots) break;
         }
     }
     if (keep) nsplit = 1;                             // kept apertures: each CTA is the only writer of its pixels
