@@ -284,3 +284,43 @@ def test_reference_wsinterpd2_and_greens_fp64_pin_oracle_algorithm(oracle_c):
             assert rel_linf(got, ref) < 1e-9, rel_linf(got, ref)
         else:
             assert np.mean(np.abs(got - ref) > 1e-9 * np.abs(ref).max()) < 1e-3
+
+
+def test_fmod_convention_cpu_branch_vs_reference_gpu_kernel():
+    """Pins the one documented semantic difference between this library and the reference's GPU kernel for `fmod != 0`
+    (include/qups_b200.h): the library follows the CPU branch — data re-modulated at ABSOLUTE time before
+    sampling (kern/das_spec.m:413-417) — the reference GPU kernel multiplies by exp(2i*pi*fmod*(tau - t0)) after sampling
+    (src/bf.cu:111-115).  For band-limited data the two differ per transmit by exp(2i*pi*fmod*t0(m)): with per-transmit
+    start times that is NOT a global phase.  Check: ours(sum over m) == sum_m ref_m * exp(2i*pi*fmod*t0(m)) to interpolation
+    accuracy, and the plain sum of the reference's transmits is visibly different."""
+    ref_ptx = _need("bf", "ieee")
+    import qups_b200
+    P = small_problem("FC", nz=48, nx=40, N=16, M=6, T=400, zlim=(3e-3, 12e-3))
+    fs, fmod = P["fs"], P["fs"] / 20   # 20 samples per carrier period: the reference's pass-band cubic stays accurate to ~1 %
+    T, N, M = P["x"].shape
+    t0 = np.linspace(0.0, 0.9e-6, M)
+    # narrow-band data around -fmod: after modulation by +fmod it is base-band, so interpolating the modulated data (CPU
+    # branch) and modulating the interpolated data (GPU kernel) agree to the interpolator's accuracy
+    t = np.arange(T)[:, None, None]
+    ph = np.random.default_rng(1).uniform(0, 2 * np.pi, (1, N, M))
+    env = np.hanning(T)[:, None, None]
+    x = (env * np.exp(1j * (-2 * np.pi * (fmod / fs) * t + 2 * np.pi * 0.01 * t + ph))).astype(np.complex64)
+    x[:4] = 0; x[T - 4:] = 0
+    x = np.asfortranarray(x)
+    ours = qups_b200.das_spec("DAS", P["Pi"].astype(f32), P["Pr"].astype(f32), P["Pv"].astype(f32), P["Nv"].astype(f32), x,
+                              t0.astype(f32), fs, P["c"], *P["opts"], "interp", "cubic", "modulation", fmod)
+    kw = oracle_kwargs(P["opts"])
+    want = np.zeros(P["Pi"].shape[1:], np.complex128)
+    plain = np.zeros(P["Pi"].shape[1:], np.complex128)
+    for m in range(M):
+        k = ref_ptx.RefDASf("ieee")
+        k.prepare(P["Pi"], P["Pr"], P["Pv"][:, m:m + 1], P["Nv"][:, m:m + 1], np.asfortranarray(x[:, :, m:m + 1]), t0[m:m + 1], fs, P["c"],
+                  interp=2, VS=kw["VS"], DV=kw["DV"], fmod=fmod)
+        k.launch()
+        rm = k.result(P["Pi"].shape[1:]).reshape(want.shape)
+        plain += rm
+        want += rm * np.exp(2j * np.pi * fmod * float(np.float32(t0[m])))
+    ours = np.asarray(ours).reshape(want.shape)
+    assert np.abs(want).max() > 1
+    assert rel_linf(ours, want) < 3e-2, rel_linf(ours, want)      # cubic on base-band vs pass-band data + the reference's Horner cubic
+    assert rel_linf(ours, plain) > 5 * rel_linf(ours, want)        # without the per-transmit factor the images differ

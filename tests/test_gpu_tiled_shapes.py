@@ -126,3 +126,39 @@ def test_kept_aperture_short_slots_and_sum_consistency(oracle_c, fun):
         assert rel_linf(got, ref) < 1e-5, env
     das = _tiled(P, "cubic")
     assert rel_linf(got.sum(axis=(3, 4)), das[..., 0, 0] if das.ndim == 5 else das) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["FC", "PW", "DV"])
+@pytest.mark.parametrize("interp", ["nearest", "cubic"])
+def test_receive_split_with_bounds_prepass(oracle_c, kind, interp):
+    """M >= 16 transmits and several receive tiles on a small image: the launcher splits the receive axis down to one tile per
+    CTA and takes the per-tile path-length bounds from das_bounds_kernel (csrc/das_tiled.cu) instead of the in-kernel phase 0.
+    Same result as with the pre-pass disabled (the bounds only select windows; the receive split — hence the summation order —
+    differs between the two launch policies, so bit-equality holds for integer data only) and as the oracle; also with a real
+    apodization array, per-transmit t0 and two frames."""
+    import qups_b200
+    from qups_b200 import _lib
+    P = small_problem(kind, nz=70, nx=45, N=40, M=19, T=520, zlim=(2e-3, 14e-3), int_data=(interp == "nearest"), F=2,
+                      t0=np.linspace(0.0, 0.4e-6, 19))
+    got = _tiled(P, interp)
+    n0 = _lib.launch_count()
+    ref = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp=interp,
+                            **oracle_kwargs(P["opts"]))
+    nob = _tiled(P, interp, QUPS_B200_NOBOUNDS=1)
+    assert np.array_equal(got, nob) if interp == "nearest" else rel_linf(got, nob) <= 2e-6
+    got, ref = np.squeeze(got), np.squeeze(ref)
+    assert got.shape == ref.shape
+    if interp == "nearest":
+        assert np.array_equal(got, ref)
+    else:
+        assert rel_linf(got, ref) <= 1e-5
+    # a real apodization array over (pixels x receives) rides along (NAP = 1)
+    rng = np.random.default_rng(5)
+    A = rng.uniform(0.2, 1.0, P["Pi"].shape[1:] + (40, 1)).astype(f32)
+    ga = qups_b200.das_spec("DAS", P["Pi"].astype(f32), P["Pr"].astype(f32), P["Pv"].astype(f32), P["Nv"].astype(f32), P["x"], P["t0"],
+                            P["fs"], P["c"], *P["opts"], "interp", interp, "apod", A, _path=_lib.PATH_TILED)
+    assert qups_b200.last_das_kernel() == "das_tiled"
+    ra = oracle_c.das_spec("DAS", P["Pi"], P["Pr"], P["Pv"], P["Nv"], P["x"], P["t0"], P["fs"], P["c"], interp=interp, apod=[A],
+                           **oracle_kwargs(P["opts"]))
+    assert rel_linf(np.squeeze(ga), np.squeeze(ra)) <= 1e-5
+    assert n0 > 0
