@@ -583,27 +583,31 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
         if (nch > 1) {
             if ((e = cudaEventRecord(g_ws.ev[HostWs::NEV - 1], sc)) != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord");
             if (rc == 0 && (e = cudaStreamWaitEvent(sx, g_ws.ev[HostWs::NEV - 1], 0)) != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent");
-            // chunk sizes grow geometrically (x1.3): the first copy that cannot overlap anything is short, and each
-            // later copy still finishes before the previous chunk's beamforming does (copy is faster than compute)
             uint64_t bounds[HostWs::NEV];
             uint64_t nb = 0, pos = 0;
             if (p->host_chunks > 1) {
                 for (uint64_t c = 0; c <= nch; ++c) bounds[c] = p->M * c / nch;
                 nb = nch;
             } else {
-                // launches below ~32 transmits lose >8 % to per-launch setup (measured), so large calls start at max(32, M/8).
-                // A transmit-partitioned rank of an 8-GPU job holds only M/8 = 32 transmits: there the un-overlapped copy is
-                // the larger loss (8 ranks share the host's memory bandwidth), so short calls start at max(8, M/4)
-                double sz = (p->M >= 64) ? (double)p->M / 8.0 : (double)p->M / 4.0;
-                const double szmin = (p->M >= 64) ? 32.0 : 8.0;
-                if (sz < szmin) sz = szmin;
+                // the first chunk is what cannot overlap anything (with the 12.6 MB of pixel positions in front of it), so it is
+                // short: 8 transmits; each later chunk is 2-3x longer — the copy runs ~3x faster than the beamforming on an idle
+                // host (55 GB/s vs 4 transmits/ms at C2), so chunk c + 1 lands before chunk c is done, and still does when 8
+                // ranks share the host's memory bandwidth.  (Round 1 started at 32 transmits because short launches lost
+                // > 8 % to the per-CTA bounds pass; with das_bounds_kernel and the finer receive split they no longer do.)
+                double sz = 8.0;
+                const char *eg = getenv("QUPS_B200_CHUNK_GROWTH");
+                // measured, C2 through this call on one GPU (device-resident kernel 64.4 ms): chunks 32 x1.3 -> 71.3 ms, 8 x2 -> 69.3,
+                // 8 x3 -> 68.5 (fewer launches; every launch recomputes dr per receive tile and has its own tail).  Short
+                // transmit shards (one rank of a multi-GPU job, where the copy is the contended resource) keep x2
+                const double growth = eg && atof(eg) >= 1.0 ? atof(eg) : (p->M >= 128 ? 3.0 : 2.0);
+                if (const char *e0 = getenv("QUPS_B200_CHUNK0")) { const double v = atof(e0); if (v >= 1.0) sz = v; }
                 bounds[0] = 0;
                 while (pos < p->M && nb < HostWs::NEV - 3) {
                     uint64_t step = (uint64_t)sz;
                     if (p->M - pos < step + step / 2) step = p->M - pos;
                     pos += step;
                     bounds[++nb] = pos;
-                    sz *= 1.3;
+                    sz *= growth;
                 }
                 bounds[nb] = p->M;
             }
