@@ -26,6 +26,8 @@ template <typename R> struct c2 { using type = float2; };
 template <> struct c2<double> { using type = double2; };
 
 template <typename R> __device__ __forceinline__ R rsqrt_(R x) { return R(1) / sqrt(x); }
+__device__ __forceinline__ float fast_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
 template <typename R> __device__ __forceinline__ R atan2_(R y, R x) { return atan2(y, x); }
 __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
 
@@ -142,9 +144,14 @@ __global__ void __launch_bounds__(256) aperture_tile_kernel(void *out, void *out
                                                             uint64_t C, uint32_t A, uint64_t S, uint32_t nlags, R gamma) {
     using V = typename c2<R>::type;
     extern __shared__ __align__(16) unsigned char ap_smem[];
-    V *tile = reinterpret_cast<V *>(ap_smem);                  // [A][32]
-    R *pre = reinterpret_cast<R *>(tile + (size_t)A * 32);     // prefix powers [A + 1][32] (slsc ensemble), phases [A][32] (pcf)
+    constexpr uint32_t kPadRows = 12;                          // zero rows after the aperture: the register-blocked loads of the
+                                                               // pair loop run past the last valid pair without any range test
+    V *tile = reinterpret_cast<V *>(ap_smem);                  // [A + kPadRows][32]
+    R *pre = reinterpret_cast<R *>(tile + (size_t)(A + kPadRows) * 32); // prefix powers [A + 1][32] (slsc ensemble), phases [A][32] (pcf)
     __shared__ R red[8][3][32];
+    __shared__ R segtot[8][32];                                // per-warp segment totals of the prefix powers (slsc ensemble)
+    __shared__ uint16_t s_act[4096];                           // lag blocks with at least one requested lag (A < 16384)
+    __shared__ uint32_t s_nact;
     const V *b = reinterpret_cast<const V *>(bin);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t total = C * S, e = (uint64_t)blockIdx.x * 32 + lane;
@@ -152,15 +159,31 @@ __global__ void __launch_bounds__(256) aperture_tile_kernel(void *out, void *out
     const uint64_t c = valid ? e % C : 0, sidx = valid ? e / C : 0;
     const V *col = b + c + sidx * C * A;
     const R PI = R(3.14159265358979323846);
-    for (uint32_t n = warp; n < A; n += 8) {
-        V v; v.x = R(0); v.y = R(0);
-        if (valid) v = col[(uint64_t)n * C];
-        if (OP == QUPS_APD_SLSC_AVERAGE) { // x ./ vecnorm(x, 2, kdim), nan2zero
-            const R m = sqrt(v.x * v.x + v.y * v.y);
-            v.x = m > 0 ? v.x / m : 0; v.y = m > 0 ? v.y / m : 0;
+    if (threadIdx.x == 0) s_nact = 0;
+    for (uint32_t r = threadIdx.x; r < kPadRows * 32; r += 256) { V z; z.x = R(0); z.y = R(0); tile[(size_t)A * 32 + r] = z; }
+    const V *src = col + (uint64_t)warp * C;                   // this warp's rows: n = warp, warp + 8, ...
+    const uint64_t step = 8 * C;
+    // 8 rows of this warp in flight per batch: the loads are issued before the first store (one exposed DRAM latency per
+    // batch instead of one per row)
+    for (uint32_t n = warp; n < A; n += 64, src += 8 * step) {
+        V vb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            vb[u].x = R(0); vb[u].y = R(0);
+            if (valid && n + 8 * u < A) vb[u] = src[(uint64_t)u * step];
         }
-        tile[n * 32 + lane] = v;
-        if (OP == QUPS_APD_PCF) pre[n * 32 + lane] = atan2_(v.y, v.x);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (n + 8 * u >= A) break;
+            V v = vb[u];
+            if (OP == QUPS_APD_SLSC_AVERAGE) { // x ./ vecnorm(x, 2, kdim), nan2zero
+                const R q2 = v.x * v.x + v.y * v.y;
+                const R inv = q2 > 0 ? fast_rsqrt(q2) : R(0); // x * rsqrt(|x|^2): 2 ulp of x / |x| (fp32: MUFU.RSQ instead of sqrt + divide)
+                v.x *= inv; v.y *= inv;
+            }
+            tile[(n + 8 * u) * 32 + lane] = v;
+            if (OP == QUPS_APD_PCF) pre[(n + 8 * u) * 32 + lane] = atan2_(v.y, v.x);
+        }
     }
     __syncthreads();
     R zr = 0, zi = 0, na = 0;
@@ -198,31 +221,55 @@ __global__ void __launch_bounds__(256) aperture_tile_kernel(void *out, void *out
         }
         return;
     }
-    if (OP == QUPS_APD_SLSC_ENSEMBLE) { // prefix powers P(k) = sum_{n < k} |x_n|^2, one column per lane (warp 0)
-        if (warp == 0) {
-            R p = 0;
-            pre[lane] = 0;
-            for (uint32_t n = 0; n < A; ++n) { const V v = tile[n * 32 + lane]; p += v.x * v.x + v.y * v.y; pre[(n + 1) * 32 + lane] = p; }
-        }
+    const uint32_t seg = (A + 7) / 8;   // prefix powers: warp w scans rows [w seg, (w + 1) seg), the segment totals join at use
+    auto P = [&](uint32_t k) -> R {     // P(k) = sum_{n < k} |x_n|^2 of this lane's column
+        if (k == 0) return R(0);
+        R v = pre[k * 32 + lane];
+        for (uint32_t w = 0; w < (k - 1) / seg; ++w) v += segtot[w][lane];
+        return v;
+    };
+    if (OP == QUPS_APD_SLSC_ENSEMBLE) {
+        R p = 0;
+        for (uint32_t n = warp * seg; n < min(A, (warp + 1) * seg); ++n) { const V v = tile[n * 32 + lane]; p += v.x * v.x + v.y * v.y; pre[(n + 1) * 32 + lane] = p; }
+        segtot[warp][lane] = p;
         __syncthreads();
     }
-    // work items: (block of 4 consecutive lags starting at 1 + 4 blk, chunk of 64 aperture elements)
+    // work items: (block of 4 consecutive lags starting at 1 + 4 blk, chunk of 64 aperture elements); only the lag blocks
+    // that hold a requested lag are listed (in ascending order: the item -> warp assignment stays a function of the
+    // arguments alone, so the result is deterministic)
     const uint32_t NB = (A + 2) / 4, NK = (A + 63) / 64; // lags 1 .. A-1
-    for (uint32_t it = warp; it < NB * NK; it += 8) {
-        const uint32_t blk = it / NK, k = it % NK, lag0 = 1 + 4 * blk;
+    if (warp == 0) {
+        for (uint32_t b0 = 0; b0 < NB; b0 += 32) {
+            const uint32_t blk = b0 + lane, lag0 = 1 + 4 * blk;
+            bool any = false;
+            if (blk < NB)
+                for (int j = 0; j < 4; ++j) any = any || ((lag0 + j < A) && lagmask[lag0 + j]);
+            const unsigned bal = __ballot_sync(0xffffffffu, any);
+            const uint32_t base = s_nact;
+            if (any) s_act[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)blk;
+            __syncwarp();
+            if (lane == 0) s_nact = base + __popc(bal);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const uint32_t nact = s_nact;
+    for (uint32_t it = warp; it < nact * NK; it += 8) {
+        const uint32_t blk = s_act[it / NK], k = it % NK, lag0 = 1 + 4 * blk;
         bool m[4];
-        bool any = false;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { m[j] = (lag0 + j < A) && lagmask[lag0 + j]; any = any || m[j]; }
-        if (!any) continue; // warp-uniform
+        for (int j = 0; j < 4; ++j) m[j] = (lag0 + j < A) && lagmask[lag0 + j];
         R ar[4] = {0, 0, 0, 0}, ai[4] = {0, 0, 0, 0};
-        const uint32_t nend = min(A, k * 64 + 64);
+        // pairs (n, n + lag) need n + lag < A: past n = A - lag0 every partner is a zero row; chunk ends are multiples of 4
+        // (or the end of the aperture, followed by zero rows), so neither load needs a range test
+        const uint32_t nend = min(min(A, k * 64 + 64), A > lag0 ? A - lag0 : 0u);
+        const V *tu = tile + lane, *tv = tile + (size_t)lag0 * 32 + lane;
         for (uint32_t n0 = k * 64; n0 < nend; n0 += 4) {
             V u[4], v[7];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { u[i].x = u[i].y = R(0); if (n0 + i < nend) u[i] = tile[(n0 + i) * 32 + lane]; }
+            for (int i = 0; i < 4; ++i) u[i] = tu[(n0 + i) * 32];
 #pragma unroll
-            for (int t = 0; t < 7; ++t) { v[t].x = v[t].y = R(0); if (n0 + lag0 + t < A) v[t] = tile[(n0 + lag0 + t) * 32 + lane]; }
+            for (int t = 0; t < 7; ++t) v[t] = tv[(n0 + t) * 32];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -241,7 +288,7 @@ __global__ void __launch_bounds__(256) aperture_tile_kernel(void *out, void *out
             const uint32_t lag = lag0 + j;
             if (OP == QUPS_APD_DMAS) { zr += ar[j]; zi += ai[j]; }
             else if (OP == QUPS_APD_SLSC_AVERAGE) zr += ar[j] / (R)(A - lag) / R(2) / (R)nlags; // W = S ./ (A - H) / 2 / L
-            else { zr += ar[j]; if (k == 0) na += pre[(A - lag) * 32 + lane] + pre[A * 32 + lane] - pre[lag * 32 + lane]; }
+            else { zr += ar[j]; if (k == 0) na += P(A - lag) + P(A) - P(lag); }
         }
     }
     if (OP != QUPS_APD_DMAS && warp == 0 && lagmask[0]) { // ismember(H, lags) with a zero lag: the diagonal, each element once
@@ -293,8 +340,8 @@ int launch_aperture(const qups_aperture_params &p, void *out, void *out2, const 
     // pair-sum operators: shared-memory tile of 32 columns x the whole aperture when it fits (pcf measured slower on the tile —
     // 2.47 vs 1.7 ms on the C2 cube: its two atan2 per element hide behind the stream — and stays on the streaming kernel)
     const size_t esz = p.dtype == QUPS_F64 ? 16 : 8;
-    const size_t tile_smem = (size_t)p.A * 32 * esz + (p.op == QUPS_APD_SLSC_ENSEMBLE || p.op == QUPS_APD_PCF ? (size_t)(p.A + 1) * 32 * (esz / 2) : 0);
-    if (p.op != QUPS_APD_COHFAC && p.op != QUPS_APD_PCF && tile_smem <= 200 * 1024 && p.A < (1u << 24) && !getenv("QUPS_B200_APERTURE_SIMPLE")) {
+    const size_t tile_smem = (size_t)(p.A + 12) * 32 * esz + (p.op == QUPS_APD_SLSC_ENSEMBLE || p.op == QUPS_APD_PCF ? (size_t)(p.A + 1) * 32 * (esz / 2) : 0);
+    if (p.op != QUPS_APD_COHFAC && p.op != QUPS_APD_PCF && tile_smem <= 200 * 1024 && p.A < 16384 && !getenv("QUPS_B200_APERTURE_SIMPLE")) {
         const uint64_t blocks = (total + 31) / 32;
         if (blocks <= 0x7fffffffull) {
             cudaError_t e2 = cudaSuccess;
