@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import oracle_c, apod_np, prep_np, aperture_np  # noqa: E402
+from oracle import oracle_c, apod_np, prep_np, aperture_np, xcorr_np, refocus_np  # noqa: E402
 from qups_b200 import synth  # noqa: E402
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ext")
@@ -62,7 +62,32 @@ def greens():
                         R0=2e-4, y32=y32, y64=y64)
 
 
+def xcorr():
+    rng = np.random.default_rng(11)
+    x = (rng.standard_normal((160, 5, 2)) + 1j * rng.standard_normal((160, 5, 2))).astype(np.complex64)
+    w = (np.hanning(7) + 0.2).astype(f32)
+    np.savez_compressed(os.path.join(HERE, "xcorr.npz"), x=x, w=w, lags=np.array([-3, 0, 2]),
+                        y_neighbor=xcorr_np.pwznxcorr(x, [-3, 0, 2], w), y_center_nonorm=xcorr_np.pwznxcorr(x, [-3, 0, 2], 6, ref="center", norm=False),
+                        y_x0=xcorr_np.pwznxcorr(x, 2, 8, ref="x0", x0=x[:, 1:2], zero=False))
+
+
+def refocus():
+    rng = np.random.default_rng(13)
+    T, N, V, fs, c0 = 64, 8, 6, 20e6, 1540.0
+    xe = (np.arange(N) - (N - 1) / 2) * 0.3e-3
+    th = np.deg2rad(np.linspace(-9, 9, V))
+    tau = -(np.sin(th)[None, :] * xe[:, None]) / c0                   # plane-wave delays, elements x pulses
+    apd = np.ones((N, V))
+    x = (rng.standard_normal((T, N, V)) + 1j * rng.standard_normal((T, N, V))).astype(np.complex64)
+    t0 = np.linspace(1e-6, 1.4e-6, V)
+    out = dict(x=x, tau=tau, apd=apd, t0=t0, fs=fs, angles=np.rad2deg(th), c0=c0)
+    for m in ("tikhonov", "adjoint"):
+        y, t0m, Hi = refocus_np.refocus(x, t0, fs, tau, apd, m)
+        out["y_" + m], out["Hi_" + m], out["t0_out"] = y, Hi, t0m
+    np.savez_compressed(os.path.join(HERE, "refocus.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(HERE, exist_ok=True)
-    apod(); prep(); aperture(); greens()
+    apod(); prep(); aperture(); greens(); xcorr(); refocus()
     print("wrote", sorted(os.listdir(HERE)), sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE)), "bytes")

@@ -44,7 +44,41 @@ def test_oracle_reproduces_prep_aperture_greens_golden(oracle_c):
     assert rel_linf(g["y32"], g["y64"]) < 1e-3       # the fp32 oracle's own delay rounding vs the fp64 arbiter
 
 
+def test_oracle_reproduces_xcorr_refocus_golden():
+    from oracle import xcorr_np, refocus_np
+    d = _ld("xcorr.npz")
+    x, w = d["x"], d["w"]
+    assert np.allclose(xcorr_np.pwznxcorr(x, [-3, 0, 2], w), d["y_neighbor"], atol=1e-6, equal_nan=True)
+    assert np.allclose(xcorr_np.pwznxcorr(x, [-3, 0, 2], 6, ref="center", norm=False), d["y_center_nonorm"], atol=1e-6 * np.abs(d["y_center_nonorm"]).max())
+    assert np.allclose(xcorr_np.pwznxcorr(x, 2, 8, ref="x0", x0=x[:, 1:2], zero=False), d["y_x0"], atol=1e-6, equal_nan=True)
+    r = _ld("refocus.npz")
+    for m in ("tikhonov", "adjoint"):
+        y, t0m, Hi = refocus_np.refocus(r["x"], r["t0"], float(r["fs"]), r["tau"], r["apd"], m)
+        assert np.allclose(y, r["y_" + m], atol=1e-9 * np.abs(r["y_" + m]).max()) and np.allclose(Hi, r["Hi_" + m], atol=1e-9 * np.abs(r["Hi_" + m]).max())
+        assert t0m == float(r["t0_out"])
+
+
 # ------------------------------------------------------------------ GPU: CUDA == fixtures -----------------------------
+@pytest.mark.gpu
+def test_cuda_xcorr_refocus_match_golden():
+    import qups_b200
+    from qups_b200 import synth, ultrasound as U
+    d = _ld("xcorr.npz")
+    x, w = d["x"], d["w"]
+    assert rel_linf(qups_b200.pwznxcorr(x, [-3, 0, 2], w), d["y_neighbor"]) < 1e-5
+    assert rel_linf(qups_b200.pwznxcorr(x, [-3, 0, 2], 6, ref="center", norm=False), d["y_center_nonorm"]) < 2e-4
+    assert rel_linf(qups_b200.pwznxcorr(x, 2, 8, ref="x0", x0=x[:, 1:2], zero=False), d["y_x0"]) < 1e-5
+    r = _ld("refocus.npz")
+    th = np.deg2rad(r["angles"])
+    seq = U.Sequence("PW", np.stack([np.sin(th), 0 * th, np.cos(th)]), float(r["c0"]))
+    tx = synth.linear_array(8, 0.3e-3)
+    assert np.allclose(U.seq_delays(seq, tx), r["tau"], atol=1e-15)
+    for m in ("tikhonov", "adjoint"):
+        chd, Hi = U.refocus(U.ChannelData(r["x"], r["t0"], float(r["fs"])), seq, tx, m)
+        assert rel_linf(Hi, r["Hi_" + m]) < 1e-9 and abs(chd.t0 - float(r["t0_out"])) < 1e-15
+        assert rel_linf(np.asarray(chd.data), r["y_" + m]) < 1e-5
+
+
 @pytest.mark.gpu
 def test_cuda_apod_matches_golden():
     from qups_b200 import ultrasound as U
