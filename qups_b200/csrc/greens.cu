@@ -388,20 +388,16 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
                 __syncwarp();
             }
             __syncthreads();
-            // ---- (3) each train position gathers the entries that arrive exactly there (sorted order) -----------
-            for (int r = tid; r < W; r += kGThreads) {
-                const int b = min(r / kCBW, nbk - 1);
-                const int e_lo = s_start[b], e_hi = s_start[b + 1];
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, az = 0.f;
-                for (int e = e_lo; e < e_hi; ++e) {
-                    const int q = s_perm[e];
-                    if (s_ci[q] == r) {
-                        const float4 w = s_w[q];
-                        a0 += w.x; a1 += w.y; a2 += w.z; a3 += w.w; az += s_z[q];
-                    }
-                }
-                if (e_hi > e_lo) {
-                    trains[r] += a0; trains[Wp + r] += a1; trains[2 * Wp + r] += a2; trains[3 * Wp + r] += a3; trains[4 * Wp + r] += az;
+            // ---- (3) one thread per bucket walks ITS entries in sorted order and adds each into its train position -------
+            // O(entries) instead of O(positions x bucket size) (round 1: every train position scanned its whole bucket for
+            // the entries arriving exactly there — 35 % of the kernel's instructions).  A bucket is owned by one thread, its
+            // entries are in stable (scatterer-index) order, so the sum per position is deterministic.
+            for (int bk = tid; bk < nbk; bk += kGThreads) {
+                const int e_hi = s_start[bk + 1];
+                for (int e = s_start[bk]; e < e_hi; ++e) {
+                    const int q = s_perm[e], r = s_ci[q];
+                    const float4 w = s_w[q];
+                    trains[r] += w.x; trains[Wp + r] += w.y; trains[2 * Wp + r] += w.z; trains[3 * Wp + r] += w.w; trains[4 * Wp + r] += s_z[q];
                 }
             }
         }
