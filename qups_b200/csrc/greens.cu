@@ -267,6 +267,9 @@ constexpr int kCChunk = 1024;   // scatterer entries staged per pass
 constexpr int kCBW = 32;        // bucket width (train positions)
 constexpr int kCNB = 136;       // max buckets: (kCBlock + K) / 32 + 1
 constexpr int kCBlock = 3072;   // output samples per train window
+constexpr int kNO = 11;         // step (4): consecutive outputs per thread (odd: conflict-free at a lane stride of kNO words)
+constexpr int kPB = 8;          // step (4): kernel taps per register block
+constexpr int kConvPad = 12;    // zero samples after every train row (>= kNO - 1)
 
 template <typename DOUT>
 __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<float> p, DOUT *y, const float *Pi, const float *amp,
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
     extern __shared__ __align__(16) unsigned char gsm[];
     const int K = (int)p.T;
     const int W = blk + K - 1;                                   // train window: tau in [tau0, tau0 + W)
-    const int Wp = (W + 3) & ~3;
+    const int Wp = (W + kConvPad + 3) & ~3;
     float2 *kx = reinterpret_cast<float2 *>(gsm);                // kx[q + 1], q = -1 .. K
     float *trains = reinterpret_cast<float *>(kx + ((K + 2 + 1) & ~1)); // 5 x Wp
     float4 *s_w = reinterpret_cast<float4 *>(trains + 5 * Wp + ((5 * Wp) & 3 ? 4 - ((5 * Wp) & 3) : 0));
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
         kx[0] = lo; kx[K + 1] = hi;
     }
     const int nbk = min(kCNB, (W + kCBW - 1) / kCBW);
+    const double fs_c0 = fs / c0;   // one fp64 division per thread instead of one per (scatterer, trace) entry
 
     for (uint64_t sb = 0; sb < p.S; sb += (uint64_t)blk) {
         const long long tau0 = p.n0 + (long long)sb - (K - 1);
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
                 const double r_rx = sqrt(ax * ax + ay * ay + az * az), r_tx = sqrt(bx * bx + by * by + bz * bz);
                 double att = (double)amp[i];
                 if (R0 != 0.0) att /= (fmax(r_rx, R0) * fmax(r_tx, R0));
-                const double c = (r_rx + r_tx) / c0 * fs + t0s;      // arrival: kernel position of sample t is d = t - c
+                const double c = fma(r_rx + r_tx, fs_c0, t0s);       // arrival (r_rx + r_tx) / c0 * fs + t0s: kernel position of sample t is d = t - c
                 const double cc = ceil(c);
                 const float f = (float)(cc - c), a = (float)att;
                 float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -403,37 +407,55 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
         }
         __syncthreads();
         // ---- (4) x(t) = sum_p sum_j kx[p-1+j] I_j[t-p] + kx[K-1] I_z[t-(K-1)] ----------------------------------
-        for (int s0 = 0; s0 < blk; s0 += kGThreads * 8) {
-            float2 acc[8];
-            int rt[8];
+        // A thread owns kNO CONSECUTIVE outputs (odd count: lanes kNO words apart hit 32 distinct banks) and walks p in blocks
+        // of kPB: per train the kNO + kPB - 1 samples the block touches are loaded once and feed kNO x kPB products —
+        // 7 FMA per shared load instead of the 2 of a one-output-at-a-time loop.  The rows carry kConvPad zeros so the window
+        // of the last outputs needs no range test.
+        for (int task = tid; task * kNO < blk; task += kGThreads) {
+            const int o0 = task * kNO;
+            float2 acc[kNO];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { acc[i] = make_float2(0.f, 0.f); rt[i] = s0 + tid + i * kGThreads + (K - 1); }
-            float2 k0 = kx[0], k1 = kx[1], k2 = kx[2], k3 = (K >= 2) ? kx[3] : make_float2(0.f, 0.f); // kx[p-1+j], p = 0
-            for (int pp = 0; pp <= K - 2; ++pp) {
+            for (int i = 0; i < kNO; ++i) acc[i] = make_float2(0.f, 0.f);
+            int pp0 = 0;
+            for (; pp0 + kPB - 1 <= K - 2; pp0 += kPB) {
+                float2 kk[kPB + 3];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = rt[i] - pp;
-                    if (r < W) {
-                        const float i0 = trains[r], i1 = trains[Wp + r], i2 = trains[2 * Wp + r], i3 = trains[3 * Wp + r];
-                        acc[i].x = fmaf(k0.x, i0, acc[i].x); acc[i].y = fmaf(k0.y, i0, acc[i].y);
-                        acc[i].x = fmaf(k1.x, i1, acc[i].x); acc[i].y = fmaf(k1.y, i1, acc[i].y);
-                        acc[i].x = fmaf(k2.x, i2, acc[i].x); acc[i].y = fmaf(k2.y, i2, acc[i].y);
-                        acc[i].x = fmaf(k3.x, i3, acc[i].x); acc[i].y = fmaf(k3.y, i3, acc[i].y);
-                    }
+                for (int q = 0; q < kPB + 3; ++q) kk[q] = kx[pp0 + q];   // kx[p - 1 + j] at index p + j <= K + 1
+                const int base = o0 + (K - 1) - pp0 - (kPB - 1);          // >= 1: o0 >= 0, pp0 + kPB - 1 <= K - 2
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v[kNO + kPB - 1];
+                    const float *tr = trains + j * Wp + base;
+#pragma unroll
+                    for (int m = 0; m < kNO + kPB - 1; ++m) v[m] = tr[m];
+#pragma unroll
+                    for (int d = 0; d < kPB; ++d)
+#pragma unroll
+                        for (int i = 0; i < kNO; ++i) {
+                            acc[i].x = fmaf(kk[d + j].x, v[i + kPB - 1 - d], acc[i].x);
+                            acc[i].y = fmaf(kk[d + j].y, v[i + kPB - 1 - d], acc[i].y);
+                        }
                 }
-                k0 = k1; k1 = k2; k2 = k3;
-                k3 = (pp + 4 <= K + 1) ? kx[pp + 4] : make_float2(0.f, 0.f);
+            }
+            for (; pp0 <= K - 2; ++pp0) {                                 // remaining p (fewer than kPB)
+                const float2 k0 = kx[pp0], k1 = kx[pp0 + 1], k2 = kx[pp0 + 2], k3 = kx[pp0 + 3];
+#pragma unroll
+                for (int i = 0; i < kNO; ++i) {
+                    const int r = o0 + i + (K - 1) - pp0;
+                    const float i0 = trains[r], i1 = trains[Wp + r], i2 = trains[2 * Wp + r], i3 = trains[3 * Wp + r];
+                    acc[i].x = fmaf(k0.x, i0, acc[i].x); acc[i].y = fmaf(k0.y, i0, acc[i].y);
+                    acc[i].x = fmaf(k1.x, i1, acc[i].x); acc[i].y = fmaf(k1.y, i1, acc[i].y);
+                    acc[i].x = fmaf(k2.x, i2, acc[i].x); acc[i].y = fmaf(k2.y, i2, acc[i].y);
+                    acc[i].x = fmaf(k3.x, i3, acc[i].x); acc[i].y = fmaf(k3.y, i3, acc[i].y);
+                }
             }
             const float2 kl = kx[K]; // kernel sample K-1: the closed end of interp1's support (xq == K)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rt[i] - (K - 1);
-                if (r < W) {
-                    const float iz = trains[4 * Wp + r];
-                    acc[i].x = fmaf(kl.x, iz, acc[i].x); acc[i].y = fmaf(kl.y, iz, acc[i].y);
-                }
-                const uint64_t sidx = sb + (uint64_t)(s0 + tid + i * kGThreads);
-                if (s0 + tid + i * kGThreads < blk && sidx < p.S)
+            for (int i = 0; i < kNO; ++i) {
+                const float iz = trains[4 * Wp + o0 + i];
+                acc[i].x = fmaf(kl.x, iz, acc[i].x); acc[i].y = fmaf(kl.y, iz, acc[i].y);
+                const uint64_t sidx = sb + (uint64_t)(o0 + i);
+                if (o0 + i < blk && sidx < p.S)
                     data_traits<DOUT>::store(yt, sidx, {acc[i].x, acc[i].y});
             }
         }
@@ -442,7 +464,7 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
 }
 
 static size_t greens_conv_smem(int K, int blk) {
-    const int W = blk + K - 1, Wp = (W + 3) & ~3;
+    const int W = blk + K - 1, Wp = (W + kConvPad + 3) & ~3;
     size_t b = sizeof(float2) * ((K + 2 + 1) & ~1);
     b += sizeof(float) * (5 * Wp + 4);
     b += sizeof(float4) * kCChunk + sizeof(float) * kCChunk + sizeof(int) * kCChunk;
