@@ -9,6 +9,7 @@ launch geometry, call the kernel by its base name:
     DASf          kern/das_spec.m:284-373
     wsinterpd2f   kern/wsinterpd2.m:193-235
     greensf       src/UltrasoundSystem.m:649-718
+    convf/convcf  kern/convd.m:135-201
 
 It is used to (i) pin the oracle against the real reference kernels (tests/test_gpu_reference_kernel.py) and (ii) time
 "the reference's kernel on this box" beside ours (bench.py `ref_kernel`).  Never imported by the product path.
@@ -207,3 +208,37 @@ def ref_greensf(ps, amp, pn, pv, kern, n0, S, fs, c0, wv_t0, fsr=1.0, R0=1e-3, i
     k.launch((gx, N, M), (bx, 1, 1), [x, col(ps), das, col(pn), col(pv), dk, sb, iblock, pack, E, C.c_int32(int(interp))])
     torch.cuda.synchronize()
     return x.cpu().numpy().reshape((S, N, M), order="F")
+
+
+class RefConvd:
+    """The reference's batched convolution kernels convf / convcf (src/convd.cu:133-156) behind the launcher of
+    kern/convd.m:98-201: x is C x M x S, y is C x N x S, z is C x L x S (column-major), start lag L0 as a __constant__."""
+
+    def __init__(self, cplx: bool, variant: str = "ieee"):
+        self.cplx = cplx
+        self.k = RefModule("convd", "convcf" if cplx else "convf", variant)
+
+    def run(self, x, y, shape="full"):
+        """x: (C, M, S), y: (C, N, S) NumPy arrays (logical shapes).  Returns z (C, L, S) and the lags."""
+        dt, tdt = (np.complex64, torch.complex64) if self.cplx else (np.float32, torch.float32)
+        Cn, M, S = x.shape
+        N = y.shape[1]
+        if shape == "full":
+            lags = np.arange(-(N - 1), M)                       # kern/convd.m:104-105
+        elif shape == "same":
+            lags = np.arange(0, M) - (N - 1) // 2               # :106-107
+        else:
+            lags = np.arange(0, M - N + 1)                      # :108-109
+        L = len(lags)
+        l0 = int(-lags[0]) if L else 0                          # :113
+        col = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dt).transpose(2, 1, 0))).cuda()  # memory: C fastest
+        dx, dy = col(x), col(y)
+        dz = torch.zeros((S, L, Cn), dtype=tdt, device="cuda")
+        sizes = torch.tensor([Cn, M, Cn, N, Cn, L, Cn], dtype=torch.int64, device="cuda")   # [xstr, M, ystr, N, zstr, L, C]  (:120-121)
+        self.k.set_const("L0", l0, C.c_int32)
+        mt = self.k.max_threads
+        blk = (1, min(L, mt), 1) if Cn == 1 else (min(Cn, mt), 1, 1)                        # :187-191
+        grid = tuple(-(-a // b) for a, b in zip((Cn, L, S), blk))
+        self.k.launch(grid, blk, [dx, dy, dz, sizes])
+        torch.cuda.synchronize()
+        return dz.cpu().numpy().transpose(2, 1, 0), lags

@@ -324,3 +324,22 @@ def test_fmod_convention_cpu_branch_vs_reference_gpu_kernel():
     assert np.abs(want).max() > 1
     assert rel_linf(ours, want) < 3e-2, rel_linf(ours, want)      # cubic on base-band vs pass-band data + the reference's Horner cubic
     assert rel_linf(ours, plain) > 5 * rel_linf(ours, want)        # without the per-transmit factor the images differ
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", ["full", "same", "valid"])
+def test_reference_convd_kernel_pins_qups_convd(cplx, shape):
+    """The reference's own convf / convcf (src/convd.cu, IEEE build, launched as kern/convd.m:135-201 does) against qups_convd on
+    the same data: same lags, values to 1e-6 of the largest output (the reference accumulates in the same tap order; what is
+    left is FMA contraction inside its complex product)."""
+    ref_ptx = _need("convd", "ieee")
+    import qups_b200
+    rng = np.random.default_rng(7)
+    Cn, M, N, S = 5, 37, 9, 3
+    mk = (lambda *s: (rng.standard_normal(s) + 1j * rng.standard_normal(s)).astype(np.complex64)) if cplx else (lambda *s: rng.standard_normal(s).astype(f32))
+    x, y = mk(Cn, M, S), mk(Cn, N, S)
+    zr, lags_r = ref_ptx.RefConvd(cplx).run(x, y, shape)
+    z, lags = qups_b200.convd(x, y, 2, shape)
+    assert np.array_equal(np.ravel(lags), lags_r)
+    assert z.shape == zr.shape
+    assert np.max(np.abs(z - zr)) <= 1e-6 * np.max(np.abs(zr))
