@@ -467,6 +467,24 @@ def next_row_legs(dev, peak, log):
             out[name] = {"error": repr(e)}
         log(f"next-row {name}: {out[name]}")
 
+    # ---- qups_das_cohfac at C2: DAS + coherence factor of the per-receive images in one pass (no 2.15 GB keep_rx cube) ----
+    try:
+        import qups_b200
+        P2, o2 = workload("c2")
+        x2 = rand_cube(P2.T, P2.N, P2.M, dev)
+        r2 = DasRunner(P2, o2, dev, x_dev=x2)
+        cf = torch.empty(r2.I, dtype=torch.float32, device=dev)
+        fn = lambda: _lib.check(L.qups_das_cohfac(C.byref(r2.p), vp(r2.y), vp(cf), vp(r2.dPi), vp(r2.dPr), vp(r2.dPv4), vp(r2.dNv), vp(r2.dC),
+                                                  vp(r2.dX), st))
+        ms, mn = time_device(fn, 1, 3)
+        out["das_cohfac_c2"] = {"ms": mn, "value": P2.I / mn / 1e3, "unit": UNIT, "kernel": qups_b200.last_das_kernel(),
+                                "cf_mean": float(torch.nan_to_num(cf).mean()),
+                                "note": "replaces DAS(keep_rx) -> cohfac + sum (SYN on the staged kernel + aperture pass)"}
+        log(f"next-row das_cohfac_c2: {out['das_cohfac_c2']}")
+        del r2, x2, cf
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["das_cohfac_c2"] = {"error": repr(e)}
     # ---- qups_chd_prep (src/ChannelData.m zeropad / hilbert / downmix / cast) ----
     g = torch.Generator(device=dev); g.manual_seed(1)
     rf = torch.randn((K, T), generator=g, device=dev, dtype=torch.float32)

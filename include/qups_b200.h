@@ -157,6 +157,14 @@ typedef struct {
 QUPS_API int qups_das_fused(const qups_das_params *p, const qups_apod_fused *apf, void *y, const void *Pi, const void *Pr,
                    const void *Pv4, const void *Nv, const void *apod, const void *cinv, const uint64_t *acstride, const void *x,
                    qups_stream_t stream);
+
+/* DAS and the coherence factor of its per-receive images in ONE pass, without the I x N cube:
+ *   b  = DAS(us, chd, 'keep_rx', true);  y = sum(b, rxdim);  cf = cohfac(b, rxdim) = |sum_n b_n|^2 ./ sum_n |b_n|^2 / N
+ * (src/UltrasoundSystem.m:3172 + kern/cohfac.m).  y: I complex, cf: I real.  Plain weights only: dtype F32, S = 0, scalar cinv,
+ * no kept aperture, fmod = 0, F = 1.  Calls outside the staged kernel's envelope (lanczos3, very large N + M) are served by
+ * DAS(keep_rx) into library scratch + the cohfac reduction, same results. */
+QUPS_API int qups_das_cohfac(const qups_das_params *p, void *y, void *cf, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
+                             const void *cinv, const void *x, qups_stream_t stream);
 /* The dense array the reference's generator would return: which = 0 -> receive weights I1 x I2 x I3 x NM(=N),
  * which = 1 -> transmit weights I1 x I2 x I3 x 1 x NM(=M); real fp32, or complex (imag 0) when as_complex. */
 QUPS_API int qups_apod_generate(const qups_apod_fused *apf, int32_t which, void *out, int32_t as_complex, const void *Pi, const void *Pr,

@@ -18,6 +18,8 @@
 //   r = qups_b200_mex('aperture', C, r0, b)                                    cohfac / dmas / pcf / slsc along one dimension
 //                                                                               (C.op, C.C, C.A, C.S, C.lags (uint32), C.gamma)
 //   y = qups_b200_mex('prep',   C, y0, x, t0)                                 zeropad -> hilbert -> downmix -> cast (C.B, C.A, C.hilbert, C.fmix, C.fs, C.N)
+//   y = qups_b200_mex('das_cohfac', C, yg, Pi, Pr, Pv4, Nv, cinv, x, cf0)       DAS image; the coherence factor is written into the
+//                                                                               gpuArray cf0 (single, size of the image) in place
 //   y = qups_b200_mex('xcorr',  C, y0, x, x0, w)                               pwznxcorr: C.ref, C.zero, C.norm, C.pad, C.stride, C.lags (int32, host),
 //                                                                               x is T x N x F, w the window weights (single/double gpuArray), x0 may be []
 //   y = qups_b200_mex('refocus',C, y0, x, Hi)                                  REFoCUS decode: C.fs, C.t0 (double, host, 1 or V values); y0 T x N x E prototype
@@ -184,6 +186,22 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         p.fs = fld(C, "fs", 1); p.fmix = fld(C, "fmix", 0);
         check(qups_chd_prep(&p, y, RO(x), p.n_t0 ? RO(t0) : NULL, NULL));
         mxGPUDestroyGPUArray(x); mxGPUDestroyGPUArray(t0);
+    } else if (!strcmp(op, "das_cohfac")) {
+        if (nrhs != 10) mexErrMsgIdAndTxt("QUPS:b200:usage", "'das_cohfac' takes 10 arguments");
+        const mxGPUArray *Pi = IN(3), *Pr = IN(4), *Pv = IN(5), *Nv = IN(6), *cinv = IN(7), *x = IN(8), *cf = IN(9);
+        qups_das_params p;
+        memset(&p, 0, sizeof(p));
+        p.struct_size = sizeof(p);
+        p.dtype = dtype_of(x);
+        p.I1 = (uint64_t)fld(C, "I1", 1); p.I2 = (uint64_t)fld(C, "I2", 1); p.I3 = (uint64_t)fld(C, "I3", 1);
+        p.N = (uint64_t)fld(C, "N", 1); p.M = (uint64_t)fld(C, "M", 1); p.T = (uint64_t)fld(C, "T", 1); p.F = 1;
+        p.flag = (int32_t)fld(C, "flag", 0); p.vs = (int32_t)fld(C, "VS", 1); p.dv = (int32_t)fld(C, "DV", 0);
+        p.fs = fld(C, "fs", 1);
+        /* cf0 is written in place: the factor comes back through the caller's gpuArray (a second output would need a second
+         * prototype argument; the reference's feval convention returns one array per non-const pointer) */
+        check(qups_das_cohfac(&p, y, (void *)mxGPUGetDataReadOnly(cf), RO(Pi), RO(Pr), RO(Pv), RO(Nv), RO(cinv), RO(x), NULL));
+        mxGPUDestroyGPUArray(Pi); mxGPUDestroyGPUArray(Pr); mxGPUDestroyGPUArray(Pv); mxGPUDestroyGPUArray(Nv);
+        mxGPUDestroyGPUArray(cinv); mxGPUDestroyGPUArray(x); mxGPUDestroyGPUArray(cf);
     } else if (!strcmp(op, "xcorr")) {
         if (nrhs != 6) mexErrMsgIdAndTxt("QUPS:b200:usage", "'xcorr' takes 6 arguments");
         const mxGPUArray *x = IN(3), *x0 = IN(4), *w = IN(5);

@@ -19,7 +19,7 @@ INTERP = {"nearest": NEAREST, "linear": LINEAR, "cubic": CUBIC, "lanczos3": LANC
 
 EXPORTS = (
     "qups_das", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
-    "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_greens", "qups_convd", "qups_pwznxcorr", "qups_refocus", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel", "qups_last_ws2_kernel",
+    "qups_das_fused", "qups_das_cohfac", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_greens", "qups_convd", "qups_pwznxcorr", "qups_refocus", "qups_host_release", "qups_last_error", "qups_version", "qups_launch_count", "qups_last_das_kernel", "qups_last_ws2_kernel",
 )
 
 
@@ -147,6 +147,8 @@ def lib() -> C.CDLL:
     vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
     L.qups_das.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, vp, u64p, vp, vp]
     L.qups_das_fused.argtypes = [C.POINTER(DasParams), C.POINTER(ApodFused), vp, vp, vp, vp, vp, vp, vp, u64p, vp, vp]
+    L.qups_das_cohfac.argtypes = [C.POINTER(DasParams), vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.qups_das_cohfac.restype = C.c_int
     L.qups_apod_generate.argtypes = [C.POINTER(ApodFused), C.c_int32, vp, C.c_int32, vp, vp, C.c_uint64, C.c_uint64,
                                      C.c_uint64, C.c_uint64, vp]
     L.qups_chd_prep.argtypes = [C.POINTER(PrepParams), vp, vp, vp, vp]
@@ -165,7 +167,7 @@ def lib() -> C.CDLL:
     L.qups_pwznxcorr.restype = C.c_int
     L.qups_refocus.argtypes = [C.POINTER(RefocusParams), vp, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
     L.qups_refocus.restype = C.c_int
-    for f in ("qups_das", "qups_das_fused", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
+    for f in ("qups_das", "qups_das_fused", "qups_das_cohfac", "qups_apod_generate", "qups_chd_prep", "qups_aperture", "qups_delays", "qups_das_host", "qups_modulate", "qups_wsinterpd2", "qups_wsinterpd",
               "qups_greens", "qups_version"):
         getattr(L, f).restype = C.c_int
     L.qups_last_error.restype = C.c_char_p

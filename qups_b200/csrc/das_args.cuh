@@ -32,6 +32,10 @@ template <typename R> struct DasArgs {
     // xq = 1 + (lut_tm[m * I + i] + lut_tn[n * I + i]), y = w * sum; Pi / Pr / Pv4 / Nv / cinv are then unused
     const float *lut_tn = nullptr, *lut_tm = nullptr, *lut_w = nullptr;
     int lut_wcplx = 0;
+    // coherence mode (staged kernel only, qups_das_cohfac): y = sum over both apertures, cf[i] = |sum_n b_n|^2 / sum_n |b_n|^2 / N with
+    // b_n the per-receive sums (kern/cohfac.m on DAS(..., 'keep_rx') output) — no I x N cube is materialised
+    int cohfac = 0;
+    float *cf = nullptr;
 };
 
 // launch entry points implemented in das_generic.cu / das_tiled.cu

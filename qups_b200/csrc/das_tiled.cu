@@ -86,9 +86,11 @@ constexpr int threads_of(int interp) { return (kCW + (interp == 0 ? kPW : 1)) * 
 #endif
 constexpr int kBarBytes = ((2 * kStages * 8 + 63) / 64) * 64;  // full[] + empty[] mbarriers
 // per-stage header block: [0] int4 (kind, outer index, inner tile, uniform sign of dv: +1 / -1 / 0 = mixed) | [1] float4 geometry A
-// (Pv.xyz, t0 of transmit `outer`; Pr.xyz when the inner traces are transmits) | [2] float4 geometry B (Nv.xyz) | [3] pad |
-// then the compact slot-offset table of all-fast stages (kNT x uint32)
-constexpr int kHdrBytes = 64 + 4 * kNT;
+// (Pv.xyz, t0 of transmit `outer`; Pr.xyz when the inner traces are transmits) | [2] float4 geometry B (Nv.xyz) | [3], [4] the
+// same two for the SECOND transmit of a coherence-mode stage (KEEP == 3: 8 receives x 2 transmits; the sign word then holds
+// (sgn0 + 1) | (sgn1 + 1) << 2) | then the compact slot-offset table of all-fast stages (kNT x uint32)
+constexpr int kHdrTab = 80;
+constexpr int kHdrBytes = kHdrTab + 4 * kNT;
 constexpr int kTilePix = kCW * 32 * kR; // pixels per tile; its SHAPE (tA x tB, lane patch lpa) is chosen per call from the pixel spacing
 
 // QUPS_MAGIC: the cubic fast path derives the tap address from the bits of 2^23 + floor(xq); the constant
@@ -135,6 +137,7 @@ struct TiledArgs {
     // CTA — [tile][4 M + 2 N] ordered ints: dv < 0 cluster min / max [M], dv >= 0 cluster min / max [M], dr min / max [N]
     int *bounds;
     int split_major;
+    float *partP;           // KEEP == 3: partial sums of |b_n|^2 [nsplit][I] next to the partial images in `part`
 };
 
 // ---- small PTX wrappers -----------------------------------------------------
@@ -434,10 +437,17 @@ __device__ __forceinline__ int tap_window(float xlo, float xhi, float Tf, int T,
 //        traces of a stage are 16 transmits of ONE receive, the registers hold dv(i, m) of a transmit tile and the stage
 //        scalar is dr(i, n) — so every stage adds to y(:,n).  (sample_pos only adds dv + dr: the swap is bit-neutral.)
 //        y is pre-zeroed by the launcher; a CTA owns its pixels (nsplit = 1), so the read-modify-write needs no atomics.
+//        3 = COHERENCE mode: DAS(..., 'keep_rx') -> cohfac / sum over the receive dimension WITHOUT the I x N cube
+//        (kern/cohfac.m: |sum_n b_n|^2 / sum_n |b_n|^2 / N needs every per-receive sum b_n = sum_m complete).  A stage holds
+//        8 receives x 2 consecutive transmits, so the 8 x 2 per-receive accumulators of a thread fit next to 8 (not 16) receive
+//        path lengths; after the last transmit of a receive group S += b_n, P += |b_n|^2.  Outputs S (the DAS image) and P go
+//        to the partial buffers; das_cf_reduce_kernel sums the receive splits and forms the factor.
 template <int INTERP, int NAP, int FUSED, int KEEP, int LUT = 0>
 __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_kernel(const TiledArgs a) {
     constexpr int kThreads = threads_of(INTERP);
     constexpr bool kInnerTx = (KEEP == 2); // the 16 traces of a stage run over transmits instead of receives
+    constexpr bool kCF = (KEEP == 3);      // coherence mode: trace j of a stage = receive (j & 7) of the group, transmit 2 outer + (j >> 3)
+    constexpr int kRX = kCF ? 8 : kNT;     // receives per inner tile
     static_assert(KEEP == 0 || (NAP == 0 && FUSED == 0), "kept apertures: plain weights only");
     static_assert(LUT == 0 || (NAP == 0 && FUSED == 0 && KEEP == 0), "table-driven delays: plain sum over both apertures");
     static_assert(kR == 2, "the packed fp32x2 inner loop assumes two pixel rows per thread");
@@ -487,7 +497,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
     }
-    const bool have_bounds = (FUSED == 0 && KEEP == 0 && LUT == 0) && a.bounds != nullptr;
+    const bool have_bounds = (FUSED == 0 && (KEEP == 0 || KEEP == 3) && LUT == 0) && a.bounds != nullptr;
     if (have_bounds) { // the six tables are contiguous in shared memory and in the pre-pass output
         const int *src = a.bounds + (uint64_t)tile * (4 * a.M + 2 * a.N);
         for (uint32_t i = tid; i < 4 * a.M + 2 * a.N; i += kThreads) s_dvnmin[i] = __ldg(src + i);
@@ -577,7 +587,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                 }
             }
         }
-        for (uint32_t n = kInnerTx ? 0u : nt0 * kNT; n < (have_bounds ? 0u : (kInnerTx ? a.N : min(nt1 * kNT, a.N))); ++n) {
+        for (uint32_t n = kInnerTx ? 0u : nt0 * kRX; n < (have_bounds ? 0u : (kInnerTx ? a.N : min(nt1 * kRX, a.N))); ++n) {
             float rx = 0.f, ry = 0.f, rz = 0.f;
             if constexpr (!LUT) { rx = __ldg(a.Pr + 3 * n); ry = __ldg(a.Pr + 3 * n + 1); rz = __ldg(a.Pr + 3 * n + 2); }
             int lo = INT_MAX, hi = INT_MIN;
@@ -601,9 +611,26 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
         // The ring carries only stages with work: (receive tile nt, transmit m) pairs whose 16 traces
         // are all outside the data for this tile are dropped by the producer and never cost a handshake.
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-        Pack2 pk;
-        pk.cinv = cinv;
-        pk.fs = fs;
+        // coherence mode: per-receive sums of the current receive group (both pixel rows), sum of their squared magnitudes
+        float2 b0[kCF ? 8 : 1], b1[kCF ? 8 : 1];
+        float accP0 = 0.f, accP1 = 0.f;
+#pragma unroll
+        for (int r = 0; r < (kCF ? 8 : 1); ++r) b0[r] = b1[r] = make_float2(0.f, 0.f);
+        auto cf_fold = [&]() { // a receive group is complete: S += b_n, P += |b_n|^2   (kern/cohfac.m)
+            if constexpr (kCF) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    acc0.x += b0[r].x; acc0.y += b0[r].y; acc1.x += b1[r].x; acc1.y += b1[r].y;
+                    accP0 = fmaf(b0[r].x, b0[r].x, fmaf(b0[r].y, b0[r].y, accP0));
+                    accP1 = fmaf(b1[r].x, b1[r].x, fmaf(b1[r].y, b1[r].y, accP1));
+                    b0[r] = b1[r] = make_float2(0.f, 0.f);
+                }
+            }
+        };
+        Pack2 pk, pk2;   // pk2: the second transmit of a coherence-mode stage
+        pk.cinv = pk2.cinv = cinv;
+        pk.fs = pk2.fs = fs;
+        pk2.dv = make_float2(0.f, 0.f); pk2.t0 = 0.f;
         float2 dr[kNT]; // .x = pixel row 0, .y = pixel row 1
 #pragma unroll
         for (int j = 0; j < kNT; ++j) dr[j] = make_float2(0.f, 0.f);
@@ -614,9 +641,10 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
             const int4 *hblk = stage_hdr(s);
             const int4 hdr = hblk[0]; // kind, m, nt, uniform sign of dv
             if (hdr.x == ST_END) break;
+            if constexpr (kCF) { if ((int)hdr.z != cur_nt && cur_nt >= 0) cf_fold(); }
             // hdr.y = outer index of the stage (transmit m; receive n when kInnerTx), hdr.z = inner tile (16 receives; 16 transmits)
             const uint32_t outer = (uint32_t)hdr.y, nt = (uint32_t)hdr.z;
-            const uint32_t m = kInnerTx ? 0u : outer;
+            const uint32_t m = kInnerTx ? 0u : (kCF ? 2u * outer : outer);
             float t0m = 0.f;
             if ((int)nt != cur_nt) { // new inner tile: its 16 path lengths go to registers
                 cur_nt = (int)nt;
@@ -633,7 +661,8 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                         dr[j].x = __ldg(a.tn + (uint64_t)n * a.I + pix[0]);
                         dr[j].y = __ldg(a.tn + (uint64_t)n * a.I + pix[1]);
                     } else {
-                        const uint32_t n = min(nt * kNT + j, a.N - 1);
+                        if (kCF && j >= 8) continue;
+                        const uint32_t n = min(nt * kRX + j, a.N - 1);
                         const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
                         dr[j].x = rx_dist(px[0], py[0], pz[0], rx, ry, rz);
                         dr[j].y = rx_dist(px[1], py[1], pz[1], rx, ry, rz);
@@ -660,16 +689,30 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
             } else {
 #if QUPS_HDRGEO
                 const float4 pv = reinterpret_cast<const float4 *>(hblk)[1];
-                if (VS && !DV && hdr.w != 0) {
+                const int sg0 = kCF ? ((hdr.w & 3) - 1) : hdr.w;
+                if (VS && !DV && sg0 != 0) {
                     // every pixel of the tile lies strictly on one side of the transmit's focal plane: dv = +-|Pi - Pv| exactly
                     // (d * (+-1) is exact), no dot product with the normal
                     const float d0 = rx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z), d1 = rx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z);
-                    pk.dv.x = hdr.w > 0 ? d0 : -d0;
-                    pk.dv.y = hdr.w > 0 ? d1 : -d1;
+                    pk.dv.x = sg0 > 0 ? d0 : -d0;
+                    pk.dv.y = sg0 > 0 ? d1 : -d1;
                 } else {
                     const float4 nv = reinterpret_cast<const float4 *>(hblk)[2];
                     pk.dv.x = tx_dist(px[0], py[0], pz[0], pv.x, pv.y, pv.z, nv.x, nv.y, nv.z, VS, DV);
                     pk.dv.y = tx_dist(px[1], py[1], pz[1], pv.x, pv.y, pv.z, nv.x, nv.y, nv.z, VS, DV);
+                }
+                if constexpr (kCF) { // the stage's second transmit (2 outer + 1; geometry zeroed by the producer when it does not exist)
+                    const float4 pv1 = reinterpret_cast<const float4 *>(hblk)[3], nv1 = reinterpret_cast<const float4 *>(hblk)[4];
+                    const int sg1 = ((hdr.w >> 2) & 3) - 1;
+                    if (VS && !DV && sg1 != 0) {
+                        const float d0 = rx_dist(px[0], py[0], pz[0], pv1.x, pv1.y, pv1.z), d1 = rx_dist(px[1], py[1], pz[1], pv1.x, pv1.y, pv1.z);
+                        pk2.dv.x = sg1 > 0 ? d0 : -d0;
+                        pk2.dv.y = sg1 > 0 ? d1 : -d1;
+                    } else {
+                        pk2.dv.x = tx_dist(px[0], py[0], pz[0], pv1.x, pv1.y, pv1.z, nv1.x, nv1.y, nv1.z, VS, DV);
+                        pk2.dv.y = tx_dist(px[1], py[1], pz[1], pv1.x, pv1.y, pv1.z, nv1.x, nv1.y, nv1.z, VS, DV);
+                    }
+                    pk2.t0 = pv1.w;
                 }
 #else
                 const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
@@ -682,7 +725,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
             pk.t0 = t0m;
             // kept aperture: fetch the output element early so the read-modify-write at the end of the stage is latency-free
             float2 yold0 = make_float2(0.f, 0.f), yold1 = make_float2(0.f, 0.f);
-            if constexpr (KEEP != 0) {
+            if constexpr (KEEP == 1 || KEEP == 2) {
                 if (valid[0]) yold0 = a.y[pix[0] + (uint64_t)outer * a.I];
                 if (valid[1]) yold1 = a.y[pix[1] + (uint64_t)outer * a.I];
             }
@@ -726,7 +769,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
             if (hdr.x == ST_ALL_FAST) {
                 // every trace FAST with a single window: fully unrolled, branch-free
 #if QUPS_SOFF4
-                const uint4 *so4p = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(hblk) + 64);
+                const uint4 *so4p = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(hblk) + kHdrTab);
                 uint4 so4 = make_uint4(0u, 0u, 0u, 0u);
 #endif
 #pragma unroll
@@ -738,7 +781,9 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                     const uint32_t so = (uint32_t)dsc[j].x;
 #endif
                     if constexpr (kInnerTx) pk.t0 = t0_of(j);
-                    if constexpr (!kWeighted) {
+                    if constexpr (kCF) {   // receive j & 7 of the group, first / second transmit of the stage
+                        fast_pair2<INTERP, LUT>(j < 8 ? pk : pk2, dr[j & 7], so, so, b0[j & 7], b1[j & 7]);
+                    } else if constexpr (!kWeighted) {
                         fast_pair2<INTERP, LUT>(pk, dr[j], so, so, sa0, sa1);
                     } else { // a .* interp1(...): sample into temporaries, then one weighted accumulate per pixel
                         float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
@@ -760,31 +805,38 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                 for (int j = 0; j < kNT; ++j) {
                     const int4 d = dsc[j];
                     if (d.y == TR_SKIP) continue;
-                    const float2 drj = drl[j];
+                    const float2 drj = drl[kCF ? (j & 7) : j];
                     float t0j = t0m;
                     if constexpr (kInnerTx) { neg0 = drj.x < 0.f; neg1 = drj.y < 0.f; t0j = t0_of(j); pk.t0 = t0j; }
+                    const Pack2 &pkj = (kCF && j >= 8) ? pk2 : pk;
+                    if constexpr (kCF) { neg0 = pkj.dv.x < 0.f; neg1 = pkj.dv.y < 0.f; t0j = pkj.t0; }
                     const uint32_t so0 = (uint32_t)(neg0 ? d.x : d.z), so1 = (uint32_t)(neg1 ? d.x : d.z);
                     float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
                     if (d.y == TR_FAST) {
-                        fast_pair2<INTERP, LUT>(pk, drj, so0, so1, t0, t1);
+                        fast_pair2<INTERP, LUT>(pkj, drj, so0, so1, t0, t1);
                     } else {
-                        const uint32_t n = kInnerTx ? outer : nt * kNT + j, mm = kInnerTx ? nt * kNT + j : outer;
+                        const uint32_t n = kInnerTx ? outer : (kCF ? nt * 8 + (j & 7) : nt * kNT + j);
+                        const uint32_t mm = kInnerTx ? nt * kNT + j : (kCF ? 2 * outer + (j >> 3) : outer);
                         const uint64_t nm = a.tpose ? ((uint64_t)mm + (uint64_t)n * a.M) : ((uint64_t)n + (uint64_t)mm * a.N);
-                        const float xq0 = sample_pos(pk.dv.x, drj.x, cinv, t0j, fs);
-                        const float xq1 = sample_pos(pk.dv.y, drj.y, cinv, t0j, fs);
+                        const float xq0 = sample_pos(pkj.dv.x, drj.x, cinv, t0j, fs);
+                        const float xq1 = sample_pos(pkj.dv.y, drj.y, cinv, t0j, fs);
                         // an EDGE trace crosses the end of the data somewhere in the TILE; most warps of the tile are
                         // still entirely interior (-> packed fast path) or entirely outside (-> contribute 0)
                         const bool in2 = interior<INTERP>(xq0, Tf) && interior<INTERP>(xq1, Tf);
                         const bool out2 = !(xq0 >= 1.0f && xq0 <= Tf) && !(xq1 >= 1.0f && xq1 <= Tf);
                         if (d.y == TR_EDGE && __all_sync(0xffffffffu, in2)) {
-                            fast_pair2<INTERP, LUT>(pk, drj, so0, so1, t0, t1);
+                            fast_pair2<INTERP, LUT>(pkj, drj, so0, so1, t0, t1);
                         } else if (d.y == TR_EDGE && __all_sync(0xffffffffu, out2)) {
                             continue;
                         } else {
                             rare_pair2<INTERP>(a.x + nm * a.T, a.T, d.y, xq0, xq1, so0, so1, t0, t1);
                         }
                     }
-                    if constexpr (!kWeighted) {
+                    if constexpr (kCF) {   // rolled loop: the receive slot is picked by predicated adds (static register indices)
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            if ((j & 7) == r) { b0[r].x += t0.x; b0[r].y += t0.y; b1[r].x += t1.x; b1[r].y += t1.y; }
+                    } else if constexpr (!kWeighted) {
                         sa0.x += t0.x; sa0.y += t0.y; sa1.x += t1.x; sa1.y += t1.y;
                     } else {
                         const float2 w = apw2(j);
@@ -794,7 +846,9 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                 }
             }
             } // live
-            if constexpr (KEEP != 0) { // y(:, outer) += stage sum; this CTA is the only writer of its pixels
+            if constexpr (kCF) {
+                // nothing per stage: the per-receive sums are folded when the receive group changes
+            } else if constexpr (KEEP != 0) { // y(:, outer) += stage sum; this CTA is the only writer of its pixels
                 if (valid[0]) a.y[pix[0] + (uint64_t)outer * a.I] = make_float2(yold0.x + sa0.x, yold0.y + sa0.y);
                 if (valid[1]) a.y[pix[1] + (uint64_t)outer * a.I] = make_float2(yold1.x + sa1.x, yold1.y + sa1.y);
             } else if constexpr (FUSED != 0) { // the transmit weight is constant over the stage: one multiply per pixel
@@ -815,7 +869,11 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                 acc0.x *= wr; acc0.y *= wr; acc1.x *= wr; acc1.y *= wr;
             }
         }
-        if constexpr (KEEP != 0) {
+        if constexpr (kCF) {   // partial image and partial power of this receive range; das_cf_reduce_kernel finishes
+            cf_fold();
+            if (valid[0]) { a.part[(uint64_t)split * a.I + pix[0]] = acc0; a.partP[(uint64_t)split * a.I + pix[0]] = accP0; }
+            if (valid[1]) { a.part[(uint64_t)split * a.I + pix[1]] = acc1; a.partP[(uint64_t)split * a.I + pix[1]] = accP1; }
+        } else if constexpr (KEEP != 0) {
             // nothing left to write: every stage updated y in place
         } else if (a.nsplit > 1) { // partial image of this receive range; das_reduce_kernel sums the splits in order
             if (valid[0]) a.part[(uint64_t)split * a.I + pix[0]] = acc0;
@@ -843,9 +901,10 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
         const int Ti = (int)a.T;
         uint32_t it = 0;
         // inner tiles: 16 receives (16 transmits when kInnerTx); outer index: transmit m (receive n when kInnerTx)
-        const uint32_t n_inner = kInnerTx ? a.M : a.N, n_outer = kInnerTx ? a.N : a.M;
+        // coherence mode: inner tile = 8 receives, outer index = a PAIR of transmits; lane l stages receive (l & 7) of transmit (l >> 3)
+        const uint32_t n_inner = kInnerTx ? a.M : a.N, n_outer = kInnerTx ? a.N : (kCF ? (a.M + 1) / 2 : a.M);
         for (uint32_t nt = nt0; nt < nt1; ++nt) {
-            const uint32_t il = nt * kNT + lane;
+            const uint32_t il = kCF ? nt * 8 + (lane & 7) : nt * kNT + lane;
             const bool has = (lane < kNT) && (il < n_inner);
             // tile-level bounds of the inner path length (and of t0 when the inner traces are transmits): one conservative
             // skip test per outer index, 32 outer indices per pass
@@ -870,9 +929,21 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                         xl = sample_pos(rlo_t, o2f(s_drmin[ml]), cinv, t0hi_t, fs);
                         xh = sample_pos(rhi_t, o2f(s_drmax[ml]), cinv, t0lo_t, fs);
                     } else {
+                        if constexpr (kCF) { // the pair of transmits 2 ml, 2 ml + 1: keep the stage if either can reach the data
+                            const uint32_t ma = 2 * ml, mb = min(2 * ml + 1, a.M - 1);
+                            const float ta = __ldg(a.Pv4 + 4 * ma + 3), tb = __ldg(a.Pv4 + 4 * mb + 3);
+                            const float xla = sample_pos(o2f(min(s_dvnmin[ma], s_dvpmin[ma])), rlo_t, cinv, ta, fs);
+                            const float xha = sample_pos(o2f(max(s_dvnmax[ma], s_dvpmax[ma])), rhi_t, cinv, ta, fs);
+                            const float xlb = sample_pos(o2f(min(s_dvnmin[mb], s_dvpmin[mb])), rlo_t, cinv, tb, fs);
+                            const float xhb = sample_pos(o2f(max(s_dvnmax[mb], s_dvpmax[mb])), rhi_t, cinv, tb, fs);
+                            const bool ska = (xla <= xha) && (xha < 1.0f || xla > Tf), skb = (xlb <= xhb) && (xhb < 1.0f || xlb > Tf);
+                            xl = (ska && skb) ? 2.0f * Tf : 1.0f;   // both out of range -> (xl > Tf) below skips the pair
+                            xh = (ska && skb) ? 3.0f * Tf : Tf;
+                        } else {
                         const float t0l = LUT ? 0.f : __ldg(a.Pv4 + 4 * ml + 3);
                         xl = sample_pos(o2f(min(s_dvnmin[ml], s_dvpmin[ml])), rlo_t, cinv, t0l, fs);
                         xh = sample_pos(o2f(max(s_dvnmax[ml], s_dvpmax[ml])), rhi_t, cinv, t0l, fs);
+                        }
                     }
                     skip = cinv_ok && (xl <= xh) && (xh < 1.0f || xl > Tf);
                     if constexpr (FUSED != 0) skip = skip || (s_txany[ml] == 0); // no pixel of the tile uses this transmit
@@ -883,13 +954,13 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                     todo &= todo - 1;
                     if (nprod > 1 && (it % nprod) != pw) { ++it; continue; } // another producer warp's stage
                     // this lane's trace: (receive n, transmit m)
-                    const uint32_t m = kInnerTx ? il : outer, n = kInnerTx ? outer : il;
+                    const uint32_t m = kInnerTx ? il : (kCF ? 2 * outer + (lane >> 3) : outer), n = kInnerTx ? outer : il;
                     const uint32_t s = it % a.stages, ph = (it / a.stages) & 1;
                     int flag = TR_SKIP;
                     // up to two windows per trace: [0] single window / dv < 0 cluster, [1] dv >= 0 cluster
                     uint32_t bytes[2] = {0u, 0u}, soff[2] = {0u, 0u}, dst[2] = {0u, 0u};
                     const float2 *src[2] = {nullptr, nullptr};
-                    if (has) {
+                    if (has && (!kCF || m < a.M)) {   // (coherence mode: an odd transmit count leaves the last pair half empty)
                         const float t0m = LUT ? 0.f : __ldg(a.Pv4 + 4 * m + 3);
                         const int nmin = s_dvnmin[m], nmax = s_dvnmax[m], pmin = s_dvpmin[m], pmax = s_dvpmax[m];
                         const float rlo = o2f(s_drmin[n]), rhi = o2f(s_drmax[n]); // receive path-length bounds of this trace
@@ -967,27 +1038,44 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
                     int sgn = 0;
 #if QUPS_HDRGEO
                     float4 gA = make_float4(0.f, 0.f, 0.f, 0.f), gB = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 gA1 = make_float4(0.f, 0.f, 0.f, 0.f), gB1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    // uniform sign of dv over the tile: the positive cluster also holds dv == 0 (sign(0) = 0, where dv = 0 and
+                    // not |Pi - Pv|), so "+1" needs its minimum strictly positive
+                    auto tile_sign = [&](uint32_t mm) -> int {
+                        const int nmin_ = s_dvnmin[mm], nmax_ = s_dvnmax[mm], pmin_ = s_dvpmin[mm], pmax_ = s_dvpmax[mm];
+                        if (nmin_ > nmax_ && pmin_ <= pmax_ && o2f(pmin_) > 0.f) return 1;
+                        if (pmin_ > pmax_ && nmin_ <= nmax_) return -1;
+                        return 0;
+                    };
                     if constexpr (LUT) {
                         // nothing: the consumers read their delays from the tables
                     } else if constexpr (kInnerTx) {
                         gA = make_float4(__ldg(a.Pr + 3 * outer), __ldg(a.Pr + 3 * outer + 1), __ldg(a.Pr + 3 * outer + 2), 0.f);
+                    } else if constexpr (kCF) {
+                        const uint32_t ma = 2 * outer, mb = 2 * outer + 1;
+                        gA = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + ma);
+                        gB = make_float4(__ldg(a.Nv + 3 * ma), __ldg(a.Nv + 3 * ma + 1), __ldg(a.Nv + 3 * ma + 2), 0.f);
+                        int s1 = 0;
+                        if (mb < a.M) {
+                            gA1 = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + mb);
+                            gB1 = make_float4(__ldg(a.Nv + 3 * mb), __ldg(a.Nv + 3 * mb + 1), __ldg(a.Nv + 3 * mb + 2), 0.f);
+                            s1 = tile_sign(mb);
+                        }
+                        sgn = (tile_sign(ma) + 1) | ((s1 + 1) << 2);
                     } else {
                         gA = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + outer);
                         gB = make_float4(__ldg(a.Nv + 3 * outer), __ldg(a.Nv + 3 * outer + 1), __ldg(a.Nv + 3 * outer + 2), 0.f);
-                        // uniform sign of dv over the tile: the positive cluster also holds dv == 0 (sign(0) = 0, where dv = 0 and
-                        // not |Pi - Pv|), so "+1" needs its minimum strictly positive
-                        const int nmin_ = s_dvnmin[outer], nmax_ = s_dvnmax[outer], pmin_ = s_dvpmin[outer], pmax_ = s_dvpmax[outer];
-                        if (nmin_ > nmax_ && pmin_ <= pmax_ && o2f(pmin_) > 0.f) sgn = 1;
-                        else if (pmin_ > pmax_ && nmin_ <= nmax_) sgn = -1;
+                        sgn = tile_sign(outer);
                     }
 #endif
                     mbar_wait(bar_empty + 8 * s, ph ^ 1); // slot free (first lap passes immediately)
                     if (lane < kNT) desc[s * kNT + lane] = make_int4((int)soff[0], flag, (int)soff[1], 0);
-                    if (lane < kNT) reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(stage_hdr(s)) + 64)[lane] = soff[0];
+                    if (lane < kNT) reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(stage_hdr(s)) + kHdrTab)[lane] = soff[0];
                     if (lane == 0) {
 #if QUPS_HDRGEO
                         reinterpret_cast<float4 *>(stage_hdr(s))[1] = gA;
                         reinterpret_cast<float4 *>(stage_hdr(s))[2] = gB;
+                        if constexpr (kCF) { reinterpret_cast<float4 *>(stage_hdr(s))[3] = gA1; reinterpret_cast<float4 *>(stage_hdr(s))[4] = gB1; }
 #endif
                         stage_hdr(s)[0] = make_int4(all_fast ? ST_ALL_FAST : ST_MIXED, (int)outer, (int)nt, sgn);
                     }
@@ -1080,6 +1168,22 @@ __global__ void __launch_bounds__(256) das_reduce_kernel(float2 *y, const float2
     }
 }
 
+// coherence mode: sums the receive-split partial images and powers in split order, y = S, cf = |S|^2 / P / N   (kern/cohfac.m)
+__global__ void __launch_bounds__(256) das_cf_reduce_kernel(float2 *y, float *cf, const float2 *part, const float *partP, uint64_t I,
+                                                            uint32_t nsplit, float N) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < I; i += (uint64_t)gridDim.x * blockDim.x) {
+        float2 acc = make_float2(0.f, 0.f);
+        float pw = 0.f;
+        for (uint32_t s = 0; s < nsplit; ++s) {
+            const float2 v = part[(uint64_t)s * I + i];
+            acc.x += v.x; acc.y += v.y;
+            pw += partP[(uint64_t)s * I + i];
+        }
+        y[i] = acc;
+        cf[i] = (acc.x * acc.x + acc.y * acc.y) / pw / N;   // 0 / 0 = NaN where no receive contributes, as the reference
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------
 static size_t tiled_smem_bytes(uint32_t N, uint32_t M, uint32_t wmax, int fused = 0, uint32_t stages = kStages) {
     size_t head = kBarBytes + (size_t)kHdrBytes * kStages + sizeof(int4) * kStages * kNT + sizeof(int) * ((fused ? 5 : 4) * (size_t)M + (fused ? 3 : 2) * (size_t)N);
@@ -1091,6 +1195,7 @@ TiledPlan das_tiled_plan(const DasArgs<float> &a, int dtype_in, int dtype_out) {
     TiledPlan p{0, ""};
     if (dtype_in != 0 || dtype_out != 0) { p.why = "tiled path is fp32 only"; return p; }
     if (a.keep_rx && a.keep_tx) { p.why = "tiled path keeps at most one aperture"; return p; }
+    if (a.cohfac && (a.keep_rx || a.keep_tx || a.S > 0 || a.fused || a.lut_tn || a.accumulate || !a.cf)) { p.why = "coherence mode: plain weights, no kept aperture"; return p; }
     if ((a.keep_rx || a.keep_tx) && (a.S > 0 || a.fused)) { p.why = "tiled path: kept apertures take no apodization"; return p; }
     if (a.S > 2 || (a.S > 0 && !a.apod_real)) { p.why = "tiled path takes at most two REAL apodization arrays"; return p; }
     if (a.fused && a.S > 1) { p.why = "tiled path: closed-form apodization combines with at most one apodization array"; return p; }
@@ -1123,8 +1228,9 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     t.total_elems = a.T * a.N * a.M;
     const bool lut = a.lut_tn != nullptr;   // table-driven delays (wsinterpd2 canonical form): no geometry arrays at all
     t.tn = a.lut_tn; t.tm = a.lut_tm; t.wscal = a.lut_w; t.wcplx = a.lut_wcplx;
-    const int keep = a.keep_tx ? 1 : (a.keep_rx ? 2 : 0);
-    t.numNT = ((keep == 2 ? t.M : t.N) + kNT - 1) / kNT; // inner tiles: receives, or transmits when the receive dimension is kept
+    const int keep = a.cohfac ? 3 : (a.keep_tx ? 1 : (a.keep_rx ? 2 : 0));
+    // inner tiles: 16 receives; 16 transmits when the receive dimension is kept; 8 receives in coherence mode
+    t.numNT = keep == 3 ? (t.N + 7) / 8 : ((keep == 2 ? t.M : t.N) + kNT - 1) / kNT;
     // axis assignment: lanes along I2 (the slow axis of a ZXY ScanCartesian, src/ScanCartesian.m:11) when
     // it is wide enough, rows along I1; overridable for experiments (QUPS_B200_LANE_AXIS=1|2)
     int lane_axis = (a.I2 >= 8) ? 2 : 1;
@@ -1235,7 +1341,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     const int ip = a.interp < 0 ? 0 : (a.interp > 2 ? 2 : a.interp);
 #define QUPS_PICK(I_, N_, F_, K_) if (ip == I_ && a.S == N_ && fused == F_ && keep == K_) kern = das_tiled_kernel<I_, N_, F_, K_>;
 #define QUPS_PICK_I(I_) QUPS_PICK(I_, 0, 0, 0) QUPS_PICK(I_, 1, 0, 0) QUPS_PICK(I_, 2, 0, 0) QUPS_PICK(I_, 0, 1, 0) QUPS_PICK(I_, 1, 1, 0) \
-                        QUPS_PICK(I_, 0, 2, 0) QUPS_PICK(I_, 1, 2, 0) QUPS_PICK(I_, 0, 0, 1) QUPS_PICK(I_, 0, 0, 2)
+                        QUPS_PICK(I_, 0, 2, 0) QUPS_PICK(I_, 1, 2, 0) QUPS_PICK(I_, 0, 0, 1) QUPS_PICK(I_, 0, 0, 2) QUPS_PICK(I_, 0, 0, 3)
     QUPS_PICK_I(0) QUPS_PICK_I(1) QUPS_PICK_I(2)
 #undef QUPS_PICK_I
 #undef QUPS_PICK
@@ -1275,7 +1381,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     // receive ranges (nsplit 3, 5, 6 of 16 tiles) made stragglers.  So: the smallest DIVISOR of the receive-tile count that
     // gives at least `waves_target` waves of CTAs, else one receive tile per CTA.
     // (with a handful of transmits phase 0 is cheap anyway and the extra launch is not: config C1, one plane wave, 39 -> 69 us)
-    const bool can_bounds = !lut && fused == 0 && keep == 0 && t.M >= 16 && !getenv("QUPS_B200_NOBOUNDS");
+    const bool can_bounds = !lut && fused == 0 && (keep == 0 || keep == 3) && t.M >= 16 && !getenv("QUPS_B200_NOBOUNDS");
     if (can_bounds) {
         const double slots = (double)(wmax > 256 ? 1 : QUPS_MINBLOCKS) * sms;
         double waves_target = 48.0; // C2 on one GPU, same box: 12 / 24 / 48 waves = 65.12 / 64.82 / 64.40 ms (end to end 71.98 / 71.98 / 71.25)
@@ -1287,10 +1393,10 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
             if ((double)tiles * d >= waves_target * slots) break;
         }
     }
-    if (keep) nsplit = 1;                             // kept apertures: each CTA is the only writer of its pixels
+    if (keep == 1 || keep == 2) nsplit = 1;           // kept apertures: each CTA is the only writer of its pixels
     if (nsplit < 1) nsplit = 1;
     if (const char *e2 = getenv("QUPS_B200_NSPLIT")) { int v = atoi(e2); if (v >= 1 && (uint32_t)v <= t.numNT) nsplit = (uint32_t)v; }
-    if (keep) nsplit = 1;
+    if (keep == 1 || keep == 2) nsplit = 1;
     if (tiles * nsplit > 0x7fffffffull) nsplit = 1;
     t.nsplit = nsplit;
     // measured at C2 (8-way split): DRAM reads 22.6 -> 2.60 GB per launch (compulsory: 1.07 GB), writes 1.24 -> 0.46 GB, time
@@ -1301,11 +1407,16 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     if (const char *e3 = getenv("QUPS_B200_TILE_REV")) t.rev = atoi(e3) != 0;
     t.I = a.I;
     t.part = nullptr;
-    if (nsplit > 1) {
+    t.partP = nullptr;
+    if (nsplit > 1 || keep == 3) {
         e = ws_alloc((void **)&t.part, sizeof(float2) * a.I * nsplit, st);
         if (e != cudaSuccess) return (int)e;
     }
-    if (keep && !t.accumulate) { // every stage adds into y(:, n | m)
+    if (keep == 3) {
+        e = ws_alloc((void **)&t.partP, sizeof(float) * a.I * nsplit, st);
+        if (e != cudaSuccess) { ws_free(t.part, st); return (int)e; }
+    }
+    if ((keep == 1 || keep == 2) && !t.accumulate) { // every stage adds into y(:, n | m)
         e = cudaMemsetAsync(t.y, 0, sizeof(float2) * a.I * (keep == 1 ? a.M : a.N), st);
         if (e != cudaSuccess) return (int)e;
     }
@@ -1339,7 +1450,16 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
         cudaMemcpyToSymbol(g_stats, z, sizeof(z));
     }
 #endif
-    if (nsplit > 1) {
+    if (keep == 3) {
+        if (e == cudaSuccess) {
+            const uint64_t g = (a.I + 255) / 256;
+            das_cf_reduce_kernel<<<(unsigned)(g < 4096 ? g : 4096), 256, 0, st>>>(t.y, a.cf, t.part, t.partP, a.I, nsplit, (float)a.N);
+            count_launch();
+            e = cudaGetLastError();
+        }
+        ws_free(t.partP, st);
+        ws_free(t.part, st);
+    } else if (nsplit > 1) {
         if (e == cudaSuccess) {
             const uint64_t g = (a.I + 255) / 256;
             das_reduce_kernel<<<(unsigned)(g < 4096 ? g : 4096), 256, 0, st>>>(t.y, t.part, a.I, nsplit, t.accumulate);

@@ -691,6 +691,44 @@ int qups_convd(const qups_convd_params *p, void *z, const void *x, const void *y
     return 0;
 }
 
+int qups_das_cohfac(const qups_das_params *p, void *y, void *cf, const void *Pi, const void *Pr, const void *Pv4, const void *Nv,
+                    const void *cinv, const void *x, qups_stream_t stream) {
+    g_err[0] = 0;
+    if (int rc = validate(p, false)) return rc;
+    if (p->dtype != QUPS_F32) return fail(QUPS_ERR_UNSUPPORTED, "das_cohfac: dtype must be F32");
+    if (p->S != 0 || (p->flag & (QUPS_FLAG_KEEP_RX | QUPS_FLAG_KEEP_TX)) || p->fmod != 0.0 || (p->F > 1) || p->accumulate)
+        return fail(QUPS_ERR_UNSUPPORTED, "das_cohfac: plain weights only (S = 0, no kept aperture, fmod = 0, F = 1)");
+    const uint64_t I = p->I1 * p->I2 * p->I3;
+    if (I == 0) return 0;
+    if (!y || !cf || !Pi || !Pr || !Pv4 || !Nv || !cinv || !x) return fail(QUPS_ERR_INVALID, "NULL array argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t cst[6] = {0, 0, 0, 0, 0, 0};
+    DasArgs<float> a;
+    fill_args<float>(a, p, Pi, Pr, Pv4, Nv, nullptr, cinv, cst, 1, nullptr);
+    a.x = x; a.y = y;
+    a.cohfac = 1; a.cf = (float *)cf;
+    if (a.N != 0 && a.M != 0 && p->path != QUPS_PATH_GENERIC && das_tiled_plan(a, 0, 0).eligible) {
+        g_last_das = "das_tiled";
+        if (int e = launch_das_tiled(a, st)) return cuda_fail(e, "das_tiled (coherence mode)");
+        return 0;
+    }
+    // outside the staged envelope: the reference's own sequence — keep_rx cube, cohfac along the receive dimension, sum
+    float2 *cube = nullptr;
+    cudaError_t ce = ws_alloc((void **)&cube, sizeof(float2) * I * (p->N ? p->N : 1), st);
+    if (ce != cudaSuccess) return fail(QUPS_ERR_ALLOC, "das_cohfac: ws_alloc(%llu): %s", (unsigned long long)(sizeof(float2) * I * p->N), cudaGetErrorString(ce));
+    qups_das_params q = *p;
+    q.flag |= QUPS_FLAG_KEEP_RX;
+    int rc = das_impl(&q, cube, Pi, Pr, Pv4, Nv, nullptr, cinv, cst, x, st);
+    if (rc == 0) {
+        qups_aperture_params ap{};
+        ap.struct_size = sizeof(ap); ap.dtype = QUPS_F32; ap.op = QUPS_APD_COHFAC; ap.C = I; ap.A = p->N; ap.S = 1; ap.gamma = 1.0;
+        if (int e = launch_aperture(ap, cf, nullptr, cube, nullptr, st)) rc = cuda_fail(e, "cohfac");
+    }
+    if (rc == 0) rc = das_impl(p, y, Pi, Pr, Pv4, Nv, nullptr, cinv, cst, x, st);
+    ws_free(cube, st);
+    return rc;
+}
+
 int qups_pwznxcorr(const qups_xcorr_params *p, void *y, const void *x, const void *x0, const void *w, const int32_t *lags,
                    qups_stream_t stream) {
     g_err[0] = 0;

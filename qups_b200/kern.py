@@ -166,13 +166,15 @@ class FusedApod:
 def das_spec(fun, Pi, Pr, Pv, Nv, x, t0, fs=None, c=1540.0, *varargin, _path=_lib.PATH_AUTO, _y_f32=False):
     """Specialised delay-and-sum beamformer — mirror of ``kern/das_spec.m:1``.
 
-    fun in {'DAS','SYN','MUL','BF','delays'}; options (strings, as the reference :113-148):
+    fun in {'DAS','SYN','MUL','BF','delays'} — plus 'DAS+cohfac' (not a reference fun: the sequence
+    ``b = das_spec('SYN', ...); y = sum(b, 4); r = cohfac(b, 4)`` of kern/cohfac.m as ONE call that never materialises the I x N
+    cube; returns (y, r)); options (strings, as the reference :113-148):
     'plane-waves' | 'virtual-source' | 'diverging-waves' | 'focused-waves' |
     'input-precision', {'single','double','halfT'} | 'device', d | 'interp', method |
     'apod', A (repeatable) | 'modulation', fmod | 'transpose', tf.
     Returns I1 x I2 x I3 x [1|N] x [1|M] x F x ...
     """
-    if fun not in ("DAS", "SYN", "BF", "MUL", "delays"):
+    if fun not in ("DAS", "SYN", "BF", "MUL", "delays", "DAS+cohfac"):
         raise ValueError("Invalid beamformer.")
     VS, DV, interp_type, apod, fmod, tpose, device = True, False, "linear", [], 0.0, False, -1
     fused = None  # closed-form apodization (FusedApod) passed through 'apod' 
@@ -331,6 +333,14 @@ def das_spec(fun, Pi, Pr, Pv, Nv, x, t0, fs=None, c=1540.0, *varargin, _path=_li
                 yb = torch.empty((F * Om * On * I, 2), dtype=torch.float16, device=dev)
             else:
                 yb = torch.empty(F * Om * On * I, dtype=torch.complex64 if prec != "double" else torch.complex128, device=dev)
+            if fun == "DAS+cohfac":
+                if fused is not None or S != 0 or prec != "single" or F != 1:
+                    raise _lib.QupsError(-3, "DAS+cohfac: plain weights only (no apodization, single precision, one frame)")
+                cf = torch.empty(I, dtype=torch.float32, device=dev)
+                _lib.check(L.qups_das_cohfac(C.byref(p), _ptr(yb), _ptr(cf), _ptr(dPi), _ptr(dPr), _ptr(dPv), _ptr(dNv), _ptr(dC),
+                                             _ptr(dX), st))
+                y, r = _from_colmajor(yb, Isz), _from_colmajor(cf, Isz)
+                return (np.asfortranarray(y.cpu().numpy()), np.asfortranarray(r.cpu().numpy())) if numpy_out else (y, r)
             if fused is not None:
                 keep = []
                 fz = fused._struct(dev, keep)
