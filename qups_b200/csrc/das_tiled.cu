@@ -1,5 +1,5 @@
-// das_tiled.cu — the hot DAS kernel for sm_100a (B200): fp32 complex data, both
-// apertures summed (fun = 'DAS'), scalar sound speed, no apodization arrays.
+// das_tiled.cu — the hot DAS kernel for sm_100a (B200): fp32 complex data, scalar sound speed (the modes beyond the plain
+// sum over both apertures are listed below).
 //
 // What it replaces: the serial M x N loop of src/bf.cu:96-139 (one thread per
 // pixel, two sqrt + 64-bit stride math + 1/2/4 dependent global gathers per
@@ -24,6 +24,15 @@
 //     the slot, or has a NaN bound take a slow path with the full interp1 edge
 //     semantics straight from global memory; traces entirely outside the data
 //     are skipped (they contribute exactly 0).
+//
+//   * work decomposition: grid = tiles x nsplit (receive-axis split, partial images summed in split order by
+//     das_reduce_kernel: deterministic).  For split launches the per-tile path-length bounds come from das_bounds_kernel
+//     (once per tile instead of once per CTA), the split is the smallest divisor of the receive-tile count giving ~48
+//     waves of CTAs, and the CTAs are ordered split-major so that the CTAs resident at one time read windows of the same
+//     1/nsplit of the cube (DRAM reads at C2: 2.6 GB per launch, tile-major 22.6 GB).
+//   * modes (template parameters): real apodization arrays (NAP), closed-form apodization (FUSED), kept apertures MUL / SYN
+//     (KEEP = 1 / 2), table-driven delays for bfDAS (LUT), and the coherence mode (KEEP = 3: DAS image + coherence factor of
+//     the per-receive images in one pass, 8 receives x 2 transmits per stage).
 //
 // Numerics: the sample position xq uses the canonical individually-rounded
 // sequence (common.cuh), so tap indices are bit-identical to the oracle; the
