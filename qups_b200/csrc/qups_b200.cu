@@ -594,7 +594,9 @@ int qups_das_host(const qups_das_params *p, void *y, const void *Pi, const void 
                 // host (55 GB/s vs 4 transmits/ms at C2), so chunk c + 1 lands before chunk c is done, and still does when 8
                 // ranks share the host's memory bandwidth.  (Round 1 started at 32 transmits because short launches lost
                 // > 8 % to the per-CTA bounds pass; with das_bounds_kernel and the finer receive split they no longer do.)
-                double sz = 8.0;
+                // short transmit shards (a rank of a multi-GPU job: the upload is the contended resource) start smaller still —
+                // 8 GPUs, M = 32 per rank, end to end per step: first chunk 32 (no pipeline) 15.2 ms, 16 -> 13.7, 8 -> 13.1, 4 -> 12.4
+                double sz = p->M >= 128 ? 8.0 : 4.0;
                 const char *eg = getenv("QUPS_B200_CHUNK_GROWTH");
                 // measured, C2 through this call on one GPU (device-resident kernel 64.4 ms): chunks 32 x1.3 -> 71.3 ms, 8 x2 -> 69.3,
                 // 8 x3 -> 68.5 (fewer launches; every launch recomputes dr per receive tile and has its own tail).  Short
