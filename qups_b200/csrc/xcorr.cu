@@ -56,12 +56,42 @@ template <typename R> __device__ __forceinline__ R msum_r(const R *in, const R *
     return a;
 }
 
+// Three consecutive outputs at once: out[j] = sum_k w[k] * in[i0 + j + c - k], j = 0..2.  The window slides one sample per tap, so
+// every tap costs ONE new input load (+ the weight) for three outputs instead of two loads per output; the taps are still added
+// in the oracle's order k = 0 .. W-1.  Three, not four: lanes 3 elements apart hit distinct banks (3 is coprime to 16 and 32),
+// lanes 4 apart would be a 4-way conflict and give the saving back.
+template <typename R, typename V>
+__device__ __forceinline__ void msum3_c(const V *in, const R *w, int i0, int W, int c, V (&out)[3]) {
+    const V *p = in + i0 + c;
+    V a1 = p[1], a2 = p[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { out[j].x = R(0); out[j].y = R(0); }
+    for (int k = 0; k < W; ++k) {
+        const R wk = w[k];
+        const V a0 = p[-k];
+        out[0].x += wk * a0.x; out[0].y += wk * a0.y;
+        out[1].x += wk * a1.x; out[1].y += wk * a1.y;
+        out[2].x += wk * a2.x; out[2].y += wk * a2.y;
+        a2 = a1; a1 = a0;
+    }
+}
+template <typename R> __device__ __forceinline__ void msum3_r(const R *in, const R *w, int i0, int W, int c, R (&out)[3]) {
+    const R *p = in + i0 + c;
+    R a1 = p[1], a2 = p[2];
+    out[0] = out[1] = out[2] = R(0);
+    for (int k = 0; k < W; ++k) {
+        const R wk = w[k], a0 = p[-k];
+        out[0] += wk * a0; out[1] += wk * a1; out[2] += wk * a2;
+        a2 = a1; a1 = a0;
+    }
+}
+
 template <typename R>
 __global__ void __launch_bounds__(kThreads) pwznxcorr_kernel(const XcorrArgs a) {
     using V = typename cx<R>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     const int W = (int)a.W, h = W - 1, c = W / 2;
-    const int nA = kTile + 4 * h, nB = kTile + 2 * h;
+    const int nA = kTile + 4 * h + 4, nB = kTile + 2 * h + 4;   // + 4: the 3-wide groups read up to 2 elements past the last window
     // layout: w[W] | xa[nA] (left trace, tile -2h .. +2h) | xb[nA] (shifted right trace) | xlz[nB] | xrz[nB] | q[nB] | pl[nB] pr[nB] | xln[kTile]
     R *sw = reinterpret_cast<R *>(smem);
     V *xa = reinterpret_cast<V *>(smem + (((size_t)W * sizeof(R) + 15) & ~(size_t)15));
@@ -87,19 +117,30 @@ __global__ void __launch_bounds__(kThreads) pwznxcorr_kernel(const XcorrArgs a) 
     }
     __syncthreads();
     // xlz = xl - kernfun(xl) on [t0 - h, t0 + kTile + h), zero outside [0, Tp)   (kern/pwznxcorr.m:225)
-    for (int i = tid; i < nB; i += kThreads) {
-        const int s = t0 - h + i;
-        V v; v.x = R(0); v.y = R(0);
-        if (s >= 0 && s < Tp) {
-            v = xa[i + h];
-            if (a.zero) { const V m = msum_c<R, V>(xa, sw, i + h, W, c); v.x -= m.x; v.y -= m.y; }
+    const int nBv = kTile + 2 * h;                       // valid entries of the nB-arrays
+    for (int i0 = 3 * tid; i0 < nBv; i0 += 3 * kThreads) {
+        V m[3];
+        if (a.zero) msum3_c<R, V>(xa, sw, i0 + h, W, c, m);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int i = i0 + j, s = t0 - h + i;
+            V v; v.x = R(0); v.y = R(0);
+            if (s >= 0 && s < Tp) {
+                v = xa[i + h];
+                if (a.zero) { v.x -= m[j].x; v.y -= m[j].y; }
+            }
+            xlz[i] = v;                                   // (i < nB: the 4 pad entries absorb the last group's overrun)
+            pl[i] = v.x * v.x + v.y * v.y;
         }
-        xlz[i] = v;
-        pl[i] = v.x * v.x + v.y * v.y;
     }
     __syncthreads();
     if (a.norm)
-        for (int i = tid; i < kTile; i += kThreads) xln[i] = msum_r<R>(pl, sw, i + h, W, c); // :226
+        for (int i0 = 3 * tid; i0 < kTile; i0 += 3 * kThreads) { // :226
+            R m[3];
+            msum3_r<R>(pl, sw, i0 + h, W, c, m);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) if (i0 + j < kTile) xln[i0 + j] = m[j];
+        }
     // right trace source
     auto right = [&](int s) -> V { // xr[s], s in [0, Tp): zero in the appended padding
         V v; v.x = R(0); v.y = R(0);
@@ -131,30 +172,41 @@ __global__ void __launch_bounds__(kThreads) pwznxcorr_kernel(const XcorrArgs a) 
             xb[i] = v;
         }
         __syncthreads();
-        for (int i = tid; i < nB; i += kThreads) { // xrz_l, the product and the power (:240-246, :251)
-            const int s = t0 - h + i;
-            V v; v.x = R(0); v.y = R(0);
-            if (s >= 0 && s < Tp) {
-                v = xb[i + h];
-                if (a.zero) { const V m = msum_c<R, V>(xb, sw, i + h, W, c); v.x -= m.x; v.y -= m.y; }
+        for (int i0 = 3 * tid; i0 < nBv; i0 += 3 * kThreads) { // xrz_l, the product and the power (:240-246, :251)
+            V m[3];
+            if (a.zero) msum3_c<R, V>(xb, sw, i0 + h, W, c, m);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int i = i0 + j, s = t0 - h + i;
+                V v; v.x = R(0); v.y = R(0);
+                if (s >= 0 && s < Tp) {
+                    v = xb[i + h];
+                    if (a.zero) { v.x -= m[j].x; v.y -= m[j].y; }
+                }
+                xrz[i] = v;
+                const V u = xlz[i];
+                V p; p.x = u.x * v.x - u.y * v.y; p.y = u.x * v.y + u.y * v.x;
+                q[i] = p;
+                pr[i] = v.x * v.x + v.y * v.y;
             }
-            xrz[i] = v;
-            const V u = xlz[i];
-            V p; p.x = u.x * v.x - u.y * v.y; p.y = u.x * v.y + u.y * v.x;
-            q[i] = p;
-            pr[i] = v.x * v.x + v.y * v.y;
         }
         __syncthreads();
-        for (int i = tid; i < kTile; i += kThreads) {
-            const int t = t0 + i;
-            if (t >= T) break;
-            V yv = msum_c<R, V>(q, sw, i + h, W, c);
-            if (a.norm) {
-                const R xrn = msum_r<R>(pr, sw, i + h, W, c);
-                const R r = sqrt(xln[i]) * sqrt(xrn); // .* sqrt(Wn), Wn = 1 (:258)
-                yv.x /= r; yv.y /= r;
+        for (int i0 = 3 * tid; i0 < kTile; i0 += 3 * kThreads) {
+            if (t0 + i0 >= T) break;
+            V yv[3];
+            R xrn[3] = {R(1), R(1), R(1)};
+            msum3_c<R, V>(q, sw, i0 + h, W, c, yv);
+            if (a.norm) msum3_r<R>(pr, sw, i0 + h, W, c, xrn);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int i = i0 + j, t = t0 + i;
+                if (t >= T || i >= kTile) break;
+                if (a.norm) {
+                    const R r = sqrt(xln[i]) * sqrt(xrn[j]); // .* sqrt(Wn), Wn = 1 (:258)
+                    yv[j].x /= r; yv[j].y /= r;
+                }
+                reinterpret_cast<V *>(a.y)[(((uint64_t)li * a.F + f) * a.Nout + n) * a.T + t] = yv[j];
             }
-            reinterpret_cast<V *>(a.y)[(((uint64_t)li * a.F + f) * a.Nout + n) * a.T + t] = yv;
         }
     }
 }
@@ -162,7 +214,7 @@ __global__ void __launch_bounds__(kThreads) pwznxcorr_kernel(const XcorrArgs a) 
 
 size_t xcorr_smem_bytes(uint32_t W, int dbl) {
     const size_t R = dbl ? 8 : 4, V = 2 * R, h = W - 1;
-    const size_t nA = kTile + 4 * h, nB = kTile + 2 * h;
+    const size_t nA = kTile + 4 * h + 4, nB = kTile + 2 * h + 4;
     return (((size_t)W * R + 15) & ~(size_t)15) + 2 * nA * V + 3 * nB * V + 2 * nB * R + kTile * R;
 }
 
