@@ -271,10 +271,25 @@ constexpr int kNO = 11;         // step (4): consecutive outputs per thread (odd
 constexpr int kPB = 8;          // step (4): kernel taps per register block
 constexpr int kConvPad = 12;    // zero samples after every train row (>= kNO - 1)
 
-template <typename DOUT>
+// Path-length tables (TAB): r_rx depends on (scatterer, receive element) and r_tx on (scatterer, transmit element) only, but a
+// trace CTA needs them for ITS (n, m): N x M CTAs each recomputing two fp64 square roots and a division per scatterer was most
+// of the per-entry work at C5 scale.  greens_dist_kernel evaluates {r, 1 / max(r, R0)} once per (element, scatterer) with the
+// same fp64 operations; the tables ((N + M) E I x 16 B = 82 MB at C5) stay in L2 and a CTA reads its two rows coalesced.
+__global__ void __launch_bounds__(256) greens_dist_kernel(double2 *out, const float *Pi, const float *Pe, uint64_t I, uint64_t cnt, double R0) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= I * cnt) return;
+    const uint64_t i = g % I, k = g / I;
+    const double sx = Pi[3 * i], sy = Pi[3 * i + 1], sz = Pi[3 * i + 2];
+    const double ax = sx - Pe[3 * k], ay = sy - Pe[3 * k + 1], az = sz - Pe[3 * k + 2];
+    const double r = sqrt(ax * ax + ay * ay + az * az);
+    out[g] = make_double2(r, R0 != 0.0 ? 1.0 / fmax(r, R0) : 1.0);
+}
+
+template <typename DOUT, bool TAB>
 __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<float> p, DOUT *y, const float *Pi, const float *amp,
                                                                 const float *Pr, const float *Pv, const float2 *kern, int blk,
-                                                                double c0, double fs, double t0s, double R0) {
+                                                                double c0, double fs, double t0s, double R0,
+                                                                const double2 *Trx, const double2 *Ttx) {
     extern __shared__ __align__(16) unsigned char gsm[];
     const int K = (int)p.T;
     const int W = blk + K - 1;                                   // train window: tau in [tau0, tau0 + W)
@@ -317,15 +332,23 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
             for (int q = tid; q < kW * kCNB; q += kGThreads) s_cnt[q] = 0;
             // ---- (1) per-entry arrival, attenuation, interpolation weights --------------------------------------
             for (int q = tid; q < cnt; q += kGThreads) {
-                const uint64_t e = e0 + q, i = e / EE, em = (e % EE) / p.E, en = e % p.E;
-                const double sx = Pi[3 * i], sy = Pi[3 * i + 1], sz = Pi[3 * i + 2];
-                const float *pr = Pr + 3 * (n + p.N * en), *pv = Pv + 3 * (m + p.M * em);
-                const double ax = sx - pr[0], ay = sy - pr[1], az = sz - pr[2];
-                const double bx = sx - pv[0], by = sy - pv[1], bz = sz - pv[2];
-                const double r_rx = sqrt(ax * ax + ay * ay + az * az), r_tx = sqrt(bx * bx + by * by + bz * bz);
-                double att = (double)amp[i];
-                if (R0 != 0.0) att /= (fmax(r_rx, R0) * fmax(r_tx, R0));
-                const double c = fma(r_rx + r_tx, fs_c0, t0s);       // arrival (r_rx + r_tx) / c0 * fs + t0s: kernel position of sample t is d = t - c
+                const uint64_t e = e0 + q;
+                uint64_t i = e, em = 0, en = 0;
+                if (EE != 1) { i = e / EE; em = (e % EE) / p.E; en = e % p.E; }   // (E = 1 skips the 64-bit divisions)
+                double r_rx, r_tx, att = (double)amp[i];
+                if constexpr (TAB) {
+                    const double2 a = Trx[(n + p.N * en) * p.I + i], b = Ttx[(m + p.M * em) * p.I + i];
+                    r_rx = a.x; r_tx = b.x;
+                    att *= a.y * b.y;   // amp / (max(r_rx, R0) max(r_tx, R0)) to 2 ulp of fp64
+                } else {
+                    const double sx = Pi[3 * i], sy = Pi[3 * i + 1], sz = Pi[3 * i + 2];
+                    const float *pr = Pr + 3 * (n + p.N * en), *pv = Pv + 3 * (m + p.M * em);
+                    const double ax = sx - pr[0], ay = sy - pr[1], az = sz - pr[2];
+                    const double bx = sx - pv[0], by = sy - pv[1], bz = sz - pv[2];
+                    r_rx = sqrt(ax * ax + ay * ay + az * az); r_tx = sqrt(bx * bx + by * by + bz * bz);
+                    if (R0 != 0.0) att /= (fmax(r_rx, R0) * fmax(r_tx, R0));
+                }
+                const double c = fma(r_rx + r_tx, fs_c0, t0s);      // arrival (r_rx + r_tx) / c0 * fs + t0s: kernel position of sample t is d = t - c
                 const double cc = ceil(c);
                 const float f = (float)(cc - c), a = (float)att;
                 float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -396,12 +419,29 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
             // O(entries) instead of O(positions x bucket size) (round 1: every train position scanned its whole bucket for
             // the entries arriving exactly there — 35 % of the kernel's instructions).  A bucket is owned by one thread, its
             // entries are in stable (scatterer-index) order, so the sum per position is deterministic.
-            for (int bk = tid; bk < nbk; bk += kGThreads) {
+            // The five trains of a bucket are independent: work item = (train j, bucket), so all 8 warps walk (one thread per
+            // bucket adding into all five left 4 of the 8 warps idle: 24 % of the stall samples sat on the barrier after it);
+            // the next entry is fetched before the current read-modify-write, so the walk costs one shared-memory round
+            // trip per entry instead of four dependent ones.
+            for (int item = tid; item < 5 * nbk; item += kGThreads) {
+                const int j = item / nbk, bk = item - j * nbk;
+                const float *wsrc = (j < 4) ? reinterpret_cast<const float *>(s_w) + j : s_z;
+                const int wst = (j < 4) ? 4 : 1;
+                float *tr = trains + j * Wp;
+                int e = s_start[bk];
                 const int e_hi = s_start[bk + 1];
-                for (int e = s_start[bk]; e < e_hi; ++e) {
-                    const int q = s_perm[e], r = s_ci[q];
-                    const float4 w = s_w[q];
-                    trains[r] += w.x; trains[Wp + r] += w.y; trains[2 * Wp + r] += w.z; trains[3 * Wp + r] += w.w; trains[4 * Wp + r] += s_z[q];
+                if (e < e_hi) {
+                    int q = s_perm[e], r = s_ci[q];
+                    float v = wsrc[q * wst];
+                    for (++e;; ++e) {
+                        const bool more = e < e_hi;
+                        int rn = 0;
+                        float vn = 0.f;
+                        if (more) { const int qn = s_perm[e]; rn = s_ci[qn]; vn = wsrc[qn * wst]; }
+                        tr[r] += v;
+                        if (!more) break;
+                        r = rn; v = vn;
+                    }
                 }
             }
         }
@@ -516,10 +556,26 @@ int launch_greens(const qups_greens_params &p, void *y, const void *Pi, const vo
         if (conv) {
             const int blk = (int)(p.S <= (uint64_t)kCBlock ? ((p.S + 255) / 256) * 256 : 2048);
             const size_t smem = greens_conv_smem((int)p.T, blk);
-            cudaError_t e = cudaFuncSetAttribute(greens_conv_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(greens_conv_kernel<float2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            greens_conv_kernel<float2><<<grid, block, smem, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a, (const float *)Pr,
-                                                                  (const float *)Pv, (const float2 *)kern, blk, p.c0, p.fs, p.t0x * p.fs, p.R0);
+            // path-length tables unless they would be unreasonably large (then every CTA computes its own, as before)
+            const uint64_t trx = p.N * E * p.I, ttx = p.M * E * p.I;
+            double2 *tab = nullptr;
+            if (!getenv("QUPS_B200_GREENS_NOTAB") && (trx + ttx) * sizeof(double2) <= (4ull << 30) &&
+                ws_alloc((void **)&tab, (trx + ttx) * sizeof(double2), st) != cudaSuccess) { tab = nullptr; (void)cudaGetLastError(); }
+            if (tab) {
+                greens_dist_kernel<<<(unsigned)((trx + 255) / 256), 256, 0, st>>>(tab, (const float *)Pi, (const float *)Pr, p.I, p.N * E, p.R0);
+                greens_dist_kernel<<<(unsigned)((ttx + 255) / 256), 256, 0, st>>>(tab + trx, (const float *)Pi, (const float *)Pv, p.I, p.M * E, p.R0);
+                count_launch(2);
+                e = cudaFuncSetAttribute(greens_conv_kernel<float2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e == cudaSuccess)
+                    greens_conv_kernel<float2, true><<<grid, block, smem, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a, (const float *)Pr,
+                                                                                (const float *)Pv, (const float2 *)kern, blk, p.c0, p.fs, p.t0x * p.fs, p.R0, tab, tab + trx);
+                ws_free(tab, st);
+                if (e != cudaSuccess) return (int)e;
+            } else
+            greens_conv_kernel<float2, false><<<grid, block, smem, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a, (const float *)Pr,
+                                                                         (const float *)Pv, (const float2 *)kern, blk, p.c0, p.fs, p.t0x * p.fs, p.R0, nullptr, nullptr);
         } else if (binned)
             greens_binned_kernel<float2, float2, float><<<grid, block, 0, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a,
                                                                                 (const float *)Pr, (const float *)Pv, (const float2 *)kern);
