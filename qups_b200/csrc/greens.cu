@@ -296,9 +296,8 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
     const int Wp = (W + kConvPad + 3) & ~3;
     float2 *kx = reinterpret_cast<float2 *>(gsm);                // kx[q + 1], q = -1 .. K
     float *trains = reinterpret_cast<float *>(kx + ((K + 2 + 1) & ~1)); // 5 x Wp
-    float4 *s_w = reinterpret_cast<float4 *>(trains + 5 * Wp + ((5 * Wp) & 3 ? 4 - ((5 * Wp) & 3) : 0));
-    float *s_z = reinterpret_cast<float *>(s_w + kCChunk);
-    int *s_ci = reinterpret_cast<int *>(s_z + kCChunk);
+    float *s_w5 = trains + 5 * Wp + ((5 * Wp) & 3 ? 4 - ((5 * Wp) & 3) : 0);   // [5][kCChunk]: att * w_j(f) (j = 0..3), att if f == 0 (j = 4)
+    int *s_ci = reinterpret_cast<int *>(s_w5 + 5 * kCChunk);
     int *s_cnt = s_ci + kCChunk;                                 // [kW][kCNB]
     int *s_start = s_cnt + (kGThreads / 32) * kCNB;              // [kCNB + 1]
     unsigned short *s_perm = reinterpret_cast<unsigned short *>(s_start + kCNB + 1);
@@ -326,12 +325,24 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
     for (uint64_t sb = 0; sb < p.S; sb += (uint64_t)blk) {
         const long long tau0 = p.n0 + (long long)sb - (K - 1);
         for (int r = tid; r < 5 * Wp; r += kGThreads) trains[r] = 0.f;
+        for (int q = tid; q < kW * kCNB; q += kGThreads) s_cnt[q] = 0;
         for (uint64_t e0 = 0; e0 < total; e0 += kCChunk) {
             const int cnt = (int)((total - e0 < (uint64_t)kCChunk) ? (total - e0) : kCChunk);
-            __syncthreads();
-            for (int q = tid; q < kW * kCNB; q += kGThreads) s_cnt[q] = 0;
-            // ---- (1) per-entry arrival, attenuation, interpolation weights --------------------------------------
-            for (int q = tid; q < cnt; q += kGThreads) {
+            __syncthreads();   // the previous chunk's walk (and its reset of s_cnt) is complete
+            // Warp w owns the contiguous, ascending entry range [q0, q1) of the chunk — for step (1) AND for the counting sort,
+            // so the bucket of an entry never leaves the registers of the thread that computed it and the two steps need no
+            // barrier between them.
+            constexpr int kIt = kCChunk / (kW * 32);
+            const int per = ((cnt + kW * 32 - 1) / (kW * 32)) * 32;
+            const int q0 = warp * per, q1 = min(cnt, q0 + per);
+            int bsv[kIt];
+            unsigned mkv[kIt];
+            // ---- (1) per-entry arrival, attenuation, interpolation weights (planar in shared memory: s_w5[j][q]) -----------
+#pragma unroll
+            for (int k = 0; k < kIt; ++k) {
+                const int q = q0 + k * 32 + lane;
+                bsv[k] = -1;
+                if (q >= q1) continue;
                 const uint64_t e = e0 + q;
                 uint64_t i = e, em = 0, en = 0;
                 if (EE != 1) { i = e / EE; em = (e % EE) / p.E; en = e % p.E; }   // (E = 1 skips the 64-bit divisions)
@@ -363,81 +374,85 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
                 } else {                        // round half away from zero
                     if (f < 0.5f) w.y = 1.f; else w.z = 1.f;
                 }
-                s_w[q] = make_float4(a * w.x, a * w.y, a * w.z, a * w.w);
-                s_z[q] = (f == 0.f) ? a : 0.f;
+                s_w5[q] = a * w.x; s_w5[kCChunk + q] = a * w.y; s_w5[2 * kCChunk + q] = a * w.z; s_w5[3 * kCChunk + q] = a * w.w;
+                s_w5[4 * kCChunk + q] = (f == 0.f) ? a : 0.f;
                 const double rel = cc - (double)tau0;
-                s_ci[q] = (rel >= 0.0 && rel < (double)W && c == c) ? (int)rel : -1;
+                const int ci = (rel >= 0.0 && rel < (double)W && c == c) ? (int)rel : -1;
+                s_ci[q] = ci;
+                if (ci >= 0) bsv[k] = min(ci / kCBW, nbk - 1);
             }
-            __syncthreads();
-            // ---- (2) stable counting sort of the chunk by bucket: warp w owns a contiguous, ascending range ----
-            const int per = ((cnt + kW * 32 - 1) / (kW * 32)) * 32;
-            const int q0 = warp * per, q1 = min(cnt, q0 + per);
-            for (int qb = q0; qb < q1; qb += 32) {
-                const int q = qb + lane;
-                int b = -1;
-                if (q < q1 && s_ci[q] >= 0) b = min(s_ci[q] / kCBW, nbk - 1);
+            // ---- (2) stable counting sort of the chunk by bucket (warp-ordered ranks, no atomics) ------------------------
+            // one match_any per 32 entries: its mask serves the count pass here and the scatter pass below
+#pragma unroll
+            for (int k = 0; k < kIt; ++k) {
+                const int b = bsv[k];
                 const unsigned mk = __match_any_sync(0xffffffffu, b);
+                mkv[k] = mk;
                 if (b >= 0 && lane == (__ffs((int)mk) - 1)) s_cnt[warp * kCNB + b] += __popc(mk);
                 __syncwarp();
             }
             __syncthreads();
-            if (tid < nbk) {
-                int tot = 0;
-                for (int w = 0; w < kW; ++w) tot += s_cnt[w * kCNB + tid];
-                s_start[tid + 1] = tot;
-            }
-            __syncthreads();
+            // bucket starts + per-warp offsets, one warp: lane l owns buckets 5 l .. 5 l + 4 (register prefix), one warp scan
             if (warp == 0) {
-                int carry = 0;
-                for (int b0 = 0; b0 < nbk; b0 += 32) {
-                    const int b = b0 + lane;
-                    int v = (b < nbk) ? s_start[b + 1] : 0, incl = v;
-                    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-                    if (b < nbk) s_start[b + 1] = carry + incl;
-                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                constexpr int kPer = (kCNB + 31) / 32;
+                int tot[kPer], sum = 0;
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) {
+                    const int b = lane * kPer + k;
+                    int t = 0;
+                    if (b < nbk)
+                        for (int w = 0; w < kW; ++w) t += s_cnt[w * kCNB + b];
+                    tot[k] = t;
+                    sum += t;
                 }
-                if (lane == 0) s_start[0] = 0;
+                int incl = sum;
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+                int run = incl - sum;
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) {
+                    const int b = lane * kPer + k;
+                    if (b < nbk) {
+                        s_start[b] = run;
+                        int r2 = run;
+                        for (int w = 0; w < kW; ++w) { const int c = s_cnt[w * kCNB + b]; s_cnt[w * kCNB + b] = r2; r2 += c; }
+                    }
+                    run += tot[k];
+                }
+                if (lane == 31) s_start[nbk] = incl;
             }
             __syncthreads();
-            if (tid < nbk) {
-                int run = s_start[tid];
-                for (int w = 0; w < kW; ++w) { const int c = s_cnt[w * kCNB + tid]; s_cnt[w * kCNB + tid] = run; run += c; }
-            }
-            __syncthreads();
-            for (int qb = q0; qb < q1; qb += 32) {
-                const int q = qb + lane;
-                int b = -1;
-                if (q < q1 && s_ci[q] >= 0) b = min(s_ci[q] / kCBW, nbk - 1);
-                const unsigned mk = __match_any_sync(0xffffffffu, b);
-                if (b >= 0) s_perm[s_cnt[warp * kCNB + b] + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)q;
+#pragma unroll
+            for (int k = 0; k < kIt; ++k) {
+                const int b = bsv[k];
+                const unsigned mk = mkv[k];
+                if (b >= 0) s_perm[s_cnt[warp * kCNB + b] + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)(q0 + k * 32 + lane);
                 __syncwarp();
                 if (b >= 0 && lane == (__ffs((int)mk) - 1)) s_cnt[warp * kCNB + b] += __popc(mk);
                 __syncwarp();
             }
             __syncthreads();
-            // ---- (3) one thread per bucket walks ITS entries in sorted order and adds each into its train position -------
+            for (int q = tid; q < kW * kCNB; q += kGThreads) s_cnt[q] = 0;   // for the next chunk (the walk does not use it)
+            // ---- (3) walk the buckets in sorted order and add each entry into its train position --------------------------
             // O(entries) instead of O(positions x bucket size) (round 1: every train position scanned its whole bucket for
-            // the entries arriving exactly there — 35 % of the kernel's instructions).  A bucket is owned by one thread, its
-            // entries are in stable (scatterer-index) order, so the sum per position is deterministic.
-            // The five trains of a bucket are independent: work item = (train j, bucket), so all 8 warps walk (one thread per
-            // bucket adding into all five left 4 of the 8 warps idle: 24 % of the stall samples sat on the barrier after it);
-            // the next entry is fetched before the current read-modify-write, so the walk costs one shared-memory round
-            // trip per entry instead of four dependent ones.
+            // the entries arriving exactly there — 35 % of the kernel's instructions).  Work item = (train j, bucket): a train
+            // position is owned by one thread and its entries arrive in stable (scatterer-index) order, so the sum per position is
+            // deterministic; all 8 warps walk (one thread per bucket adding into all five trains left 4 of them idle: 24 % of the
+            // stall samples sat on the barrier after it); the next entry is fetched before the current read-modify-write, so the
+            // walk costs one shared-memory round trip per entry instead of four dependent ones.
             for (int item = tid; item < 5 * nbk; item += kGThreads) {
                 const int j = item / nbk, bk = item - j * nbk;
-                const float *wsrc = (j < 4) ? reinterpret_cast<const float *>(s_w) + j : s_z;
-                const int wst = (j < 4) ? 4 : 1;
+                const float *wsrc = s_w5 + j * kCChunk;
                 float *tr = trains + j * Wp;
                 int e = s_start[bk];
                 const int e_hi = s_start[bk + 1];
                 if (e < e_hi) {
                     int q = s_perm[e], r = s_ci[q];
-                    float v = wsrc[q * wst];
+                    float v = wsrc[q];
                     for (++e;; ++e) {
                         const bool more = e < e_hi;
                         int rn = 0;
                         float vn = 0.f;
-                        if (more) { const int qn = s_perm[e]; rn = s_ci[qn]; vn = wsrc[qn * wst]; }
+                        if (more) { const int qn = s_perm[e]; rn = s_ci[qn]; vn = wsrc[qn]; }
                         tr[r] += v;
                         if (!more) break;
                         r = rn; v = vn;
