@@ -219,7 +219,8 @@ def wsinterpd2_inm(x, t1, t2, w=None, *, sum_n=True, sum_m=True, interp="linear"
     return y
 
 
-def greens(ps, amp, pn, pv, kern, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, interp="cubic", dtype=np.float32):
+def greens(ps, amp, pn, pv, kern, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, interp="cubic", dtype=np.float32, E=1):
+    """E > 1: pn / pv hold E sub-element positions per element, column n + N*en (3 x N x E flattened, src/UltrasoundSystem.m:785-790)."""
     rdt = np.dtype(dtype)
     cdt = np.complex64 if rdt == np.float32 else np.complex128
     ps, pn, pv = (_f(np.asarray(a, rdt).reshape(3, -1), rdt) for a in (ps, pn, pv))
@@ -227,7 +228,7 @@ def greens(ps, amp, pn, pv, kern, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, interp=
     kern = _f(kern, cdt)
     A = GreensArgs()
     A.interp = INTERP[interp]
-    A.S, A.N, A.M, A.T, A.K, A.E = ps.shape[1], pn.shape[1], pv.shape[1], T, kern.shape[0], 1
+    A.S, A.N, A.M, A.T, A.K, A.E = ps.shape[1], pn.shape[1] // E, pv.shape[1] // E, T, kern.shape[0], E
     A.n0 = int(n0)
     A.c0, A.fs, A.fsr, A.R0, A.wv_t0 = float(c0), float(fs), float(fsr), float(R0), float(wv_t0)
     A.ps, A.amp, A.pn, A.pv, A.kern = map(_ptr, (ps, amp, pn, pv, kern))

@@ -263,11 +263,26 @@ __global__ void __launch_bounds__(kGThreads) greens_binned_kernel(const GreensDe
 // of rounding noise (the fp32 oracle has it too, the reference's own CPU-vs-GPU bar is 1e-3, test/SimTest.m:327-357);
 // with fp64 delays this kernel matches the fp64 oracle to ~2e-6 instead.  greens_kernel / greens_binned_kernel keep
 // the oracle's fp32 sequence (QUPS_B200_GREENS=simple|binned).
-constexpr int kCChunk = 1024;   // scatterer entries staged per pass
+#ifndef QUPS_GREENS_THREADS
+#define QUPS_GREENS_THREADS 256
+#endif
+#ifndef QUPS_GREENS_CHUNK
+#define QUPS_GREENS_CHUNK 1536
+#endif
+#ifndef QUPS_GREENS_NO
+#define QUPS_GREENS_NO 11
+#endif
+#ifdef QUPS_GREENS_MINB
+#define QUPS_GREENS_BOUNDS __launch_bounds__(QUPS_GREENS_THREADS, QUPS_GREENS_MINB)
+#else
+#define QUPS_GREENS_BOUNDS __launch_bounds__(QUPS_GREENS_THREADS)
+#endif
+constexpr int kCT = QUPS_GREENS_THREADS;   // threads per CTA of the convolution kernel
+constexpr int kCChunk = QUPS_GREENS_CHUNK; // scatterer entries staged per pass
 constexpr int kCBW = 32;        // bucket width (train positions)
 constexpr int kCNB = 136;       // max buckets: (kCBlock + K) / 32 + 1
 constexpr int kCBlock = 3072;   // output samples per train window
-constexpr int kNO = 11;         // step (4): consecutive outputs per thread (odd: conflict-free at a lane stride of kNO words)
+constexpr int kNO = QUPS_GREENS_NO;         // step (4): consecutive outputs per thread (odd: conflict-free at a lane stride of kNO words)
 constexpr int kPB = 8;          // step (4): kernel taps per register block
 constexpr int kConvPad = 12;    // zero samples after every train row (>= kNO - 1)
 
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(256) greens_dist_kernel(double2 *out, const fl
 }
 
 template <typename DOUT, bool TAB>
-__global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<float> p, DOUT *y, const float *Pi, const float *amp,
+__global__ void QUPS_GREENS_BOUNDS greens_conv_kernel(const GreensDev<float> p, DOUT *y, const float *Pi, const float *amp,
                                                                 const float *Pr, const float *Pv, const float2 *kern, int blk,
                                                                 double c0, double fs, double t0s, double R0,
                                                                 const double2 *Trx, const double2 *Ttx) {
@@ -299,16 +314,16 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
     float *s_w5 = trains + 5 * Wp + ((5 * Wp) & 3 ? 4 - ((5 * Wp) & 3) : 0);   // [5][kCChunk]: att * w_j(f) (j = 0..3), att if f == 0 (j = 4)
     int *s_ci = reinterpret_cast<int *>(s_w5 + 5 * kCChunk);
     int *s_cnt = s_ci + kCChunk;                                 // [kW][kCNB]
-    int *s_start = s_cnt + (kGThreads / 32) * kCNB;              // [kCNB + 1]
+    int *s_start = s_cnt + (kCT / 32) * kCNB;              // [kCNB + 1]
     unsigned short *s_perm = reinterpret_cast<unsigned short *>(s_start + kCNB + 1);
-    constexpr int kW = kGThreads / 32;
+    constexpr int kW = kCT / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t n = blockIdx.x, m = blockIdx.y;
     const uint64_t EE = p.E * p.E, total = p.I * EE;
     DOUT *yt = y + p.S * (n + p.N * m);
 
     // extended kernel (interp1's end padding for cubic: v(0) = 3v(1)-3v(2)+v(3), v(T+1) = 3v(T)-3v(T-1)+v(T-2))
-    for (int q = tid; q < K; q += kGThreads) kx[q + 1] = __ldg(kern + q);
+    for (int q = tid; q < K; q += kCT) kx[q + 1] = __ldg(kern + q);
     if (tid == 0) {
         float2 lo = make_float2(0.f, 0.f), hi = lo;
         if (p.interp == 2 && K >= 3) {
@@ -324,15 +339,15 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
 
     for (uint64_t sb = 0; sb < p.S; sb += (uint64_t)blk) {
         const long long tau0 = p.n0 + (long long)sb - (K - 1);
-        for (int r = tid; r < 5 * Wp; r += kGThreads) trains[r] = 0.f;
-        for (int q = tid; q < kW * kCNB; q += kGThreads) s_cnt[q] = 0;
+        for (int r = tid; r < 5 * Wp; r += kCT) trains[r] = 0.f;
+        for (int q = tid; q < kW * kCNB; q += kCT) s_cnt[q] = 0;
         for (uint64_t e0 = 0; e0 < total; e0 += kCChunk) {
             const int cnt = (int)((total - e0 < (uint64_t)kCChunk) ? (total - e0) : kCChunk);
             __syncthreads();   // the previous chunk's walk (and its reset of s_cnt) is complete
             // Warp w owns the contiguous, ascending entry range [q0, q1) of the chunk — for step (1) AND for the counting sort,
             // so the bucket of an entry never leaves the registers of the thread that computed it and the two steps need no
             // barrier between them.
-            constexpr int kIt = kCChunk / (kW * 32);
+            constexpr int kIt = (kCChunk + kW * 32 - 1) / (kW * 32);
             const int per = ((cnt + kW * 32 - 1) / (kW * 32)) * 32;
             const int q0 = warp * per, q1 = min(cnt, q0 + per);
             int bsv[kIt];
@@ -431,7 +446,7 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
                 __syncwarp();
             }
             __syncthreads();
-            for (int q = tid; q < kW * kCNB; q += kGThreads) s_cnt[q] = 0;   // for the next chunk (the walk does not use it)
+            for (int q = tid; q < kW * kCNB; q += kCT) s_cnt[q] = 0;   // for the next chunk (the walk does not use it)
             // ---- (3) walk the buckets in sorted order and add each entry into its train position --------------------------
             // O(entries) instead of O(positions x bucket size) (round 1: every train position scanned its whole bucket for
             // the entries arriving exactly there — 35 % of the kernel's instructions).  Work item = (train j, bucket): a train
@@ -439,7 +454,7 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
             // deterministic; all 8 warps walk (one thread per bucket adding into all five trains left 4 of them idle: 24 % of the
             // stall samples sat on the barrier after it); the next entry is fetched before the current read-modify-write, so the
             // walk costs one shared-memory round trip per entry instead of four dependent ones.
-            for (int item = tid; item < 5 * nbk; item += kGThreads) {
+            for (int item = tid; item < 5 * nbk; item += kCT) {
                 const int j = item / nbk, bk = item - j * nbk;
                 const float *wsrc = s_w5 + j * kCChunk;
                 float *tr = trains + j * Wp;
@@ -466,7 +481,7 @@ __global__ void __launch_bounds__(kGThreads) greens_conv_kernel(const GreensDev<
         // of kPB: per train the kNO + kPB - 1 samples the block touches are loaded once and feed kNO x kPB products —
         // 7 FMA per shared load instead of the 2 of a one-output-at-a-time loop.  The rows carry kConvPad zeros so the window
         // of the last outputs needs no range test.
-        for (int task = tid; task * kNO < blk; task += kGThreads) {
+        for (int task = tid; task * kNO < blk; task += kCT) {
             const int o0 = task * kNO;
             float2 acc[kNO];
 #pragma unroll
@@ -523,7 +538,7 @@ static size_t greens_conv_smem(int K, int blk) {
     size_t b = sizeof(float2) * ((K + 2 + 1) & ~1);
     b += sizeof(float) * (5 * Wp + 4);
     b += sizeof(float4) * kCChunk + sizeof(float) * kCChunk + sizeof(int) * kCChunk;
-    b += sizeof(int) * ((kGThreads / 32) * kCNB + kCNB + 1);
+    b += sizeof(int) * ((kCT / 32) * kCNB + kCNB + 1);
     b += sizeof(unsigned short) * kCChunk + 16;
     return b;
 }
@@ -584,12 +599,12 @@ int launch_greens(const qups_greens_params &p, void *y, const void *Pi, const vo
                 count_launch(2);
                 e = cudaFuncSetAttribute(greens_conv_kernel<float2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e == cudaSuccess)
-                    greens_conv_kernel<float2, true><<<grid, block, smem, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a, (const float *)Pr,
+                    greens_conv_kernel<float2, true><<<grid, kCT, smem, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a, (const float *)Pr,
                                                                                 (const float *)Pv, (const float2 *)kern, blk, p.c0, p.fs, p.t0x * p.fs, p.R0, tab, tab + trx);
                 ws_free(tab, st);
                 if (e != cudaSuccess) return (int)e;
             } else
-            greens_conv_kernel<float2, false><<<grid, block, smem, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a, (const float *)Pr,
+            greens_conv_kernel<float2, false><<<grid, kCT, smem, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a, (const float *)Pr,
                                                                          (const float *)Pv, (const float2 *)kern, blk, p.c0, p.fs, p.t0x * p.fs, p.R0, nullptr, nullptr);
         } else if (binned)
             greens_binned_kernel<float2, float2, float><<<grid, block, 0, st>>>(d, (float2 *)y, (const float *)Pi, (const float *)a,

@@ -562,10 +562,11 @@ def refocus(chd: "ChannelData", seq: "Sequence", tx: np.ndarray, method="tikhono
 
 
 def greens_raw(ps, amp, pn, pv, kern_s, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, interp="cubic", device=None,
-               dtype=np.float32):
+               dtype=np.float32, E=1):
     """Direct call of the qups_greens C ABI; returns a CUDA tensor of logical shape (T, N, M).
     dtype=np.float16 selects the half variant (greensh, src/greens.cu:113-122): half2 waveform in, half2 traces out
-    (returned widened to complex64), fp32 geometry."""
+    (returned widened to complex64), fp32 geometry.  E > 1: pn / pv hold E sub-element positions per element, column
+    n + N*en (3 x N x E flattened; element sub-divisions, src/UltrasoundSystem.m:785-790)."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     half = np.dtype(dtype) == np.float16
     rt = torch.float32 if np.dtype(dtype) in (np.float32, np.float16) else torch.float64
@@ -574,7 +575,7 @@ def greens_raw(ps, amp, pn, pv, kern_s, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, i
     dPs, dPn, dPv = col(ps), col(pn), col(pv)
     dA = torch.from_numpy(np.asarray(amp, np.float64)).to(dev, rt).contiguous()
     dK = torch.from_numpy(np.asarray(kern_s, np.complex128)).to(dev, ct).contiguous()
-    N, M = dPn.shape[0], dPv.shape[0]
+    N, M = dPn.shape[0] // E, dPv.shape[0] // E
     y = torch.empty((M, N, T), dtype=ct, device=dev)
     if half:
         dK = torch.view_as_real(dK).to(torch.float16).contiguous()
@@ -582,7 +583,7 @@ def greens_raw(ps, amp, pn, pv, kern_s, n0, T, fs, c0, wv_t0, fsr=1.0, R0=0.0, i
     p = GreensParams()
     p.struct_size = C.sizeof(GreensParams)
     p.dtype = _lib.F16 if half else (_lib.F32 if rt == torch.float32 else _lib.F64)
-    p.I, p.S, p.T, p.N, p.M, p.E = dPs.shape[0], T, dK.shape[0], N, M, 1
+    p.I, p.S, p.T, p.N, p.M, p.E = dPs.shape[0], T, dK.shape[0], N, M, E
     p.n0, p.interp = int(n0), _lib.INTERP[interp]
     p.t0x, p.fs, p.fsr, p.c0, p.R0 = float(wv_t0), float(fs), float(fsr), float(c0), float(R0)
     vp = lambda t_: C.c_void_p(t_.data_ptr())

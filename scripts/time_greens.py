@@ -8,6 +8,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--N", type=int, default=256)
 ap.add_argument("--S", type=int, default=10000)
 ap.add_argument("--modes", default="conv,binned")
+ap.add_argument("--reps", type=int, default=2)
 a = ap.parse_args()
 P = synth.config_c2(64, 64, a.N, a.N, 2048)
 rng = np.random.default_rng(1)
@@ -23,13 +24,13 @@ out = {}
 for mode in a.modes.split(","):
     os.environ["QUPS_B200_GREENS"] = mode
     ts = []
-    for _ in range(2):
+    for _ in range(a.reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         x = ultrasound.greens_raw(ps, amp, pn, pn, kern, n0, T, P.fs, P.c0, wt0, 1.0, 2e-4, "cubic")
         e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     out[mode] = x
-    print(f"greens[{mode:6s}] {min(ts):9.2f} ms   {a.S*a.N*a.N/min(ts)/1e6:8.2f} G scatterer-rx-tx/s   out {x.numel()*8/1e9:.2f} GB", flush=True)
+    print(f"greens[{mode:6s}] {min(ts):9.2f} ms (median {sorted(ts)[len(ts)//2]:.2f})   {a.S*a.N*a.N/min(ts)/1e6:8.2f} G scatterer-rx-tx/s   out {x.numel()*8/1e9:.2f} GB", flush=True)
 if len(out) == 2:
     k = list(out)
     d = (out[k[0]] - out[k[1]]).abs().max() / out[k[1]].abs().max()

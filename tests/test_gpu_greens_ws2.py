@@ -199,3 +199,41 @@ def test_greens_convolution_kernel_exact_cases(oracle_c, interp, monkeypatch):
     assert rel_linf(got, ref) < 3e-6, rel_linf(got, ref)
     z = np.abs(ref) == 0
     assert np.all(got[z] == 0)                         # exact zeros outside every scatterer's support
+
+
+@pytest.mark.parametrize("mode", ["conv", "binned", "simple"])
+def test_greens_sub_elements(oracle_c, mode, monkeypatch):
+    """Element sub-divisions (E sub-elements per element, entry order scatterer -> em -> en, src/UltrasoundSystem.m:785-790):
+    every kernel variant against the oracle, and against the sum of the E x E single-sub-element simulations."""
+    from qups_b200 import synth
+    from qups_b200.ultrasound import greens_raw
+    fs, fc, c0 = 20e6, 5e6, 1500.0
+    kern, wt0, _ = synth.greens_kernel(fc, 0.6, fs)
+    N, M, E = 6, 4, 2
+    base_n, base_v = synth.linear_array(N, 0.3e-3), synth.linear_array(M, 0.4e-3)
+    off = np.array([[-0.07e-3, 0.07e-3], [0.0, 0.0], [0.0, 0.0]])           # sub-element offsets along x
+    pn = np.concatenate([base_n + off[:, [e]] for e in range(E)], axis=1)   # column n + N*en
+    pv = np.concatenate([base_v + off[:, [e]] for e in range(E)], axis=1)
+    rng = np.random.default_rng(11)
+    S = 700                                                                  # 2800 entries: three chunks of the staged kernels
+    ps = np.stack([rng.uniform(-3e-3, 3e-3, S), rng.uniform(-1e-3, 1e-3, S), rng.uniform(3e-3, 12e-3, S)], 0)
+    amp = rng.standard_normal(S)
+    n0, T, R0 = 40, 700, 3e-4
+    monkeypatch.setenv("QUPS_B200_GREENS", mode)
+    got = greens_raw(ps, amp, pn, pv, kern, n0, T, fs, c0, wt0, 1.0, R0, "cubic", E=E).cpu().numpy()
+    assert got.shape == (T, N, M)
+    ref = oracle_c.greens(ps, amp, pn, pv, kern, n0, T, fs, c0, wt0, 1.0, R0, "cubic", E=E)
+    assert np.abs(ref).max() > 0
+    if mode == "simple":
+        assert np.array_equal(got, ref)
+    elif mode == "binned":
+        assert rel_linf(got, ref) < 2e-6, rel_linf(got, ref)
+    else:   # fp64 arrivals: the fp64 oracle on the fp32-rounded inputs is the arbiter (see test_greens_bitexact_vs_oracle)
+        f32 = np.float32
+        ref64 = oracle_c.greens(ps.astype(f32), amp.astype(f32), pn.astype(f32), pv.astype(f32), kern, n0, T, fs, c0, wt0, 1.0, R0,
+                                "cubic", dtype=np.float64, E=E)
+        assert rel_linf(got, ref64) < 5e-6, rel_linf(got, ref64)
+        assert rel_linf(got, ref) < 1e-3
+    parts = sum(greens_raw(ps, amp, pn[:, en * N:(en + 1) * N], pv[:, em * M:(em + 1) * M], kern, n0, T, fs, c0, wt0, 1.0, R0,
+                           "cubic").cpu().numpy().astype(np.complex128) for em in range(E) for en in range(E))
+    assert rel_linf(got, parts) < 5e-6, rel_linf(got, parts)
