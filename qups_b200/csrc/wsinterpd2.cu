@@ -28,6 +28,9 @@ struct Ws2Dev {
     uint64_t sw[8], sy[8], s1[8], s2[8], sx[8];
     int kept[8], nkept, summed[8], nsummed;
     uint64_t nout, nsum;
+    // the summed dims compacted (first summed dim first): extents and strides at STATIC positions, so the odometer of the
+    // term loop below reads them straight from the constant bank
+    uint64_t zn[8], zw[8], z1[8], z2[8], zx[8];
 };
 
 // table / real-weight element -> R  (the reference's half kernels take half delay tables, src/interpd.cu:451-458)
@@ -48,13 +51,22 @@ __global__ void __launch_bounds__(128) wsinterpd2_kernel(const Ws2Dev p, DOUT *y
         bw += j * p.sw[d]; by += j * p.sy[d]; b1 += j * p.s1[d]; b2 += j * p.s2[d]; bx += j * p.sx[d];
     }
     cplx<R> acc = {R(0), R(0)};
+    // the summed sub-indices advance like an odometer (first summed dim fastest — the same term order as a div / mod decode of
+    // the linear term index, which cost two 64-bit divisions per summed dim and term)
+    uint64_t kw = bw, k1 = b1, k2 = b2, kx = bx;
+    uint64_t cnt[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cnt[q] = 0;
     for (uint64_t e = 0; e < p.nsum; ++e) {
-        uint64_t kw = bw, k1 = b1, k2 = b2, kx = bx, r2 = e;
-        for (int q = 0; q < p.nsummed; ++q) {
-            const int d = p.summed[q];
-            const uint64_t j = r2 % p.sizes[d];
-            r2 /= p.sizes[d];
-            kw += j * p.sw[d]; k1 += j * p.s1[d]; k2 += j * p.s2[d]; kx += j * p.sx[d];
+        if (e != 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q >= p.nsummed) break;
+                kw += p.zw[q]; k1 += p.z1[q]; k2 += p.z2[q]; kx += p.zx[q];
+                if (++cnt[q] < p.zn[q]) break;
+                cnt[q] = 0;
+                kw -= p.zn[q] * p.zw[q]; k1 -= p.zn[q] * p.z1[q]; k2 -= p.zn[q] * p.z2[q]; kx -= p.zn[q] * p.zx[q];
+            }
         }
         R t = ldr<R, TT>(t1, k1);
         if (p.has_t2) t = add_rn(t, ldr<R, TT>(t2, k2));
@@ -90,7 +102,10 @@ int launch_wsinterpd2(const qups_ws2_params &p, void *y, const void *w, const vo
         if (p.sizes[k] == 0) return 0; // empty
         if (p.sizes[k] == 1) continue;
         if (d.sy[k] != 0) { d.kept[d.nkept++] = k; d.nout *= p.sizes[k]; }
-        else { d.summed[d.nsummed++] = k; d.nsum *= p.sizes[k]; }
+        else {
+            d.zn[d.nsummed] = p.sizes[k]; d.zw[d.nsummed] = d.sw[k]; d.z1[d.nsummed] = d.s1[k]; d.z2[d.nsummed] = d.s2[k]; d.zx[d.nsummed] = d.sx[k];
+            d.summed[d.nsummed++] = k; d.nsum *= p.sizes[k];
+        }
     }
     // ---- fp16 call in the canonical look-up-table form: widen data / tables / weight once (exact) and take the staged fp32 path
     if (p.dtype == QUPS_F16 && t2 != nullptr && p.omega == 0.0 && p.interp >= 0 && p.interp <= 2 && !getenv("QUPS_B200_WS2_GENERIC")) {

@@ -340,3 +340,46 @@ def test_full_size_kept_aperture_and_fused_mask_properties():
     assert qups_b200.last_das_kernel() == "das_generic+apod_generate"
     pick = fused.reshape(1024, 1024)[torch.from_numpy(iz).cuda(), torch.from_numpy(ix).cuda()]
     assert float((pick - genm.reshape(-1)).abs().max()) / float(genm.abs().max()) < TOL
+
+
+def test_empty_and_degenerate_shapes_through_the_c_abi(oracle_c):
+    """Empty and degenerate inputs at the boundary (the reference's sum over an empty aperture is zeros(size of the image);
+    an empty image is a no-op), and the smallest ragged grids: one pixel, one row, one column, one receive, one transmit."""
+    import ctypes as C
+    from qups_b200 import _lib
+    f32 = np.float32
+    acs = (C.c_uint64 * 6)(*([0] * 6))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def host(P, N, M, interp=_lib.CUBIC):
+        Pi = np.asfortranarray(P["Pi"].reshape(3, -1, order="F").astype(f32))
+        Pr = np.asfortranarray(P["Pr"][:, :max(N, 1)].astype(f32))
+        Mf = P["Pv"].shape[1]
+        Pv4 = np.asfortranarray(np.concatenate([P["Pv"], np.broadcast_to(np.asarray(P["t0"], float).reshape(1, -1), (1, Mf))], 0)[:, :max(M, 1)].astype(f32))
+        Nv = np.asfortranarray(P["Nv"][:, :max(M, 1)].astype(f32))
+        cinv = np.array([1.0 / f32(P["c"])], dtype=f32)
+        x = np.asfortranarray(P["x"][:, :max(N, 1), :max(M, 1)])
+        p = _lib.DasParams()
+        p.struct_size = C.sizeof(_lib.DasParams)
+        p.dtype = _lib.F32
+        p.I1, p.I2, p.I3 = P["Pi"].shape[1:]
+        p.N, p.M, p.T, p.F, p.S = N, M, P["x"].shape[0], 1, 0
+        p.flag, p.vs, p.dv = interp, 1, 0
+        p.fs = P["fs"]
+        y = np.full(P["Pi"].shape[1:], 7 + 7j, dtype=np.complex64, order="F")
+        rc = _lib.lib().qups_das_host(C.byref(p), vp(y), vp(Pi), vp(Pr), vp(Pv4), vp(Nv), None, 0, vp(cinv), 1, acs, vp(x), 0)
+        assert rc == 0, _lib.lib().qups_last_error()
+        return y
+
+    P = small_problem("FC", nz=9, nx=5, N=6, M=3, T=200)
+    assert np.all(host(P, 0, 3) == 0)      # no receives: empty sum
+    assert np.all(host(P, 6, 0) == 0)      # no transmits
+    Pe = dict(P)
+    Pe["Pi"] = P["Pi"][:, :0]              # empty image: nothing is written, the call succeeds
+    assert host(Pe, 6, 3).size == 0
+    for nz, nx, N, M in ((1, 1, 1, 1), (1, 7, 6, 3), (5, 1, 6, 3), (9, 5, 1, 3), (9, 5, 6, 1)):
+        Q = small_problem("FC", nz=nz, nx=nx, N=N, M=M, T=200)
+        ref = _ora(oracle_c, "DAS", Q, "cubic")
+        got = host(Q, N, M)
+        assert rel_linf(got.reshape(ref.shape, order="F"), ref) < TOL, (nz, nx, N, M)
+    _lib.lib().qups_host_release()
