@@ -24,7 +24,8 @@
 //                                                                               x is T x N x F, w the window weights (single/double gpuArray), x0 may be []
 //   y = qups_b200_mex('refocus',C, y0, x, Hi)                                  REFoCUS decode: C.fs, C.t0 (double, host, 1 or V values); y0 T x N x E prototype
 // where C is a scalar struct holding what the reference puts in __constant__ memory with k.setConstantMemory
-// (kern/das_spec.m:294-298): C.I1,C.I2,C.I3,C.N,C.M,C.T,C.S,C.VS,C.DV,C.flag  (+ ws2: C.T,C.interp,C.omega ;
+// (kern/das_spec.m:294-298): C.I1,C.I2,C.I3,C.N,C.M,C.T,C.S,C.VS,C.DV,C.flag  (+ optional das hints C.pitch = [dz dx], C.c0 ;
+// ws2: C.T,C.interp,C.omega ;
 // greens: C.n0,C.t0x,C.fs,C.fsr,C.c0,C.R0,C.E,C.interp).  The output is a new gpuArray of the size/type of the
 // first array argument (feval's convention for non-const pointer parameters).
 #include "mex.h"
@@ -89,6 +90,12 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         p.vs = (int32_t)fld(C, "VS", 1); p.dv = (int32_t)fld(C, "DV", 0);
         const double *fsfc = mxGetPr(prhs[11]);           /* [fs, fmod] is a host array (kern/das_spec.m:372) */
         p.fs = fsfc[0]; p.fmod = fsfc[1];
+        /* optional launcher hints (never affect results): C.pitch = [scan.dz scan.dx] (metres between neighbouring pixels along
+         * I1 / I2), C.c0 = scalar sound speed.  With them the library picks its tile shape without reading pixel positions
+         * back from the device (no host synchronisation, no pointer-keyed cache). */
+        const mxArray *pitch = mxGetField(C, 0, "pitch");
+        if (pitch && mxGetNumberOfElements(pitch) >= 2) { p.pitch_hint[0] = mxGetPr(pitch)[0]; p.pitch_hint[1] = mxGetPr(pitch)[1]; }
+        p.c_hint = fld(C, "c0", 0);
         /* [cstride, astride] arrives as a host uint64 array (MATLAB copies small arrays for feval) */
         if (!mxIsUint64(prhs[9])) mexErrMsgIdAndTxt("QUPS:b200:type", "strides must be uint64");
         const uint64_t *acs = (const uint64_t *)mxGetData(prhs[9]);
