@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(threads_of(INTERP), QUPS_MINBLOCKS) das_tiled_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
     }
-    const bool have_bounds = (FUSED == 0 && (KEEP == 0 || KEEP == 3) && LUT == 0) && a.bounds != nullptr;
+    const bool have_bounds = (FUSED == 0 && (KEEP == 0 || KEEP == 3)) && a.bounds != nullptr;
     if (have_bounds) { // the six tables are contiguous in shared memory and in the pre-pass output
         const int *src = a.bounds + (uint64_t)tile * (4 * a.M + 2 * a.N);
         for (uint32_t i = tid; i < 4 * a.M + 2 * a.N; i += kThreads) s_dvnmin[i] = __ldg(src + i);
@@ -1124,25 +1124,32 @@ __global__ void __launch_bounds__(kCW * 32) das_bounds_kernel(const TiledArgs a)
     for (uint32_t i = tid; i < a.M; i += kCW * 32) { s_dvnmin[i] = INT_MAX; s_dvnmax[i] = INT_MIN; s_dvpmin[i] = INT_MAX; s_dvpmax[i] = INT_MIN; }
     for (uint32_t i = tid; i < a.N; i += kCW * 32) { s_drmin[i] = INT_MAX; s_drmax[i] = INT_MIN; }
     __syncthreads();
-    float px[kR], py[kR], pz[kR];
+    const bool lut = a.tn != nullptr;   // table-driven delays: the path lengths are read, one cluster per transmit
+    float px[kR] = {0.f, 0.f}, py[kR] = {0.f, 0.f}, pz[kR] = {0.f, 0.f};
+    uint64_t pixr[kR];
 #pragma unroll
     for (int r = 0; r < kR; ++r) { // the same pixels (incl. the shadowing of out-of-image lanes) as the main kernel's consumers
         const uint32_t ib = tb * a.tB + ((warp / wA) * lpb + (lane / lpa)) * kR + r;
         const uint32_t ca = ia < a.IA ? ia : a.IA - 1, cb = ib < a.IB ? ib : a.IB - 1;
         const uint64_t pix = (uint64_t)ca * a.sA + (uint64_t)cb * a.sB + (uint64_t)tc * a.sC;
-        px[r] = __ldg(a.Pi + 3 * pix); py[r] = __ldg(a.Pi + 3 * pix + 1); pz[r] = __ldg(a.Pi + 3 * pix + 2);
+        pixr[r] = pix;
+        if (!lut) { px[r] = __ldg(a.Pi + 3 * pix); py[r] = __ldg(a.Pi + 3 * pix + 1); pz[r] = __ldg(a.Pi + 3 * pix + 2); }
     }
     const bool VS = a.VS, DV = a.DV;
     for (uint32_t m = 0; m < a.M; ++m) {
-        const float4 pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
-        const float nx = __ldg(a.Nv + 3 * m), ny = __ldg(a.Nv + 3 * m + 1), nz = __ldg(a.Nv + 3 * m + 2);
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        if (!lut) {
+            pv = __ldg(reinterpret_cast<const float4 *>(a.Pv4) + m);
+            nx = __ldg(a.Nv + 3 * m); ny = __ldg(a.Nv + 3 * m + 1); nz = __ldg(a.Nv + 3 * m + 2);
+        }
         int nlo = INT_MAX, nhi = INT_MIN, plo = INT_MAX, phi = INT_MIN;
 #pragma unroll
         for (int r = 0; r < kR; ++r) {
-            const float d = tx_dist(px[r], py[r], pz[r], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
+            const float d = lut ? __ldg(a.tm + (uint64_t)m * a.I + pixr[r]) : tx_dist(px[r], py[r], pz[r], pv.x, pv.y, pv.z, nx, ny, nz, VS, DV);
             const int o = f2o(d);
-            if (d < 0.f) { nlo = min(nlo, o); nhi = max(nhi, o); }
-            else         { plo = min(plo, o); phi = max(phi, o); }
+            if (!lut && d < 0.f) { nlo = min(nlo, o); nhi = max(nhi, o); }
+            else                 { plo = min(plo, o); phi = max(phi, o); }
         }
         nlo = __reduce_min_sync(0xffffffffu, nlo); nhi = __reduce_max_sync(0xffffffffu, nhi);
         plo = __reduce_min_sync(0xffffffffu, plo); phi = __reduce_max_sync(0xffffffffu, phi);
@@ -1152,10 +1159,14 @@ __global__ void __launch_bounds__(kCW * 32) das_bounds_kernel(const TiledArgs a)
         }
     }
     for (uint32_t n = 0; n < a.N; ++n) {
-        const float rx = __ldg(a.Pr + 3 * n), ry = __ldg(a.Pr + 3 * n + 1), rz = __ldg(a.Pr + 3 * n + 2);
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        if (!lut) { rx = __ldg(a.Pr + 3 * n); ry = __ldg(a.Pr + 3 * n + 1); rz = __ldg(a.Pr + 3 * n + 2); }
         int lo = INT_MAX, hi = INT_MIN;
 #pragma unroll
-        for (int r = 0; r < kR; ++r) { const int o = f2o(rx_dist(px[r], py[r], pz[r], rx, ry, rz)); lo = min(lo, o); hi = max(hi, o); }
+        for (int r = 0; r < kR; ++r) {
+            const int o = f2o(lut ? __ldg(a.tn + (uint64_t)n * a.I + pixr[r]) : rx_dist(px[r], py[r], pz[r], rx, ry, rz));
+            lo = min(lo, o); hi = max(hi, o);
+        }
         lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
         if (lane == 0) { atomicMin(&s_drmin[n], lo); atomicMax(&s_drmax[n], hi); }
     }
@@ -1390,7 +1401,7 @@ int launch_das_tiled(const DasArgs<float> &a, cudaStream_t st) {
     // receive ranges (nsplit 3, 5, 6 of 16 tiles) made stragglers.  So: the smallest DIVISOR of the receive-tile count that
     // gives at least `waves_target` waves of CTAs, else one receive tile per CTA.
     // (with a handful of transmits phase 0 is cheap anyway and the extra launch is not: config C1, one plane wave, 39 -> 69 us)
-    const bool can_bounds = !lut && fused == 0 && (keep == 0 || keep == 3) && t.M >= 16 && !getenv("QUPS_B200_NOBOUNDS");
+    const bool can_bounds = (!lut || !getenv("QUPS_B200_LUT_NOBOUNDS")) && fused == 0 && (keep == 0 || keep == 3) && t.M >= 16 && !getenv("QUPS_B200_NOBOUNDS");
     if (can_bounds) {
         const double slots = (double)(wmax > 256 ? 1 : QUPS_MINBLOCKS) * sms;
         double waves_target = 48.0; // C2 on one GPU, same box: 12 / 24 / 48 waves = 65.12 / 64.82 / 64.40 ms (end to end 71.98 / 71.98 / 71.25)
