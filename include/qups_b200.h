@@ -282,7 +282,10 @@ typedef struct {
 } qups_greens_params;
 
 /* y : out complex S x N x M ; Pi : 3 x I scatterer positions ; a : I real amplitudes ;
- * Pr : 3 x N x E ; Pv : 3 x M x E ; kern : complex T */
+ * Pr : 3 x N x E ; Pv : 3 x M x E ; kern : complex T
+ * Scratch: the default fp32 kernel (fsr == 1) takes (N + M) * E * I * 16 bytes of path-length tables from the library's
+ * stream-ordered pool for the duration of the call (82 MB at 10 k scatterers, 256 + 256 elements); above 4 GB, or if the
+ * allocation fails, every trace computes its own path lengths instead (same results to 2 ulp of fp64, slower). */
 QUPS_API int qups_greens(const qups_greens_params *p, void *y, const void *Pi, const void *a, const void *Pr, const void *Pv,
                 const void *kern, qups_stream_t stream);
 
