@@ -1,7 +1,8 @@
 """aperture_np.py — CPU restatement of the aperture-domain post-processing functions (TEST INFRASTRUCTURE ONLY; only
 tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import it).  Whole-array NumPy float64 versions of
 kern/cohfac.m, kern/dmas.m, kern/pcf.m and kern/slsc.m (native branch, kdim singleton), written as the reference's
-expressions.  `dim` is 1-based as in MATLAB.  Parity unpinned (no MATLAB here)."""
+expressions.  `dim` is 1-based as in MATLAB.  Parity unpinned against MATLAB (absent here); pinned against an independent scalar-loop
+restatement of the same reference statements in tests/test_aperture_cpu.py."""
 import numpy as np
 
 
