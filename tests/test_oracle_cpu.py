@@ -230,3 +230,25 @@ def test_interp1_cubic_equals_independent_keys_convolution_incl_ends(oracle_c):
     cr = np.stack([-u**3 + 2 * u**2 - u, 3 * u**3 - 5 * u**2 + 2, -3 * u**3 + 4 * u**2 + u, u**3 - u**2]) * 0.5
     kw = np.stack([W(u + 1), W(u), W(u - 1), W(u - 2)])
     assert np.max(np.abs(cr - kw)) < 1e-14
+
+
+def test_greens_sub_elements_sum_of_single_sub_element_simulations(oracle_c):
+    """Element sub-divisions (entry order scatterer -> em -> en, src/UltrasoundSystem.m:785-790): the E = 2 simulation is the sum
+    of the four (em, en) simulations with one sub-element each, to summation order."""
+    from qups_b200 import synth
+    fs, fc, c0 = 20e6, 5e6, 1500.0
+    kern, wt0, _ = synth.greens_kernel(fc, 0.6, fs)
+    N, M, E = 5, 3, 2
+    bn, bv = synth.linear_array(N, 0.3e-3), synth.linear_array(M, 0.4e-3)
+    off = np.array([[-0.07e-3, 0.07e-3], [0.0, 0.0], [0.0, 0.0]])
+    pn = np.concatenate([bn + off[:, [e]] for e in range(E)], axis=1)   # column n + N*en
+    pv = np.concatenate([bv + off[:, [e]] for e in range(E)], axis=1)
+    rng = np.random.default_rng(11)
+    S = 200
+    ps = np.stack([rng.uniform(-3e-3, 3e-3, S), rng.uniform(-1e-3, 1e-3, S), rng.uniform(3e-3, 12e-3, S)], 0)
+    amp = rng.standard_normal(S)
+    ref = oracle_c.greens(ps, amp, pn, pv, kern, 40, 600, fs, c0, wt0, 1.0, 3e-4, "cubic", dtype=np.float64, E=E)
+    assert ref.shape == (600, N, M) and np.abs(ref).max() > 0
+    parts = sum(oracle_c.greens(ps, amp, pn[:, en * N:(en + 1) * N], pv[:, em * M:(em + 1) * M], kern, 40, 600, fs, c0, wt0, 1.0,
+                                3e-4, "cubic", dtype=np.float64) for em in range(E) for en in range(E))
+    assert np.abs(ref - parts).max() <= 1e-12 * np.abs(parts).max()
